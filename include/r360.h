@@ -1,0 +1,164 @@
+/* r360.h -- C ABI of the B200 spherical dense-registration path.
+ *
+ * Drop-in boundary for ONE path of EduFdez/rgbd360: RegisterPhotoICP's spherical
+ * photometric + depth registration (include/RegisterPhotoICP.h, "RPI.h" below).
+ * The reference has no FFI layer (RegisterPhotoICP is a header-only C++ class), so each
+ * entry point below names the class method / loop it replaces.  Plain pointers and
+ * sizes only; all pointers are HOST pointers unless the name ends in _dev.
+ * A C++ mirror of the class (same method names) lives in include/RegisterPhotoICP_b200.hpp.
+ *
+ * Threading: one r360_ctx per GPU, not thread-safe per ctx (same contract as the
+ * reference class, which mutates members in every call).
+ * Errors: every call returns 0 on success, a negative R360_E_* code otherwise, and
+ * r360_last_error(ctx) returns text.  There is NO CPU fallback: without a CUDA device
+ * r360_create fails with R360_E_CUDA.
+ */
+#ifndef R360_H
+#define R360_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R360_MAX_LEVELS 8
+
+enum { R360_OK = 0, R360_E_ARG = -1, R360_E_CUDA = -2, R360_E_STATE = -3, R360_E_NOMEM = -4 };
+
+/* costFuncType, RPI.h:195 */
+enum { R360_PHOTO_CONSISTENCY = 0, R360_DEPTH_CONSISTENCY = 1, R360_PHOTO_DEPTH = 2 };
+
+/* per-pair status (the reference prints "ILL-POSED" and returns, RPI.h:4682-4690) */
+enum { R360_PAIR_OK = 0, R360_PAIR_ILL_POSED = 1 };
+
+/* frame roles for r360_set_frames */
+enum { R360_ROLE_SOURCE = 1, R360_ROLE_TARGET = 2, R360_ROLE_BOTH = 3 };
+
+/* Setters of RegisterPhotoICP (RPI.h:224-269) + the constants hard-coded in
+ * alignFrames360 (RPI.h:4589-4596).  r360_default_params() fills the ctor defaults
+ * (RPI.h:201-221). */
+typedef struct r360_params {
+    int32_t n_levels;        /* setNumPyr            (default 4)                        */
+    float   min_depth;       /* setMinDepth          (0.3)                              */
+    float   max_depth;       /* setMaxDepth          (6.0)                              */
+    float   std_photo;       /* setGrayVariance      (6/255; it sets stdDevPhoto)       */
+    float   std_depth;       /* setDepthVariance     (0.2)                              */
+    float   thres_sal_int;   /* thresSaliencyIntensity (0.01)                           */
+    float   thres_sal_depth; /* thresSaliencyDepth     (0.01)                           */
+    int32_t max_iters;       /* maxIters = 10        RPI.h:4593                         */
+    double  tol_residual;    /* 1e-3                 RPI.h:4594                         */
+    double  tol_update;      /* 1e-4                 RPI.h:4595                         */
+    int32_t method;          /* costFuncType; callers use R360_PHOTO_DEPTH              */
+    int32_t occlusion;       /* must be 0 (occlusion variants are out of scope)         */
+    int32_t n_sensors_mask;  /* 8: zero the 2-px sensor-joint gradient columns
+                                (RPI.h:4537-4549) when the target pyramid is built; 0: no mask */
+    int32_t reserved;
+} r360_params;
+
+/* What the getters and public fields of the class expose after alignFrames360
+ * (RPI.h:273-288, 179-189), one record per pair.  POD, fixed size: it is the unit
+ * that is all-gathered across GPUs. */
+typedef struct r360_result {
+    float   pose[16];        /* getOptimalPose(), column-major 4x4 (Eigen layout)       */
+    float   hessian[36];     /* getHessian(): of the LAST calcHessGrad_sphere call      */
+    float   gradient[6];     /* getGradient()                                           */
+    float   sso;             /* SSO = numVisiblePixels / imgSize   RPI.h:3226           */
+    int32_t n_visible;       /* numVisiblePixels of that call                           */
+    double  final_error;     /* `error` (RMS) at the accepted pose of the last level run */
+    double  final_err2;      /* its sum of squared weighted residuals                   */
+    int32_t final_n_valid;   /* its numValidPts                                         */
+    int32_t status;          /* R360_PAIR_*                                             */
+    int32_t iters[R360_MAX_LEVELS];   /* num_iterations[level] (accepted steps)         */
+    int32_t passes[R360_MAX_LEVELS];  /* fused pixel passes executed per level          */
+    int32_t pair_id;         /* index of the pair in the call                           */
+    int32_t reserved;
+} r360_result;
+
+/* Optional per-iteration trace (parity hook): one record per evaluated pose. */
+typedef struct r360_iter_record {
+    double  err2;            /* sum of squared weighted residuals at `pose`            */
+    int32_t n_valid;
+    int32_t n_visible;
+    int32_t level;
+    int32_t it;              /* accepted steps so far when this pose was evaluated      */
+    int32_t accepted;        /* 1: became pose_estim (the initial evaluation counts)    */
+    int32_t used;            /* 1: record holds data                                    */
+    float   pose[16];
+    float   hessian[21];     /* upper triangle, row-major (h11,h12,..,h66)              */
+    float   gradient[6];
+    float   pad;
+} r360_iter_record;
+
+typedef struct r360_ctx r360_ctx;
+
+void r360_default_params(r360_params* p);
+const char* r360_last_error(const r360_ctx* ctx);   /* ctx may be NULL: last create error */
+
+/* Replaces constructing RegisterPhotoICP instances (RPI.h:201) for a whole batch:
+ * `max_frames` frame slots of rows x cols, up to `max_pairs` pairs per call. */
+int r360_create(r360_ctx** ctx, int device, int rows, int cols, int max_frames, int max_pairs,
+                const r360_params* params);
+void r360_destroy(r360_ctx* ctx);
+
+/* setSourceFrame / setTargetFrame (RPI.h:480-516) for frames [first, first+n):
+ * gray conversion, gray / depth pyramids and, for target roles, the gradient pyramids
+ * with the sensor-joint mask.  rgb: n x rows x cols x 3 u8 (channel 0 is taken as R,
+ * as the reference does); depth_mm: n x rows x cols u16 millimetres.
+ * roles: n entries of R360_ROLE_* or NULL (= BOTH). */
+int r360_set_frames(r360_ctx* ctx, int first, int n, const uint8_t* rgb, const uint16_t* depth_mm,
+                    const uint8_t* roles);
+/* Same, inputs already in device memory (the HBM-resident form the throughput metric uses). */
+int r360_set_frames_dev(r360_ctx* ctx, int first, int n, const uint8_t* rgb_dev,
+                        const uint16_t* depth_mm_dev, const uint8_t* roles);
+/* setSourceFrame/setTargetFrame with a CV_32FC1 depth image in metres (RPI.h:316-319). */
+int r360_set_frames_f32(r360_ctx* ctx, int first, int n, const uint8_t* rgb, const float* depth_m,
+                        const uint8_t* roles);
+
+/* alignFrames360(pose_guess, method, occlusion = 0) (RPI.h:4519-4784) for n_pairs
+ * independent (source, target) pairs.  init_pose: n_pairs x 16 floats column-major, or
+ * NULL for Identity.  trace: NULL or n_pairs * n_levels * (max_iters + 2) records. */
+int r360_register_pairs(r360_ctx* ctx, int n_pairs, const int32_t* src_idx, const int32_t* trg_idx,
+                        const float* init_pose, r360_result* out, r360_iter_record* trace);
+
+/* errorPhotoICP_sphere(level, pose, method) (RPI.h:2545-2739): returns the two sums the
+ * RMS is formed from. */
+int r360_eval_error(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
+                    double* err2, int32_t* n_valid);
+/* calcHessGrad_sphere(level, pose, method) (RPI.h:2745-3228): H column-major 6x6. */
+int r360_eval_hessgrad(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
+                       float H[36], float g[6], int32_t* n_visible);
+
+/* Parity hooks (a1-a5 planes, warp index maps).  Any output pointer may be NULL. */
+int r360_dump_level(r360_ctx* ctx, int frame, int level, float* gray, float* depth,
+                    float* gray_gx, float* gray_gy, float* depth_gx, float* depth_gy);
+int r360_dump_warp(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
+                   int32_t* r_idx, int32_t* c_idx, uint8_t* valid_photo, uint8_t* valid_depth);
+
+/* Synthetic sphere frames of SURVEY 8(d) rendered straight into device buffers
+ * (convex box room, procedural texture); frame ids and the scene kind select poses.
+ * kind 0: odometry / batch trajectory, 1: loop-closure keyframes. */
+int r360_synth_frames_dev(r360_ctx* ctx, int kind, int first_id, int n, uint8_t* rgb_dev,
+                          uint16_t* depth_mm_dev);
+int r360_synth_frames(r360_ctx* ctx, int kind, int first_id, int n, uint8_t* rgb, uint16_t* depth_mm);
+/* Ground-truth pose T_trg<-src (column-major 4x4 double) between two synthetic frames. */
+void r360_synth_gt_pose(int kind, int src_id, int trg_id, double T[16]);
+
+/* Device memory / stream plumbing for callers that keep data on the GPU. */
+int r360_device_alloc(r360_ctx* ctx, size_t bytes, void** ptr_dev);
+int r360_device_free(r360_ctx* ctx, void* ptr_dev);
+int r360_synchronize(r360_ctx* ctx);
+/* Milliseconds spent in the last r360_register_pairs / r360_set_frames* call measured with
+ * CUDA events on the ctx stream, and kernels launched by the ctx since creation. */
+float r360_last_device_ms(const r360_ctx* ctx);
+int64_t r360_kernel_launches(const r360_ctx* ctx);
+/* Average device time (ms) and launch count of the fused warp/residual/normal-equation
+ * kernel inside the last r360_register_pairs call, and the algorithmic bytes it moved. */
+int r360_last_pass_stats(const r360_ctx* ctx, float* total_ms, int32_t* launches, double* alg_bytes);
+
+int r360_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R360_H */

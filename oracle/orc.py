@@ -1,0 +1,225 @@
+"""ctypes binding of the CPU oracle (oracle/rpi_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by the product package rgbd360_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "librpi_oracle.so")
+
+R360_MAX_LEVELS = 8
+PHOTO, DEPTH, PHOTO_DEPTH = 0, 1, 2
+MATH_PINNED, MATH_LIBM = 0, 1
+ACC_FAITHFUL, ACC_STABLE = 0, 1
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("n_levels", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float),
+        ("std_photo", C.c_float), ("std_depth", C.c_float), ("thres_sal_int", C.c_float),
+        ("thres_sal_depth", C.c_float), ("max_iters", C.c_int32), ("tol_residual", C.c_double),
+        ("tol_update", C.c_double), ("method", C.c_int32), ("occlusion", C.c_int32),
+        ("n_sensors_mask", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("pose", C.c_float * 16), ("hessian", C.c_float * 36), ("gradient", C.c_float * 6),
+        ("sso", C.c_float), ("n_visible", C.c_int32), ("final_error", C.c_double),
+        ("final_err2", C.c_double), ("final_n_valid", C.c_int32), ("status", C.c_int32),
+        ("iters", C.c_int32 * R360_MAX_LEVELS), ("passes", C.c_int32 * R360_MAX_LEVELS),
+        ("pair_id", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class IterRecord(C.Structure):
+    _fields_ = [
+        ("err2", C.c_double), ("n_valid", C.c_int32), ("n_visible", C.c_int32),
+        ("level", C.c_int32), ("it", C.c_int32), ("accepted", C.c_int32), ("used", C.c_int32),
+        ("pose", C.c_float * 16), ("hessian", C.c_float * 21), ("gradient", C.c_float * 6),
+        ("pad", C.c_float),
+    ]
+
+
+def default_params(n_levels=4, method=PHOTO_DEPTH, std_photo=None, n_sensors_mask=8):
+    """Constructor defaults of RegisterPhotoICP (RPI.h:201-221) + alignFrames360 constants."""
+    p = Params()
+    p.n_levels = n_levels
+    p.min_depth = 0.3
+    p.max_depth = 6.0
+    p.std_photo = np.float32(6.0 / 255) if std_photo is None else np.float32(std_photo)
+    p.std_depth = 0.2
+    p.thres_sal_int = 0.01
+    p.thres_sal_depth = 0.01
+    p.max_iters = 10
+    p.tol_residual = 1e-3
+    p.tol_update = 1e-4
+    p.method = method
+    p.occlusion = 0
+    p.n_sensors_mask = n_sensors_mask
+    return p
+
+
+def build(force=False):
+    """Compile the oracle with oracle/Makefile (g++ only)."""
+    if force or not os.path.exists(_SO) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
+        for f in ("rpi_oracle.cpp", "../rgbd360_b200/csrc/sphere_math.h",
+                  "../rgbd360_b200/csrc/gn_math.h", "../rgbd360_b200/csrc/synth.h", "../include/r360.h")
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.orc_frame_build.restype = C.c_void_p
+        L.orc_frame_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.POINTER(Params), C.c_int]
+        L.orc_frame_free.argtypes = [C.c_void_p]
+        L.orc_frame_level.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        L.orc_lut.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), C.c_void_p]
+        L.orc_error.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params),
+                                C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.orc_hessgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params),
+                                   C.c_int] + [C.c_void_p] * 5
+        L.orc_warp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params)] + [C.c_void_p] * 4
+        L.orc_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_int,
+                                C.POINTER(Result), C.c_void_p, C.c_int]
+        L.orc_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_synth_gt_pose.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_pinned_vec.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_pinned_sincos.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_rank6.argtypes = [C.c_void_p]
+        L.orc_inverse6.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_solve_update.argtypes = [C.c_void_p] * 3
+        L.orc_pseudo_exp.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_mat4_mul.argtypes = [C.c_void_p] * 3
+        _lib = L
+    return _lib
+
+
+def set_math(mode):
+    lib().orc_set_math(int(mode))
+
+
+def omp_threads():
+    return int(lib().orc_omp_threads())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pose_arg(pose):
+    """4x4 (row-major numpy view of a matrix) -> 16 floats column-major (Eigen layout)."""
+    if pose is None:
+        pose = np.eye(4)
+    return np.ascontiguousarray(np.asarray(pose, dtype=np.float32).reshape(4, 4).T).reshape(16)
+
+
+def pose_from(buf):
+    return np.array(buf, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+class Frame:
+    """One side of a pair: what setSourceFrame / setTargetFrame build (RPI.h:480-516)."""
+
+    def __init__(self, rgb, depth, params, with_grad=True):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        self.rows, self.cols = rgb.shape[:2]
+        self.params = params
+        self.with_grad = with_grad
+        if depth.dtype == np.uint16:
+            d = np.ascontiguousarray(depth)
+            self.h = lib().orc_frame_build(_ptr(rgb), _ptr(d), None, self.rows, self.cols, C.byref(params), int(with_grad))
+        else:
+            d = np.ascontiguousarray(depth, dtype=np.float32)
+            self.h = lib().orc_frame_build(_ptr(rgb), None, _ptr(d), self.rows, self.cols, C.byref(params), int(with_grad))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_frame_free(self.h)
+            self.h = None
+
+    def level(self, level):
+        r, c = self.rows >> level, self.cols >> level
+        names = ["gray", "depth"] + (["ggx", "ggy", "dgx", "dgy"] if self.with_grad else [])
+        out = {n: np.zeros((r, c), np.float32) for n in names}
+        args = [_ptr(out[n]) if n in out else None for n in ["gray", "depth", "ggx", "ggy", "dgx", "dgy"]]
+        lib().orc_frame_level(self.h, level, *args)
+        return out
+
+
+def lut(src, level, params):
+    r, c = src.rows >> level, src.cols >> level
+    out = np.zeros((r * c, 3), np.float32)
+    lib().orc_lut(src.h, level, C.byref(params), _ptr(out))
+    return out
+
+
+def error(src, trg, level, pose, params):
+    e2, n = C.c_double(), C.c_int()
+    T = pose_arg(pose)
+    lib().orc_error(src.h, trg.h, level, _ptr(T), C.byref(params), C.byref(e2), C.byref(n))
+    return e2.value, n.value
+
+
+def hessgrad(src, trg, level, pose, params, accum=ACC_STABLE):
+    H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+    Hd = np.zeros(21, np.float64); gd = np.zeros(6, np.float64); cnt = np.zeros(3, np.int32)
+    T = pose_arg(pose)
+    lib().orc_hessgrad(src.h, trg.h, level, _ptr(T), C.byref(params), accum, _ptr(H), _ptr(g), _ptr(Hd), _ptr(gd), _ptr(cnt))
+    return dict(H=H.reshape(6, 6), g=g, Hd=Hd, gd=gd, n_visible=int(cnt[0]), n_photo=int(cnt[1]), n_depth=int(cnt[2]))
+
+
+def warp(src, trg, level, pose, params):
+    n = (src.rows >> level) * (src.cols >> level)
+    ri = np.zeros(n, np.int32); ci = np.zeros(n, np.int32)
+    vp = np.zeros(n, np.uint8); vd = np.zeros(n, np.uint8)
+    T = pose_arg(pose)
+    lib().orc_warp(src.h, trg.h, level, _ptr(T), C.byref(params), _ptr(ri), _ptr(ci), _ptr(vp), _ptr(vd))
+    return ri, ci, vp, vd
+
+
+def align(src, trg, guess, params, accum=ACC_STABLE, trace=False):
+    res = Result()
+    T = pose_arg(guess)
+    cap = params.n_levels * (params.max_iters + 2)
+    tr = (IterRecord * cap)() if trace else None
+    lib().orc_align(src.h, trg.h, _ptr(T), C.byref(params), accum, C.byref(res),
+                    C.cast(tr, C.c_void_p) if trace else None, cap if trace else 0)
+    return (res, tr) if trace else res
+
+
+def synth_frame(kind, fid, rows, cols):
+    rgb = np.zeros((rows, cols, 3), np.uint8)
+    d = np.zeros((rows, cols), np.uint16)
+    lib().orc_synth_frame(kind, fid, rows, cols, _ptr(rgb), _ptr(d))
+    return rgb, d
+
+
+def synth_gt_pose(kind, src_id, trg_id):
+    T = np.zeros(16, np.float64)
+    lib().orc_synth_gt_pose(kind, src_id, trg_id, _ptr(T))
+    return T.reshape(4, 4).T.copy()
+
+
+def pinned_vec(fn, a, b=None):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b if b is not None else np.zeros_like(a), np.float32)
+    out = np.zeros_like(a)
+    lib().orc_pinned_vec(fn, a.size, _ptr(a), _ptr(b), _ptr(out))
+    return out

@@ -1,0 +1,804 @@
+// rpi_oracle.cpp -- CPU restatement of RegisterPhotoICP's spherical dense registration.
+//
+// *** TEST INFRASTRUCTURE ONLY. ***  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.  The product
+// (rgbd360_b200/, include/) never links, imports or calls it.
+//
+// PARITY UNPINNED: the reference (EduFdez/rgbd360) ships no tests, golden vectors or recorded
+// outputs for this path, and it cannot be compiled here (needs Eigen, OpenCV, PCL, MRPT,
+// Boost -- none present, no network).  This file follows the reference source line by line
+// (citations "RPI.h:N" = /root/reference/include/RegisterPhotoICP.h) and restates the
+// un-vendored third-party arithmetic it calls (OpenCV cvtColor/convertTo/pyrDown, Eigen
+// fixed-size products / inverse, MRPT CPose3D::exp and rank()); the OpenCV pieces are
+// cross-checked against python cv2 in tests/test_oracle.py.
+//
+// Two arithmetic modes (orc_set_math):
+//   0 PINNED : asin/atan2/sin/cos come from rgbd360_b200/csrc/sphere_math.h -- the exact
+//              operation sequences the GPU kernels execute (bit-exact index maps).
+//   1 LIBM   : the same code with glibc asinf/atan2f/sinf/cosf/sin/cos, i.e. what a g++/x86-64
+//              build of the reference would call.  The two modes differ ONLY in those calls.
+// Two accumulation modes for calcHessGrad_sphere:
+//   0 FAITHFUL : as the reference -- per-pixel Jacobian rows stored in N x 6 column-major heap
+//                matrices, then two more OpenMP passes with 27 float accumulators
+//                (RPI.h:2761-2767, 3117-3224).  This is the mode timed as "reference CPU path".
+//   1 STABLE   : same per-pixel floats, products accumulated in double in a single pass.
+//
+// Build: see oracle/Makefile (g++ -O3 -fopenmp -ffp-contract=off -mfma).
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <chrono>
+#include "../include/r360.h"
+#include "../rgbd360_b200/csrc/sphere_math.h"
+#include "../rgbd360_b200/csrc/gn_math.h"
+#include "../rgbd360_b200/csrc/synth.h"
+
+#define ORC_INVALID_POINT (-10000.0f)   // RPI.h:40
+
+namespace {
+
+struct MathPinned {
+    static float asin_(float x) { return r360_asinf(x); }
+    static float atan2_(float y, float x) { return r360_atan2f(y, x); }
+    static float sin_(float x) { return r360_sinf(x); }
+    static float cos_(float x) { return r360_cosf(x); }
+    static void sincos_d(double x, double* s, double* c) { r360_sincos(x, s, c); }
+};
+struct MathLibm {
+    static float asin_(float x) { return asinf(x); }
+    static float atan2_(float y, float x) { return atan2f(y, x); }
+    static float sin_(float x) { return sinf(x); }
+    static float cos_(float x) { return cosf(x); }
+    static void sincos_d(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+};
+
+int g_math_mode = 0;
+
+struct Frame {
+    int rows = 0, cols = 0, levels = 0;
+    bool has_grad = false;
+    std::vector<std::vector<float>> gray, depth, ggx, ggy, dgx, dgy;
+};
+
+// ------------------------------------------------------------------ a1: gray conversion
+// cv::cvtColor(CV_RGB2GRAY) on 8UC3 (RPI.h:485,502) -- fixed-point luma, verified bit-exact
+// against cv2 4.13 -- then convertTo(CV_32FC1, 1./255) (RPI.h:486,503) = u8 * (float)(1/255).
+void gray_level0(const uint8_t* rgb, int n, std::vector<float>& out) {
+    out.resize(n);
+    const float scale = (float)(1. / 255);
+    for (int i = 0; i < n; ++i) {
+        int g = (rgb[3 * i] * 9798 + rgb[3 * i + 1] * 19235 + rgb[3 * i + 2] * 3735 + 16384) >> 15;
+        out[i] = (float)g * scale;
+    }
+}
+
+inline int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+// a2: cv::pyrDown (RPI.h:303): separable [1 4 6 4 1], BORDER_REFLECT_101, even samples,
+// dst = (cols/2, rows/2).  Horizontal pass is OpenCV's scalar formula, vertical pass its SSE
+// formula (OpenCV 2.4: (r0+r4) + (r2+r2) + 4*((r1+r3)+r2), then *1/256).
+void pyr_down(const std::vector<float>& src, int rows, int cols, std::vector<float>& dst) {
+    const int h = rows / 2, w = cols / 2;
+    std::vector<float> hbuf((size_t)rows * w);
+#pragma omp parallel for
+    for (int r = 0; r < rows; ++r) {
+        const float* s = &src[(size_t)r * cols];
+        for (int x = 0; x < w; ++x) {
+            int c0 = reflect101(2 * x - 2, cols), c1 = reflect101(2 * x - 1, cols), c2 = 2 * x,
+                c3 = reflect101(2 * x + 1, cols), c4 = reflect101(2 * x + 2, cols);
+            hbuf[(size_t)r * w + x] = s[c2] * 6 + (s[c1] + s[c3]) * 4 + s[c0] + s[c4];
+        }
+    }
+    dst.resize((size_t)h * w);
+#pragma omp parallel for
+    for (int y = 0; y < h; ++y) {
+        const float* r0 = &hbuf[(size_t)reflect101(2 * y - 2, rows) * w];
+        const float* r1 = &hbuf[(size_t)reflect101(2 * y - 1, rows) * w];
+        const float* r2 = &hbuf[(size_t)(2 * y) * w];
+        const float* r3 = &hbuf[(size_t)reflect101(2 * y + 1, rows) * w];
+        const float* r4 = &hbuf[(size_t)reflect101(2 * y + 2, rows) * w];
+        for (int x = 0; x < w; ++x) {
+            float a = (r0[x] + r4[x]) + (r2[x] + r2[x]);
+            float b = ((r1[x] + r3[x]) + r2[x]) * 4.0f;
+            dst[(size_t)y * w + x] = (a + b) * (1.f / 256);
+        }
+    }
+}
+
+// a3: buildPyramidRange level step (RPI.h:322-350): mean of the 2x2 parents inside
+// (minDepth, maxDepth), else 0.
+void range_down(const std::vector<float>& src, int rows, int cols, float minD, float maxD,
+                std::vector<float>& dst) {
+    const int h = rows / 2, w = cols / 2;
+    dst.assign((size_t)h * w, 0.f);
+#pragma omp parallel for
+    for (int r = 0; r < 2 * h; r += 2)
+        for (int c = 0; c < 2 * w; c += 2) {
+            float av = 0.f;
+            unsigned n = 0;
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j) {
+                    float z = src[(size_t)(r + i) * cols + c + j];
+                    if (z > minD && z < maxD) { av += z; ++n; }
+                }
+            if (n > 0) dst[(size_t)(r / 2) * w + c / 2] = av / n;
+        }
+}
+
+// a4: calcGradientXY (RPI.h:365-398).  Serial in the reference; rows are independent, so the
+// OpenMP loop here changes nothing but time.
+void grad_xy(const std::vector<float>& s, int rows, int cols, std::vector<float>& gx,
+             std::vector<float>& gy) {
+    gx.assign((size_t)rows * cols, 0.f);
+    gy.assign((size_t)rows * cols, 0.f);
+#pragma omp parallel for
+    for (int r = 1; r < rows - 1; ++r)
+        for (int c = 1; c < cols - 1; ++c) {
+            const size_t i = (size_t)r * cols + c;
+            const float v = s[i], e = s[i + 1], w = s[i - 1], d = s[i + cols], u = s[i - cols];
+            if ((v > e && v < w) || (v < e && v > w)) gx[i] = 2.f / (1 / (e - v) + 1 / (v - w));
+            if ((v > d && v < u) || (v < d && v > u)) gy[i] = 2.f / (1 / (d - v) + 1 / (v - u));
+        }
+}
+
+// a5: sensor-joint mask (RPI.h:4537-4549): zero columns k*W/8-1 and k*W/8, k = 1..7.
+void joint_mask(std::vector<float>& p, int rows, int cols, int n_sensors) {
+    if (n_sensors <= 1) return;
+    const int ws = cols / n_sensors;
+    for (int k = 1; k < n_sensors; ++k)
+        for (int r = 0; r < rows; ++r) {
+            p[(size_t)r * cols + k * ws - 1] = 0.f;
+            p[(size_t)r * cols + k * ws] = 0.f;
+        }
+}
+
+Frame* build_frame(const uint8_t* rgb, const uint16_t* depth_mm, const float* depth_m, int rows,
+                   int cols, const r360_params* P, int with_grad) {
+    Frame* f = new Frame;
+    f->rows = rows; f->cols = cols; f->levels = P->n_levels; f->has_grad = with_grad != 0;
+    const int L = P->n_levels;
+    f->gray.resize(L); f->depth.resize(L);
+    gray_level0(rgb, rows * cols, f->gray[0]);
+    f->depth[0].resize((size_t)rows * cols);
+    if (depth_mm) {
+        const float scale = (float)0.001;            // convertTo(CV_32FC1, 0.001) RPI.h:317
+        for (int i = 0; i < rows * cols; ++i) f->depth[0][i] = (float)depth_mm[i] * scale;
+    } else {
+        memcpy(f->depth[0].data(), depth_m, sizeof(float) * rows * cols);   // RPI.h:319
+    }
+    for (int l = 1; l < L; ++l) {
+        pyr_down(f->gray[l - 1], rows >> (l - 1), cols >> (l - 1), f->gray[l]);
+        range_down(f->depth[l - 1], rows >> (l - 1), cols >> (l - 1), P->min_depth, P->max_depth,
+                   f->depth[l]);
+    }
+    if (with_grad) {
+        f->ggx.resize(L); f->ggy.resize(L); f->dgx.resize(L); f->dgy.resize(L);
+        for (int l = 0; l < L; ++l) {
+            const int r = rows >> l, c = cols >> l;
+            grad_xy(f->gray[l], r, c, f->ggx[l], f->ggy[l]);     // RPI.h:448
+            grad_xy(f->depth[l], r, c, f->dgx[l], f->dgy[l]);    // RPI.h:450
+            joint_mask(f->ggx[l], r, c, P->n_sensors_mask);
+            joint_mask(f->ggy[l], r, c, P->n_sensors_mask);
+            joint_mask(f->dgx[l], r, c, P->n_sensors_mask);
+            joint_mask(f->dgy[l], r, c, P->n_sensors_mask);
+        }
+    }
+    return f;
+}
+
+// ------------------------------------------------------------------ level constants + LUT (a6)
+struct LevelK {
+    int rows, cols;
+    float res, res_inv, half_rows;
+};
+LevelK level_consts(const Frame* f, int level) {
+    LevelK k;
+    k.rows = f->rows >> level;
+    k.cols = f->cols >> level;
+    k.res = (float)(2 * R360_PI_D / k.cols);          // RPI.h:2553
+    k.res_inv = 1 / k.res;                            // RPI.h:2554
+    k.half_rows = (float)(0.5 * k.rows - 0.5);        // RPI.h:2556
+    return k;
+}
+
+// LUT_xyz_sphere (RPI.h:4553-4587), 3 floats per pixel, x = INVALID_POINT when out of range.
+template <class M>
+void build_lut(const Frame* src, int level, const r360_params* P, std::vector<float>& lut) {
+    const LevelK k = level_consts(src, level);
+    std::vector<float> st(k.cols), ct(k.cols);
+    for (int c = 0; c < k.cols; ++c) {
+        float theta = c * k.res;
+        st[c] = M::sin_(theta);
+        ct[c] = M::cos_(theta);
+    }
+    lut.resize((size_t)3 * k.rows * k.cols);
+    const std::vector<float>& D = src->depth[level];
+#pragma omp parallel for
+    for (int r = 0; r < k.rows; ++r) {
+        float phi = (k.half_rows - r) * k.res;
+        float sp = M::sin_(phi), cp = M::cos_(phi);
+        for (int c = 0; c < k.cols; ++c) {
+            const size_t i = (size_t)r * k.cols + c;
+            float d = D[i];
+            if (P->min_depth < d && d < P->max_depth) {
+                lut[3 * i + 0] = d * sp;
+                lut[3 * i + 1] = -d * cp * st[c];
+                lut[3 * i + 2] = -d * cp * ct[c];
+            } else {
+                lut[3 * i + 0] = ORC_INVALID_POINT;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ per-pixel warp (a8/a9 core)
+struct Warped {
+    float px, py, pz, dist, dinv;
+    int r, c;
+};
+// RPI.h:2672-2680 == 2973-2981.  Eigen 3x3*3x1 coefficient product sums left to right, then
+// + translation; norm() = sqrt(x^2 + (y^2 + z^2)) (Eigen's unrolled redux splits 3 as 1 + 2).
+template <class M>
+inline bool warp_point(const float* T, const float* X, const LevelK& k, Warped& w) {
+    w.px = ((T[0] * X[0] + T[4] * X[1]) + T[8] * X[2]) + T[12];
+    w.py = ((T[1] * X[0] + T[5] * X[1]) + T[9] * X[2]) + T[13];
+    w.pz = ((T[2] * X[0] + T[6] * X[1]) + T[10] * X[2]) + T[14];
+    w.dist = sqrtf(w.px * w.px + (w.py * w.py + w.pz * w.pz));
+    w.dinv = 1.f / w.dist;
+    float phi = M::asin_(w.px * w.dinv);
+    float theta = (float)((double)M::atan2_(w.py, w.pz) + R360_PI_D);
+    w.r = r360_round_to_int(k.half_rows - phi * k.res_inv);
+    w.c = r360_round_to_int(theta * k.res_inv);
+    return (w.r >= 0 && w.r < k.rows) && w.c < k.cols;        // RPI.h:2683 (no c >= 0 test)
+}
+
+// ------------------------------------------------------------------ a8 errorPhotoICP_sphere
+template <class M>
+void error_sphere(const Frame* src, const Frame* trg, int level, const float* T,
+                  const r360_params* P, const std::vector<float>& lut, double* err2_out,
+                  int* nvalid_out) {
+    const LevelK k = level_consts(src, level);
+    const int N = k.rows * k.cols;
+    const double stdDevPhoto_inv = 1. / P->std_photo;          // RPI.h:2561 (double)
+    const float* Is = src->gray[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Dt = trg->depth[level].data();
+    const float* Ix = trg->ggx[level].data();
+    const float* Iy = trg->ggy[level].data();
+    const float* Dx = trg->dgx[level].data();
+    const float* Dy = trg->dgy[level].data();
+    const int method = P->method;
+    double error2 = 0.0;
+    int numValidPts = 0;
+#pragma omp parallel for reduction(+ : error2, numValidPts)
+    for (int i = 0; i < N; ++i) {
+        if (lut[3 * (size_t)i] == ORC_INVALID_POINT) continue;
+        Warped w;
+        if (!warp_point<M>(T, &lut[3 * (size_t)i], k, w)) continue;
+        const size_t j = (size_t)w.r * k.cols + w.c;
+        if (method == R360_PHOTO_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            if (fabsf(Ix[j]) < P->thres_sal_int && fabsf(Iy[j]) < P->thres_sal_int) continue;
+            float photoDiff = It[j] - Is[i];
+            double weight_photo = r360_huber(photoDiff, P->std_photo) * stdDevPhoto_inv;
+            float werr = (float)(weight_photo * photoDiff);
+            error2 += werr * werr;
+            ++numValidPts;
+        }
+        if (method == R360_DEPTH_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            float depth2 = Dt[j];
+            if (std::isfinite(depth2)) {
+                if (fabsf(Dx[j]) < P->thres_sal_depth && fabsf(Dy[j]) < P->thres_sal_depth) continue;
+                float depthDiff = depth2 - w.dist;
+                float sd = P->std_depth * depth2;
+                double weight_depth = r360_huber(depthDiff, sd) / sd;
+                float werr = (float)(weight_depth * depthDiff);
+                error2 += werr * werr;
+                ++numValidPts;
+            }
+        }
+    }
+    *err2_out = error2;
+    *nvalid_out = numValidPts;
+}
+
+// ------------------------------------------------------------------ a9 per-pixel Jacobian rows
+// RPI.h:2991-3088.  Returns bit 0: photo row valid, bit 1: depth row valid.
+inline int jacobian_rows(const Warped& w, const LevelK& k, const r360_params* P, float Is,
+                         float It, float Dt, float Ix, float Iy, float Dx, float Dy,
+                         float stdDevPhoto_inv, float* Jp, float* rp, float* Jd, float* rd) {
+    const int method = P->method;
+    const float x = w.px, y = w.py, z = w.pz;
+    // jacobianProj23
+    float z_inv = 1.f / z;
+    float z_inv2 = z_inv * z_inv;
+    float D_atan = 1.f / (1 + y * y * z_inv2) * k.res_inv;
+    float P01 = D_atan * z_inv;
+    float P02 = -y * z_inv2 * D_atan;
+    float dinv2 = w.dinv * w.dinv;
+    float xd = x * dinv2;
+    float D_asin = 1.f / sqrtf(1 - x * xd) * k.res_inv;
+    float P10 = -D_asin * w.dinv * (1 - x * xd);
+    float P11 = D_asin * (xd * y * w.dinv);
+    float P12 = D_asin * (xd * z * w.dinv);
+    // jacobianWarpRt = jacobianProj23 * [I | -skew(p)], coefficient sums k = 0,1,2 left to right
+    float Jw0[6], Jw1[6];
+    const float P00 = 0.f;
+    Jw0[0] = (P00 * 1 + P01 * 0) + P02 * 0;  Jw0[1] = (P00 * 0 + P01 * 1) + P02 * 0;
+    Jw0[2] = (P00 * 0 + P01 * 0) + P02 * 1;
+    Jw0[3] = (P00 * 0 + P01 * (-z)) + P02 * y;
+    Jw0[4] = (P00 * z + P01 * 0) + P02 * (-x);
+    Jw0[5] = (P00 * (-y) + P01 * x) + P02 * 0;
+    Jw1[0] = (P10 * 1 + P11 * 0) + P12 * 0;  Jw1[1] = (P10 * 0 + P11 * 1) + P12 * 0;
+    Jw1[2] = (P10 * 0 + P11 * 0) + P12 * 1;
+    Jw1[3] = (P10 * 0 + P11 * (-z)) + P12 * y;
+    Jw1[4] = (P10 * z + P11 * 0) + P12 * (-x);
+    Jw1[5] = (P10 * (-y) + P11 * x) + P12 * 0;
+    int valid = 0;
+    if (method == R360_PHOTO_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+        if (fabsf(Ix) < P->thres_sal_int && fabsf(Iy) < P->thres_sal_int) return 0;   // `continue`
+        float photoDiff = It - Is;
+        float weight_photo = r360_huber(photoDiff, P->std_photo) * stdDevPhoto_inv;
+        *rp = weight_photo * photoDiff;
+        float a = weight_photo * Ix, b = weight_photo * Iy;
+        for (int q = 0; q < 6; ++q) Jp[q] = a * Jw0[q] + b * Jw1[q];
+        valid |= 1;
+    }
+    if (method == R360_DEPTH_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+        if (std::isfinite(Dt)) {
+            if (fabsf(Dx) < P->thres_sal_depth && fabsf(Dy) < P->thres_sal_depth) return valid;
+            float depthDiff = Dt - w.dist;
+            float sd = P->std_depth * Dt;
+            float weight_depth = r360_huber(depthDiff, sd) / sd;
+            *rd = weight_depth * depthDiff;
+            const float n0 = x * w.dinv, n1 = y * w.dinv, n2 = z * w.dinv;
+            float nT[6];
+            nT[0] = (n0 * 1 + n1 * 0) + n2 * 0;  nT[1] = (n0 * 0 + n1 * 1) + n2 * 0;
+            nT[2] = (n0 * 0 + n1 * 0) + n2 * 1;
+            nT[3] = (n0 * 0 + n1 * (-z)) + n2 * y;
+            nT[4] = (n0 * z + n1 * 0) + n2 * (-x);
+            nT[5] = (n0 * (-y) + n1 * x) + n2 * 0;
+            for (int q = 0; q < 6; ++q) Jd[q] = weight_depth * ((Dx * Jw0[q] + Dy * Jw1[q]) - nT[q]);
+            valid |= 2;
+        }
+    }
+    return valid;
+}
+
+struct HessOut {
+    float H[36];
+    float g[6];
+    double Hd[21], gd[6];
+    int n_visible;
+    int n_photo, n_depth;
+};
+
+template <class M>
+void hessgrad_sphere(const Frame* src, const Frame* trg, int level, const float* T,
+                     const r360_params* P, const std::vector<float>& lut, int accum_mode,
+                     HessOut* out) {
+    const LevelK k = level_consts(src, level);
+    const int N = k.rows * k.cols;
+    const float stdDevPhoto_inv = (float)(1. / P->std_photo);      // RPI.h:2774 (float)
+    const float* Is = src->gray[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Dt = trg->depth[level].data();
+    const float* Ix = trg->ggx[level].data();
+    const float* Iy = trg->ggy[level].data();
+    const float* Dx = trg->dgx[level].data();
+    const float* Dy = trg->dgy[level].data();
+    int numVisible = 0, nPhoto = 0, nDepth = 0;
+    double acc[27];
+    for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+
+    if (accum_mode == 0) {
+        // FAITHFUL: heap Jacobian store (column-major N x 6), then float reductions.
+        float* JP = (float*)malloc(sizeof(float) * 6 * (size_t)N);       // MatrixXf(imgSize,6), uninitialised
+        float* JD = (float*)malloc(sizeof(float) * 6 * (size_t)N);
+        float* RP = (float*)calloc(N, sizeof(float));
+        float* RD = (float*)calloc(N, sizeof(float));
+        int* VP = (int*)calloc(N, sizeof(int));
+        int* VD = (int*)calloc(N, sizeof(int));
+        float* ZB = (float*)calloc(N, sizeof(float));                    // invDepthBuffer (unused, RPI.h:2767)
+#pragma omp parallel for reduction(+ : numVisible)
+        for (int i = 0; i < N; ++i) {
+            if (lut[3 * (size_t)i] == ORC_INVALID_POINT) continue;
+            Warped w;
+            if (!warp_point<M>(T, &lut[3 * (size_t)i], k, w)) continue;
+            ++numVisible;
+            const size_t j = (size_t)w.r * k.cols + w.c;
+            float Jp[6], Jd[6], rp = 0.f, rd = 0.f;
+            int v = jacobian_rows(w, k, P, Is[i], It[j], Dt[j], Ix[j], Iy[j], Dx[j], Dy[j],
+                                  stdDevPhoto_inv, Jp, &rp, Jd, &rd);
+            if (v & 1) { for (int q = 0; q < 6; ++q) JP[(size_t)q * N + i] = Jp[q]; RP[i] = rp; VP[i] = 1; }
+            if (v & 2) { for (int q = 0; q < 6; ++q) JD[(size_t)q * N + i] = Jd[q]; RD[i] = rd; VD[i] = 1; }
+        }
+        float h11 = 0, h12 = 0, h13 = 0, h14 = 0, h15 = 0, h16 = 0, h22 = 0, h23 = 0, h24 = 0, h25 = 0,
+              h26 = 0, h33 = 0, h34 = 0, h35 = 0, h36 = 0, h44 = 0, h45 = 0, h46 = 0, h55 = 0, h56 = 0,
+              h66 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            const float* J = pass == 0 ? JP : JD;
+            const float* R = pass == 0 ? RP : RD;
+            const int* V = pass == 0 ? VP : VD;
+            const bool on = pass == 0 ? (P->method != R360_DEPTH_CONSISTENCY)
+                                      : (P->method != R360_PHOTO_CONSISTENCY);
+            if (!on) continue;
+            int cnt = 0;
+#pragma omp parallel for reduction(+ : h11, h12, h13, h14, h15, h16, h22, h23, h24, h25, h26, h33, h34, h35, h36, h44, h45, h46, h55, h56, h66, g1, g2, g3, g4, g5, g6, cnt)
+            for (int i = 0; i < N; ++i)
+                if (V[i]) {
+                    const float j0 = J[i], j1 = J[(size_t)N + i], j2 = J[2 * (size_t)N + i],
+                                j3 = J[3 * (size_t)N + i], j4 = J[4 * (size_t)N + i], j5 = J[5 * (size_t)N + i];
+                    const float r = R[i];
+                    h11 += j0 * j0; h12 += j0 * j1; h13 += j0 * j2; h14 += j0 * j3; h15 += j0 * j4; h16 += j0 * j5;
+                    h22 += j1 * j1; h23 += j1 * j2; h24 += j1 * j3; h25 += j1 * j4; h26 += j1 * j5;
+                    h33 += j2 * j2; h34 += j2 * j3; h35 += j2 * j4; h36 += j2 * j5;
+                    h44 += j3 * j3; h45 += j3 * j4; h46 += j3 * j5;
+                    h55 += j4 * j4; h56 += j4 * j5; h66 += j5 * j5;
+                    g1 += j0 * r; g2 += j1 * r; g3 += j2 * r; g4 += j3 * r; g5 += j4 * r; g6 += j5 * r;
+                    ++cnt;
+                }
+            if (pass == 0) nPhoto = cnt; else nDepth = cnt;
+        }
+        const float hv[21] = { h11, h12, h13, h14, h15, h16, h22, h23, h24, h25, h26, h33, h34, h35,
+                               h36, h44, h45, h46, h55, h56, h66 };
+        const float gv[6] = { g1, g2, g3, g4, g5, g6 };
+        for (int q = 0; q < 21; ++q) acc[q] = hv[q];
+        for (int q = 0; q < 6; ++q) acc[21 + q] = gv[q];
+        free(JP); free(JD); free(RP); free(RD); free(VP); free(VD); free(ZB);
+    } else {
+        // STABLE: same per-pixel float rows and float products, double accumulation.
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0, a10 = 0,
+               a11 = 0, a12 = 0, a13 = 0, a14 = 0, a15 = 0, a16 = 0, a17 = 0, a18 = 0, a19 = 0, a20 = 0,
+               b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+#pragma omp parallel for reduction(+ : numVisible, nPhoto, nDepth, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15, a16, a17, a18, a19, a20, b0, b1, b2, b3, b4, b5)
+        for (int i = 0; i < N; ++i) {
+            if (lut[3 * (size_t)i] == ORC_INVALID_POINT) continue;
+            Warped w;
+            if (!warp_point<M>(T, &lut[3 * (size_t)i], k, w)) continue;
+            ++numVisible;
+            const size_t j = (size_t)w.r * k.cols + w.c;
+            float Jp[6], Jd[6], rp = 0.f, rd = 0.f;
+            int v = jacobian_rows(w, k, P, Is[i], It[j], Dt[j], Ix[j], Iy[j], Dx[j], Dy[j],
+                                  stdDevPhoto_inv, Jp, &rp, Jd, &rd);
+            for (int pass = 0; pass < 2; ++pass) {
+                if (!(v & (1 << pass))) continue;
+                const float* J = pass == 0 ? Jp : Jd;
+                const float r = pass == 0 ? rp : rd;
+                if (pass == 0) ++nPhoto; else ++nDepth;
+                a0 += J[0] * J[0]; a1 += J[0] * J[1]; a2 += J[0] * J[2]; a3 += J[0] * J[3]; a4 += J[0] * J[4]; a5 += J[0] * J[5];
+                a6 += J[1] * J[1]; a7 += J[1] * J[2]; a8 += J[1] * J[3]; a9 += J[1] * J[4]; a10 += J[1] * J[5];
+                a11 += J[2] * J[2]; a12 += J[2] * J[3]; a13 += J[2] * J[4]; a14 += J[2] * J[5];
+                a15 += J[3] * J[3]; a16 += J[3] * J[4]; a17 += J[3] * J[5];
+                a18 += J[4] * J[4]; a19 += J[4] * J[5]; a20 += J[5] * J[5];
+                b0 += J[0] * r; b1 += J[1] * r; b2 += J[2] * r; b3 += J[3] * r; b4 += J[4] * r; b5 += J[5] * r;
+            }
+        }
+        const double av[27] = { a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15, a16,
+                                a17, a18, a19, a20, b0, b1, b2, b3, b4, b5 };
+        for (int q = 0; q < 27; ++q) acc[q] = av[q];
+    }
+    // RPI.h:3197-3224: symmetric fill
+    int q = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++q) {
+            out->Hd[q] = acc[q];
+            out->H[a + 6 * b] = out->H[b + 6 * a] = (float)acc[q];
+        }
+    for (int a = 0; a < 6; ++a) { out->gd[a] = acc[21 + a]; out->g[a] = (float)acc[21 + a]; }
+    out->n_visible = numVisible;
+    out->n_photo = nPhoto;
+    out->n_depth = nDepth;
+}
+
+// ------------------------------------------------------------------ a10 alignFrames360
+template <class M>
+int align360(const Frame* src, const Frame* trg, const float* guess, const r360_params* P,
+             int accum_mode, r360_result* out, r360_iter_record* trace, int trace_cap) {
+    memset(out, 0, sizeof(*out));
+    const int L = P->n_levels;
+    const int per_level = P->max_iters + 2;
+    float pose_estim[16], pose_tmp[16];
+    memcpy(pose_estim, guess, sizeof(pose_estim));
+    double error = 0.0, err2 = 0.0;
+    int nvalid = 0;
+    HessOut ho;
+    memset(&ho, 0, sizeof(ho));
+    bool have_hess = false;
+    std::vector<float> lut;
+    auto rec_at = [&](int level, int idx) -> r360_iter_record* {
+        if (!trace) return nullptr;
+        int k = level * per_level + idx;
+        if (idx >= per_level || k >= trace_cap) return nullptr;
+        return &trace[k];
+    };
+    bool ill_posed = false;
+    for (int level = L - 1; level >= 0 && !ill_posed; --level) {
+        build_lut<M>(src, level, P, lut);                                  // RPI.h:4553-4587
+        double lambda = 1e0;                                               // RPI.h:4589
+        const double step = 5;
+        int it = 0;
+        float upd[6] = { 1, 1, 1, 1, 1, 1 };                               // RPI.h:4596
+        error_sphere<M>(src, trg, level, pose_estim, P, lut, &err2, &nvalid);   // RPI.h:4599
+        error = sqrt(err2 / nvalid);
+        out->passes[level] = 1;
+        int ev = 0;
+        r360_iter_record* cur = rec_at(level, ev++);
+        if (cur) {
+            memset(cur, 0, sizeof(*cur));
+            cur->err2 = err2; cur->n_valid = nvalid; cur->level = level; cur->it = 0;
+            cur->accepted = 1; cur->used = 1; memcpy(cur->pose, pose_estim, 64);
+        }
+        double diff_error = error;                                         // RPI.h:4605
+        auto norm6 = [](const float* u) {
+            // Eigen redux of 6 floats: (u0^2 + u1^2 + u2^2) + (u3^2 + u4^2 + u5^2), halves split 1+2
+            float a = u[0] * u[0] + (u[1] * u[1] + u[2] * u[2]);
+            float b = u[3] * u[3] + (u[4] * u[4] + u[5] * u[5]);
+            return sqrtf(a + b);
+        };
+        while (it < P->max_iters && norm6(upd) > P->tol_update && diff_error > P->tol_residual) {
+            hessgrad_sphere<M>(src, trg, level, pose_estim, P, lut, accum_mode, &ho);   // RPI.h:4623
+            have_hess = true;
+            ++out->passes[level];
+            if (cur) {
+                cur->used |= 2; cur->n_visible = ho.n_visible;
+                int q = 0;
+                for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b, ++q) cur->hessian[q] = ho.H[a + 6 * b];
+                for (int a = 0; a < 6; ++a) cur->gradient[a] = ho.g[a];
+            }
+            float Hl[36];
+            const float lam = (float)lambda;
+            for (int q = 0; q < 36; ++q) Hl[q] = ho.H[q];
+            for (int a = 0; a < 6; ++a) Hl[a + 6 * a] = ho.H[a + 6 * a] + lam * ho.H[a + 6 * a];
+            if (r360_rank6(Hl) != 6) {                                     // RPI.h:4682-4690
+                out->status = R360_PAIR_ILL_POSED;
+                ill_posed = true;
+                break;
+            }
+            {
+                float inv[36];
+                r360_inverse6(ho.H, inv);
+                r360_solve_update(inv, ho.g, upd);                          // RPI.h:4693
+                double ud[6], Td[16], A, B;
+                for (int a = 0; a < 6; ++a) ud[a] = (double)upd[a];
+                const double th2 = ud[3] * ud[3] + ud[4] * ud[4] + ud[5] * ud[5];
+                if (r360_rodrigues_small(th2, &A, &B)) {
+                    const double th = sqrt(th2);
+                    double s, c;
+                    M::sincos_d(th, &s, &c);
+                    const double inv_th = 1.0 / th;
+                    A = s * inv_th;
+                    B = (1 - c) * (inv_th * inv_th);
+                }
+                r360_pseudo_exp_AB(ud, A, B, Td);
+                float Tf[16];
+                for (int a = 0; a < 16; ++a) Tf[a] = (float)Td[a];
+                r360_mat4_mul(Tf, pose_estim, pose_tmp);                    // RPI.h:4697
+            }
+            double new_err2; int new_nvalid;
+            error_sphere<M>(src, trg, level, pose_tmp, P, lut, &new_err2, &new_nvalid);   // RPI.h:4705
+            ++out->passes[level];
+            double new_error = sqrt(new_err2 / new_nvalid);
+            diff_error = error - new_error;                                // RPI.h:4711
+            r360_iter_record* nr = rec_at(level, ev++);
+            if (nr) {
+                memset(nr, 0, sizeof(*nr));
+                nr->err2 = new_err2; nr->n_valid = new_nvalid; nr->level = level; nr->it = it;
+                nr->used = 1; memcpy(nr->pose, pose_tmp, 64);
+            }
+            if (diff_error > P->tol_residual) {                            // RPI.h:4715-4722
+                lambda /= step;
+                memcpy(pose_estim, pose_tmp, sizeof(pose_estim));
+                error = new_error; err2 = new_err2; nvalid = new_nvalid;
+                it = it + 1;
+                if (nr) { nr->accepted = 1; nr->it = it; }
+                cur = nr;
+            }
+        }
+        if (!ill_posed) out->iters[level] = it;                            // RPI.h:4772
+    }
+    memcpy(out->pose, pose_estim, sizeof(pose_estim));                     // RPI.h:4783 / 4687
+    if (have_hess) {
+        memcpy(out->hessian, ho.H, sizeof(ho.H));
+        memcpy(out->gradient, ho.g, sizeof(ho.g));
+        out->n_visible = ho.n_visible;
+        // SSO of the last calcHessGrad_sphere call (its level's imgSize), RPI.h:3226
+    }
+    out->final_error = error;
+    out->final_err2 = err2;
+    out->final_n_valid = nvalid;
+    return 0;
+}
+
+// Warp index maps + validity masks at `pose` (what r360_dump_warp returns):
+// r_idx/c_idx = transformed_r_int / transformed_c_int for every source pixel with a valid LUT
+// point (INT_MIN elsewhere); valid_photo / valid_depth = validPixelsPhoto / validPixelsDepth.
+template <class M>
+void warp_dump(const Frame* src, const Frame* trg, int level, const float* T,
+                      const r360_params* P, int32_t* ri, int32_t* ci, uint8_t* vp, uint8_t* vd) {
+    std::vector<float> lut;
+    build_lut<M>(src, level, P, lut);
+    const LevelK k = level_consts(src, level);
+    const int N = k.rows * k.cols;
+    const float inv = (float)(1. / P->std_photo);
+#pragma omp parallel for
+    for (int i = 0; i < N; ++i) {
+        int r = INT_MIN, c = INT_MIN, v = 0;
+        if (lut[3 * (size_t)i] != ORC_INVALID_POINT) {
+            Warped w;
+            bool inb = warp_point<M>(T, &lut[3 * (size_t)i], k, w);
+            r = w.r; c = w.c;
+            if (inb) {
+                const size_t j = (size_t)w.r * k.cols + w.c;
+                float Jp[6], Jd[6], rp, rd;
+                v = jacobian_rows(w, k, P, src->gray[level][i], trg->gray[level][j], trg->depth[level][j],
+                                  trg->ggx[level][j], trg->ggy[level][j], trg->dgx[level][j],
+                                  trg->dgy[level][j], inv, Jp, &rp, Jd, &rd);
+            }
+        }
+        if (ri) ri[i] = r;
+        if (ci) ci[i] = c;
+        if (vp) vp[i] = (uint8_t)(v & 1);
+        if (vd) vd[i] = (uint8_t)((v >> 1) & 1);
+    }
+}
+
+}  // namespace
+
+// ====================================================================== C interface (ctypes)
+extern "C" {
+
+void orc_set_math(int mode) { g_math_mode = mode ? 1 : 0; }
+int orc_get_math(void) { return g_math_mode; }
+
+void* orc_frame_build(const uint8_t* rgb, const uint16_t* depth_mm, const float* depth_m, int rows,
+                      int cols, const r360_params* P, int with_grad) {
+    return build_frame(rgb, depth_mm, depth_m, rows, cols, P, with_grad);
+}
+void orc_frame_free(void* f) { delete (Frame*)f; }
+
+int orc_frame_level(void* fv, int level, float* gray, float* depth, float* ggx, float* ggy,
+                    float* dgx, float* dgy) {
+    Frame* f = (Frame*)fv;
+    if (level < 0 || level >= f->levels) return -1;
+    const size_t n = (size_t)(f->rows >> level) * (f->cols >> level) * sizeof(float);
+    if (gray) memcpy(gray, f->gray[level].data(), n);
+    if (depth) memcpy(depth, f->depth[level].data(), n);
+    if (f->has_grad) {
+        if (ggx) memcpy(ggx, f->ggx[level].data(), n);
+        if (ggy) memcpy(ggy, f->ggy[level].data(), n);
+        if (dgx) memcpy(dgx, f->dgx[level].data(), n);
+        if (dgy) memcpy(dgy, f->dgy[level].data(), n);
+    }
+    return 0;
+}
+
+int orc_lut(void* srcv, int level, const r360_params* P, float* xyz) {
+    std::vector<float> lut;
+    if (g_math_mode) build_lut<MathLibm>((Frame*)srcv, level, P, lut);
+    else build_lut<MathPinned>((Frame*)srcv, level, P, lut);
+    memcpy(xyz, lut.data(), lut.size() * sizeof(float));
+    return 0;
+}
+
+int orc_error(void* srcv, void* trgv, int level, const float* pose, const r360_params* P,
+              double* err2, int* nvalid) {
+    std::vector<float> lut;
+    if (g_math_mode) {
+        build_lut<MathLibm>((Frame*)srcv, level, P, lut);
+        error_sphere<MathLibm>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, err2, nvalid);
+    } else {
+        build_lut<MathPinned>((Frame*)srcv, level, P, lut);
+        error_sphere<MathPinned>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, err2, nvalid);
+    }
+    return 0;
+}
+
+// H: 36 floats column-major, g: 6 floats, Hd/gd: optional double sums (21 upper-tri + 6),
+// counts: optional {n_visible, n_photo_rows, n_depth_rows}.
+int orc_hessgrad(void* srcv, void* trgv, int level, const float* pose, const r360_params* P,
+                 int accum_mode, float* H, float* g, double* Hd, double* gd, int* counts) {
+    std::vector<float> lut;
+    HessOut ho;
+    if (g_math_mode) {
+        build_lut<MathLibm>((Frame*)srcv, level, P, lut);
+        hessgrad_sphere<MathLibm>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, &ho);
+    } else {
+        build_lut<MathPinned>((Frame*)srcv, level, P, lut);
+        hessgrad_sphere<MathPinned>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, &ho);
+    }
+    if (H) memcpy(H, ho.H, sizeof(ho.H));
+    if (g) memcpy(g, ho.g, sizeof(ho.g));
+    if (Hd) memcpy(Hd, ho.Hd, sizeof(ho.Hd));
+    if (gd) memcpy(gd, ho.gd, sizeof(ho.gd));
+    if (counts) { counts[0] = ho.n_visible; counts[1] = ho.n_photo; counts[2] = ho.n_depth; }
+    return 0;
+}
+
+int orc_warp(void* srcv, void* trgv, int level, const float* pose, const r360_params* P, int32_t* ri,
+             int32_t* ci, uint8_t* vp, uint8_t* vd) {
+    if (g_math_mode) warp_dump<MathLibm>((Frame*)srcv, (Frame*)trgv, level, pose, P, ri, ci, vp, vd);
+    else warp_dump<MathPinned>((Frame*)srcv, (Frame*)trgv, level, pose, P, ri, ci, vp, vd);
+    return 0;
+}
+
+int orc_align(void* srcv, void* trgv, const float* guess, const r360_params* P, int accum_mode,
+              r360_result* out, r360_iter_record* trace, int trace_cap) {
+    float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    const float* g0 = guess ? guess : ident;
+    Frame* s = (Frame*)srcv;
+    int rc;
+    if (g_math_mode) rc = align360<MathLibm>(s, (Frame*)trgv, g0, P, accum_mode, out, trace, trace_cap);
+    else rc = align360<MathPinned>(s, (Frame*)trgv, g0, P, accum_mode, out, trace, trace_cap);
+    // SSO = numVisiblePixels / imgSize of the level of the last calcHessGrad_sphere call: the
+    // finest level whose loop body ran.
+    int lvl = -1;
+    for (int l = 0; l < P->n_levels; ++l)
+        if (out->passes[l] > 1) { lvl = l; break; }
+    if (lvl >= 0) out->sso = (float)out->n_visible / (float)((s->rows >> lvl) * (s->cols >> lvl));
+    return rc;
+}
+
+// Synthetic frame (host render of rgbd360_b200/csrc/synth.h).
+void orc_synth_frame(int kind, int id, int rows, int cols, uint8_t* rgb, uint16_t* depth_mm) {
+    double Rd[9], td[3];
+    r360_synth_pose(kind, id, Rd, td);
+    float R[9], t[3];
+    for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
+    for (int i = 0; i < 3; ++i) t[i] = (float)td[i];
+    const float res = (float)(2 * R360_PI_D / cols);
+    const float half_rows = (float)(0.5 * rows - 0.5);
+    std::vector<float> st(cols), ct(cols);
+    for (int c = 0; c < cols; ++c) r360_sincosf(c * res, &st[c], &ct[c]);
+#pragma omp parallel for
+    for (int r = 0; r < rows; ++r) {
+        float sp, cp;
+        r360_sincosf((half_rows - r) * res, &sp, &cp);
+        for (int c = 0; c < cols; ++c) {
+            uint8_t g; uint16_t d;
+            r360_synth_pixel(R, t, sp, cp, st[c], ct[c], &g, &d);
+            const size_t i = (size_t)r * cols + c;
+            rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = g;
+            depth_mm[i] = d;
+        }
+    }
+}
+void orc_synth_gt_pose(int kind, int src_id, int trg_id, double* T) { r360_synth_relpose(kind, src_id, trg_id, T); }
+
+// math hooks for tests/test_sphere_math.py
+float orc_pinned_asinf(float x) { return r360_asinf(x); }
+float orc_pinned_atan2f(float y, float x) { return r360_atan2f(y, x); }
+float orc_pinned_sinf(float x) { return r360_sinf(x); }
+float orc_pinned_cosf(float x) { return r360_cosf(x); }
+void orc_pinned_sincos(double x, double* s, double* c) { r360_sincos(x, s, c); }
+void orc_pinned_vec(int fn, int n, const float* a, const float* b, float* out) {
+    for (int i = 0; i < n; ++i) {
+        switch (fn) {
+            case 0: out[i] = r360_asinf(a[i]); break;
+            case 1: out[i] = r360_atan2f(a[i], b[i]); break;
+            case 2: out[i] = r360_sinf(a[i]); break;
+            case 3: out[i] = r360_cosf(a[i]); break;
+            case 4: out[i] = asinf(a[i]); break;
+            case 5: out[i] = atan2f(a[i], b[i]); break;
+            case 6: out[i] = sinf(a[i]); break;
+            case 7: out[i] = cosf(a[i]); break;
+            case 8: out[i] = (float)r360_round_to_int(a[i]); break;
+            default: out[i] = 0.f;
+        }
+    }
+}
+int orc_rank6(const float* M) { return r360_rank6(M); }
+int orc_inverse6(const float* M, float* inv) { return r360_inverse6(M, inv); }
+void orc_solve_update(const float* inv, const float* g, float* upd) { r360_solve_update(inv, g, upd); }
+void orc_pseudo_exp(const double* v, double* T) { r360_pseudo_exp(v, T); }
+void orc_mat4_mul(const float* A, const float* B, float* C) { r360_mat4_mul(A, B, C); }
+int orc_omp_threads(void);
+}
+
+#include <omp.h>
+extern "C" int orc_omp_threads(void) { return omp_get_max_threads(); }
