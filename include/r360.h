@@ -132,6 +132,8 @@ int r360_eval_hessgrad(r360_ctx* ctx, int src, int trg, int level, const float p
 /* Parity hooks (a1-a5 planes, warp index maps).  Any output pointer may be NULL. */
 int r360_dump_level(r360_ctx* ctx, int frame, int level, float* gray, float* depth,
                     float* gray_gx, float* gray_gy, float* depth_gx, float* depth_gy);
+/* Source-role planes ({depth, gray} pyramid read by the warp) of a frame. */
+int r360_dump_source_level(r360_ctx* ctx, int frame, int level, float* gray, float* depth);
 int r360_dump_warp(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
                    int32_t* r_idx, int32_t* c_idx, uint8_t* valid_photo, uint8_t* valid_depth);
 

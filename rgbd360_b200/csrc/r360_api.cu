@@ -1,0 +1,652 @@
+// r360_api.cu -- host side of the C ABI declared in include/r360.h.
+//
+// Owns device memory, streams and launch order; all arithmetic of the path runs in the kernels
+// of r360_kernels.cu.  There is no CPU fallback: every entry point needs a CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "r360_kernels.h"
+#include "synth.h"
+
+namespace {
+
+std::string g_create_error;
+
+constexpr int kChunkFrames = 16;     // frames per pyramid-build launch / H2D staging buffer
+
+struct Ctx {
+    int device = 0, sm_count = 0, pass_grid = 0;
+    int rows = 0, cols = 0, L = 0, max_frames = 0, max_pairs = 0;
+    r360_params P{};
+    R360Level lv[R360_MAX_LEVELS]{};
+    long long px_total = 0;
+    cudaStream_t st = nullptr, cs = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_copy[2]{}, ev_done[2]{};
+    std::vector<cudaEvent_t> ev_pass;            // pairs of events around each pixel pass
+    float* d_tables = nullptr;
+    // frame slots
+    std::vector<float2*> src;                    // {depth, gray} pyramids
+    std::vector<float*> trg;                     // texel pyramids
+    float2* scratch = nullptr;                   // kChunkFrames source-format pyramids (target-only frames)
+    uint8_t* stage_rgb[2]{};
+    uint16_t* stage_depth[2]{};                  // also holds float depth (sized for it)
+    // pointer tables for the pyramid kernels (pinned host + device)
+    float2** h_pyr = nullptr; float2** d_pyr = nullptr;
+    float2** h_pyr_t = nullptr; float2** d_pyr_t = nullptr;
+    float** h_trg_t = nullptr; float** d_trg_t = nullptr;
+    // pair batch
+    R360Pair* d_pairs = nullptr;
+    double* d_acc = nullptr; int* d_cnt = nullptr;
+    int* d_active = nullptr; int* d_nactive = nullptr;
+    const float2** h_srcb = nullptr; const float2** d_srcb = nullptr;
+    const float** h_trgb = nullptr; const float** d_trgb = nullptr;
+    int32_t* h_idx = nullptr; int32_t* d_idx = nullptr;          // src idx | trg idx
+    float* h_pose = nullptr; float* d_pose = nullptr;
+    r360_result* d_res = nullptr; r360_result* h_res = nullptr;
+    r360_iter_record* d_trace = nullptr; size_t trace_cap = 0;
+    float* d_cams = nullptr; float* h_cams = nullptr;
+    // stats
+    float last_ms = 0.f, pass_ms = 0.f;
+    int pass_launches = 0;
+    double pass_bytes = 0.0;
+    int64_t launches = 0;
+    std::string err;
+};
+
+int fail(Ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(c, call)                                                                           \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail((c), e_ == cudaErrorMemoryAllocation ? R360_E_NOMEM : R360_E_CUDA,    \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure_src(Ctx* c, int slot) {
+    if (!c->src[slot]) CK(c, cudaMalloc(&c->src[slot], sizeof(float2) * c->px_total));
+    return R360_OK;
+}
+int ensure_trg(Ctx* c, int slot) {
+    if (!c->trg[slot]) CK(c, cudaMalloc(&c->trg[slot], sizeof(float) * R360_TEXEL_FLOATS * c->px_total));
+    return R360_OK;
+}
+
+R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint) {
+    R360PassArgs a{};
+    a.lv = c->lv[level];
+    a.params = c->P;
+    a.inv_std_photo = (float)(1. / c->P.std_photo);
+    const long long n = c->lv[level].n;
+    long long want = n * (long long)std::max(n_pairs_hint, 1) / (8LL * c->pass_grid);
+    long long ppi = ((want + 1023) / 1024) * 1024;
+    ppi = std::min<long long>(std::max<long long>(ppi, 2048), 16384);
+    a.px_per_item = (int)ppi;
+    a.items_per_pair = (int)((n + ppi - 1) / ppi);
+    a.n_active = c->d_nactive;
+    a.active_list = c->d_active;
+    a.pairs = c->d_pairs;
+    a.src_base = c->d_srcb;
+    a.trg_base = c->d_trgb;
+    a.acc = c->d_acc;
+    a.cnt = c->d_cnt;
+    return a;
+}
+
+R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace) {
+    R360GnArgs g{};
+    g.params = c->P;
+    g.n_pairs = n_pairs;
+    g.pairs = c->d_pairs;
+    g.acc = c->d_acc;
+    g.cnt = c->d_cnt;
+    g.active_list = c->d_active;
+    g.n_active = c->d_nactive;
+    g.trace = trace;
+    return g;
+}
+
+// Pyramid build of frames [first, first+n) from inputs resident on the device (or staged there).
+int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t* depth_mm_dev,
+                const float* depth_m_dev, const uint8_t* roles, int table_off) {
+    int n_t = 0;
+    for (int k = 0; k < n; ++k) {
+        const int slot = first + k;
+        const int role = roles ? roles[k] : R360_ROLE_BOTH;
+        if (role & R360_ROLE_SOURCE) {
+            int rc = ensure_src(c, slot);
+            if (rc) return rc;
+            c->h_pyr[table_off + k] = c->src[slot];
+        } else {
+            c->h_pyr[table_off + k] = c->scratch + (size_t)k * c->px_total;
+        }
+        if (role & R360_ROLE_TARGET) {
+            int rc = ensure_trg(c, slot);
+            if (rc) return rc;
+            c->h_pyr_t[table_off + n_t] = c->h_pyr[table_off + k];
+            c->h_trg_t[table_off + n_t] = c->trg[slot];
+            ++n_t;
+        }
+    }
+    CK(c, cudaMemcpyAsync(c->d_pyr + table_off, c->h_pyr + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
+    if (n_t) {
+        CK(c, cudaMemcpyAsync(c->d_pyr_t + table_off, c->h_pyr_t + table_off, sizeof(float2*) * n_t, cudaMemcpyHostToDevice, c->st));
+        CK(c, cudaMemcpyAsync(c->d_trg_t + table_off, c->h_trg_t + table_off, sizeof(float*) * n_t, cudaMemcpyHostToDevice, c->st));
+    }
+    r360_launch_level0(c->st, rgb_dev, depth_mm_dev, depth_m_dev, c->d_pyr + table_off, n, c->rows * c->cols, c->sm_count);
+    ++c->launches;
+    for (int l = 1; l < c->L; ++l) {
+        r360_launch_down(c->st, c->d_pyr + table_off, c->lv[l - 1].px_off, c->lv[l].px_off, c->lv[l - 1].rows,
+                         c->lv[l - 1].cols, c->P.min_depth, c->P.max_depth, n, c->sm_count);
+        ++c->launches;
+    }
+    if (n_t)
+        for (int l = 0; l < c->L; ++l) {
+            r360_launch_texel(c->st, c->d_pyr_t + table_off, c->d_trg_t + table_off, c->lv[l].px_off, c->lv[l].rows,
+                              c->lv[l].cols, c->P.n_sensors_mask, n_t, c->sm_count);
+            ++c->launches;
+        }
+    CK(c, cudaGetLastError());
+    return R360_OK;
+}
+
+int set_frames_impl(Ctx* c, int first, int n, const uint8_t* rgb, const void* depth, bool depth_is_f32,
+                    bool on_device, const uint8_t* roles) {
+    if (!c) return R360_E_ARG;
+    if (first < 0 || n < 0 || first + n > c->max_frames || !rgb || !depth)
+        return fail(c, R360_E_ARG, "set_frames: bad range [%d,%d) of %d slots or null input", first, first + n, c->max_frames);
+    if (roles)
+        for (int k = 0; k < n; ++k)
+            if (roles[k] < 1 || roles[k] > 3) return fail(c, R360_E_ARG, "set_frames: role %d of frame %d invalid", roles[k], k);
+    CK(c, cudaSetDevice(c->device));
+    const size_t npx = (size_t)c->rows * c->cols;
+    const size_t dsz = depth_is_f32 ? sizeof(float) : sizeof(uint16_t);
+    CK(c, cudaEventRecord(c->ev_t0, c->st));
+    int chunk_id = 0;
+    for (int off = 0; off < n; off += kChunkFrames, ++chunk_id) {
+        const int m = std::min(kChunkFrames, n - off);
+        const uint8_t* r_dev;
+        const void* d_dev;
+        const int b = chunk_id & 1;
+        if (on_device) {
+            r_dev = rgb + (size_t)off * npx * 3;
+            d_dev = (const uint8_t*)depth + (size_t)off * npx * dsz;
+        } else {
+            // double-buffered staging: copy stream runs ahead of the compute stream
+            if (chunk_id >= 2) CK(c, cudaStreamWaitEvent(c->cs, c->ev_done[b], 0));
+            CK(c, cudaMemcpyAsync(c->stage_rgb[b], rgb + (size_t)off * npx * 3, (size_t)m * npx * 3, cudaMemcpyHostToDevice, c->cs));
+            CK(c, cudaMemcpyAsync(c->stage_depth[b], (const uint8_t*)depth + (size_t)off * npx * dsz, (size_t)m * npx * dsz, cudaMemcpyHostToDevice, c->cs));
+            CK(c, cudaEventRecord(c->ev_copy[b], c->cs));
+            CK(c, cudaStreamWaitEvent(c->st, c->ev_copy[b], 0));
+            r_dev = c->stage_rgb[b];
+            d_dev = c->stage_depth[b];
+        }
+        int rc = build_chunk(c, first + off, m, r_dev, depth_is_f32 ? nullptr : (const uint16_t*)d_dev,
+                             depth_is_f32 ? (const float*)d_dev : nullptr, roles ? roles + off : nullptr, off);
+        if (rc) return rc;
+        if (!on_device) CK(c, cudaEventRecord(c->ev_done[b], c->st));
+    }
+    CK(c, cudaEventRecord(c->ev_t1, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    CK(c, cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1));
+    return R360_OK;
+}
+
+int check_pair(Ctx* c, int src, int trg) {
+    if (src < 0 || src >= c->max_frames || trg < 0 || trg >= c->max_frames)
+        return fail(c, R360_E_ARG, "frame index out of range (src %d, trg %d, %d slots)", src, trg, c->max_frames);
+    if (!c->src[src]) return fail(c, R360_E_STATE, "frame %d has no source pyramid (r360_set_frames with a SOURCE role first)", src);
+    if (!c->trg[trg]) return fail(c, R360_E_STATE, "frame %d has no target pyramid (r360_set_frames with a TARGET role first)", trg);
+    return R360_OK;
+}
+
+// One fused pixel pass over a single pair at `pose` (the eval / dump hooks).
+int eval_setup(Ctx* c, int src, int trg, int level, const float pose[16], R360PassArgs* a) {
+    if (level < 0 || level >= c->L || !pose) return fail(c, R360_E_ARG, "eval: bad level %d or null pose", level);
+    int rc = check_pair(c, src, trg);
+    if (rc) return rc;
+    CK(c, cudaSetDevice(c->device));
+    const int slot = c->max_pairs;          // spare pair slot
+    R360Pair hp;
+    memset(&hp, 0, sizeof(hp));
+    memcpy(hp.pose_eval, pose, 64);
+    memcpy(hp.pose_estim, pose, 64);
+    hp.active = 1;
+    CK(c, cudaMemcpyAsync(c->d_pairs + slot, &hp, sizeof(hp), cudaMemcpyHostToDevice, c->st));
+    const float2* sb = c->src[src];
+    const float* tb = c->trg[trg];
+    CK(c, cudaMemcpyAsync(c->d_srcb + slot, &sb, sizeof(sb), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_trgb + slot, &tb, sizeof(tb), cudaMemcpyHostToDevice, c->st));
+    const int one = 1;
+    CK(c, cudaMemcpyAsync(c->d_active + slot, &slot, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_nactive + 1, &one, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(c->d_acc + (size_t)slot * R360_ACC_DOUBLES, 0, sizeof(double) * R360_ACC_DOUBLES, c->st));
+    CK(c, cudaMemsetAsync(c->d_cnt + (size_t)slot * R360_ACC_INTS, 0, sizeof(int) * R360_ACC_INTS, c->st));
+    CK(c, cudaStreamSynchronize(c->st));    // hp / sb / tb are stack variables
+    *a = pass_args(c, level, 1);
+    a->n_active = c->d_nactive + 1;
+    a->active_list = c->d_active + slot;
+    return R360_OK;
+}
+
+int eval_pass(Ctx* c, int src, int trg, int level, const float pose[16], double acc[R360_ACC_DOUBLES], int cnt[R360_ACC_INTS]) {
+    R360PassArgs a;
+    int rc = eval_setup(c, src, trg, level, pose, &a);
+    if (rc) return rc;
+    r360_launch_pass(c->st, a, c->pass_grid);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    const int slot = c->max_pairs;
+    CK(c, cudaMemcpyAsync(acc, c->d_acc + (size_t)slot * R360_ACC_DOUBLES, sizeof(double) * R360_ACC_DOUBLES, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(cnt, c->d_cnt + (size_t)slot * R360_ACC_INTS, sizeof(int) * R360_ACC_INTS, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    return R360_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+struct r360_ctx : Ctx {};
+
+int r360_version(void) { return 100; }
+
+void r360_default_params(r360_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->n_levels = 4;                       // RPI.h:204
+    p->min_depth = 0.3f;                   // RPI.h:202   (float member = 0.3 double literal)
+    p->max_depth = 6.0f;                   // RPI.h:203
+    p->std_photo = (float)(6. / 255);      // RPI.h:208
+    p->std_depth = (float)0.2;             // RPI.h:211
+    p->thres_sal_int = 0.01f;              // RPI.h:218
+    p->thres_sal_depth = 0.01f;            // RPI.h:219
+    p->max_iters = 10;                     // RPI.h:4593
+    p->tol_residual = 1e-3;                // RPI.h:4594
+    p->tol_update = 1e-4;                  // RPI.h:4595
+    p->method = R360_PHOTO_DEPTH;          // what every caller passes
+    p->occlusion = 0;
+    p->n_sensors_mask = 8;                 // RPI.h:4537
+}
+
+const char* r360_last_error(const r360_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void r360_destroy(r360_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    if (c->cs) cudaStreamSynchronize(c->cs);
+    for (auto p : c->src) if (p) cudaFree(p);
+    for (auto p : c->trg) if (p) cudaFree(p);
+    cudaFree(c->d_tables); cudaFree(c->scratch);
+    for (int b = 0; b < 2; ++b) { cudaFree(c->stage_rgb[b]); cudaFree(c->stage_depth[b]); }
+    cudaFree(c->d_pyr); cudaFree(c->d_pyr_t); cudaFree(c->d_trg_t);
+    cudaFreeHost(c->h_pyr); cudaFreeHost(c->h_pyr_t); cudaFreeHost(c->h_trg_t);
+    cudaFree(c->d_pairs); cudaFree(c->d_acc); cudaFree(c->d_cnt); cudaFree(c->d_active); cudaFree(c->d_nactive);
+    cudaFree(c->d_srcb); cudaFree(c->d_trgb); cudaFreeHost(c->h_srcb); cudaFreeHost(c->h_trgb);
+    cudaFree(c->d_idx); cudaFreeHost(c->h_idx); cudaFree(c->d_pose); cudaFreeHost(c->h_pose);
+    cudaFree(c->d_res); cudaFreeHost(c->h_res); cudaFree(c->d_trace);
+    cudaFree(c->d_cams); cudaFreeHost(c->h_cams);
+    for (auto e : c->ev_pass) cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->cs) cudaStreamDestroy(c->cs);
+    delete c;
+}
+
+static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_frames, int max_pairs, const r360_params* params) {
+    c->device = device; c->rows = rows; c->cols = cols; c->max_frames = max_frames; c->max_pairs = max_pairs;
+    c->P = *params; c->L = params->n_levels;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(c, R360_E_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    CK(c, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(c, cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->pass_grid = c->sm_count * 2;
+    CK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
+    CK(c, cudaEventCreate(&c->ev_t0));
+    CK(c, cudaEventCreate(&c->ev_t1));
+    for (int b = 0; b < 2; ++b) {
+        CK(c, cudaEventCreateWithFlags(&c->ev_copy[b], cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming));
+    }
+    c->ev_pass.resize((size_t)2 * c->L * (params->max_iters + 1));
+    for (auto& ev : c->ev_pass) CK(c, cudaEventCreate(&ev));
+
+    // ---- per-level geometry and trig tables (RPI.h:2553-2556, 4555-4569), host-computed with
+    //      the pinned sin/cos so that they equal the oracle's tables bit for bit.
+    size_t n_tab = 0;
+    long long off = 0;
+    for (int l = 0; l < c->L; ++l) {
+        R360Level& v = c->lv[l];
+        v.rows = rows >> l; v.cols = cols >> l; v.n = v.rows * v.cols;
+        v.div_magic = ((1ULL << 40) + v.cols - 1) / v.cols;
+        v.px_off = off; off += v.n;
+        v.res = (float)(2 * R360_PI_D / v.cols);
+        v.res_inv = 1 / v.res;
+        v.half_rows = (float)(0.5 * v.rows - 0.5);
+        n_tab += 2 * (size_t)(v.rows + v.cols);
+    }
+    c->px_total = off;
+    std::vector<float> tab(n_tab);
+    CK(c, cudaMalloc(&c->d_tables, sizeof(float) * n_tab));
+    size_t t = 0;
+    for (int l = 0; l < c->L; ++l) {
+        R360Level& v = c->lv[l];
+        v.sin_t = c->d_tables + t; v.cos_t = v.sin_t + v.cols; v.sin_p = v.cos_t + v.cols; v.cos_p = v.sin_p + v.rows;
+        for (int k = 0; k < v.cols; ++k) { float th = k * v.res; r360_sincosf(th, &tab[t + k], &tab[t + v.cols + k]); }
+        for (int r = 0; r < v.rows; ++r) { float ph = (v.half_rows - r) * v.res; r360_sincosf(ph, &tab[t + 2 * v.cols + r], &tab[t + 2 * v.cols + v.rows + r]); }
+        t += 2 * (size_t)(v.rows + v.cols);
+    }
+    CK(c, cudaMemcpy(c->d_tables, tab.data(), sizeof(float) * n_tab, cudaMemcpyHostToDevice));
+
+    c->src.assign(max_frames, nullptr);
+    c->trg.assign(max_frames, nullptr);
+    const size_t npx = (size_t)rows * cols;
+    CK(c, cudaMalloc(&c->scratch, sizeof(float2) * c->px_total * kChunkFrames));
+    for (int b = 0; b < 2; ++b) {
+        CK(c, cudaMalloc(&c->stage_rgb[b], npx * 3 * kChunkFrames));
+        CK(c, cudaMalloc(&c->stage_depth[b], npx * sizeof(float) * kChunkFrames));
+    }
+    CK(c, cudaMallocHost(&c->h_pyr, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_pyr, sizeof(void*) * max_frames));
+    CK(c, cudaMallocHost(&c->h_pyr_t, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_pyr_t, sizeof(void*) * max_frames));
+    CK(c, cudaMallocHost(&c->h_trg_t, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_trg_t, sizeof(void*) * max_frames));
+
+    const int np = max_pairs + 1;     // + 1 spare slot for the eval hooks
+    CK(c, cudaMalloc(&c->d_pairs, sizeof(R360Pair) * np));
+    CK(c, cudaMalloc(&c->d_acc, sizeof(double) * R360_ACC_DOUBLES * np));
+    CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * R360_ACC_INTS * np));
+    CK(c, cudaMalloc(&c->d_active, sizeof(int) * np));
+    CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 2));
+    CK(c, cudaMemset(c->d_nactive, 0, sizeof(int) * 2));
+    CK(c, cudaMallocHost(&c->h_srcb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_srcb, sizeof(void*) * np));
+    CK(c, cudaMallocHost(&c->h_trgb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_trgb, sizeof(void*) * np));
+    CK(c, cudaMallocHost(&c->h_idx, sizeof(int32_t) * 2 * np)); CK(c, cudaMalloc(&c->d_idx, sizeof(int32_t) * 2 * np));
+    CK(c, cudaMallocHost(&c->h_pose, sizeof(float) * 16 * np)); CK(c, cudaMalloc(&c->d_pose, sizeof(float) * 16 * np));
+    CK(c, cudaMalloc(&c->d_res, sizeof(r360_result) * np)); CK(c, cudaMallocHost(&c->h_res, sizeof(r360_result) * np));
+    CK(c, cudaMalloc(&c->d_cams, sizeof(float) * 12 * kChunkFrames)); CK(c, cudaMallocHost(&c->h_cams, sizeof(float) * 12 * kChunkFrames));
+    return R360_OK;
+}
+
+int r360_create(r360_ctx** out, int device, int rows, int cols, int max_frames, int max_pairs, const r360_params* params) {
+    if (!out) return fail(nullptr, R360_E_ARG, "r360_create: null ctx pointer");
+    *out = nullptr;
+    r360_params def;
+    if (!params) { r360_default_params(&def); params = &def; }
+    if (rows <= 0 || cols <= 0 || max_frames <= 0 || max_pairs <= 0)
+        return fail(nullptr, R360_E_ARG, "r360_create: rows/cols/max_frames/max_pairs must be positive");
+    if (params->n_levels < 1 || params->n_levels > R360_MAX_LEVELS)
+        return fail(nullptr, R360_E_ARG, "r360_create: n_levels %d not in [1,%d]", params->n_levels, R360_MAX_LEVELS);
+    if ((rows % (1 << (params->n_levels - 1))) || (cols % (1 << (params->n_levels - 1))))
+        return fail(nullptr, R360_E_ARG, "r360_create: %dx%d is not divisible by 2^(n_levels-1)", cols, rows);
+    if (params->occlusion != 0)
+        return fail(nullptr, R360_E_ARG, "r360_create: occlusion variants 1/2 (RPI.h:3232-4249) are not built; use 0");
+    if (params->method < 0 || params->method > 2) return fail(nullptr, R360_E_ARG, "r360_create: bad method %d", params->method);
+    if (params->max_iters < 1 || params->max_iters > 64) return fail(nullptr, R360_E_ARG, "r360_create: max_iters %d not in [1,64]", params->max_iters);
+    if ((long long)rows * cols >= (1LL << 27)) return fail(nullptr, R360_E_ARG, "r360_create: image too large");
+    r360_ctx* c = new r360_ctx;
+    int rc = create_impl(c, device, rows, cols, max_frames, max_pairs, params);
+    if (rc) { g_create_error = c->err; r360_destroy(c); return rc; }
+    *out = c;
+    return R360_OK;
+}
+
+int r360_set_frames(r360_ctx* c, int first, int n, const uint8_t* rgb, const uint16_t* depth_mm, const uint8_t* roles) {
+    return set_frames_impl(c, first, n, rgb, depth_mm, false, false, roles);
+}
+int r360_set_frames_dev(r360_ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t* depth_mm_dev, const uint8_t* roles) {
+    return set_frames_impl(c, first, n, rgb_dev, depth_mm_dev, false, true, roles);
+}
+int r360_set_frames_f32(r360_ctx* c, int first, int n, const uint8_t* rgb, const float* depth_m, const uint8_t* roles) {
+    return set_frames_impl(c, first, n, rgb, depth_m, true, false, roles);
+}
+
+int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const int32_t* trg_idx, const float* init_pose,
+                        r360_result* out, r360_iter_record* trace) {
+    if (!c) return R360_E_ARG;
+    if (n_pairs < 0 || n_pairs > c->max_pairs || !src_idx || !trg_idx || !out)
+        return fail(c, R360_E_ARG, "register_pairs: n_pairs %d not in [0,%d] or null argument", n_pairs, c->max_pairs);
+    if (n_pairs == 0) return R360_OK;
+    CK(c, cudaSetDevice(c->device));
+    for (int p = 0; p < n_pairs; ++p) {
+        int rc = check_pair(c, src_idx[p], trg_idx[p]);
+        if (rc) return rc;
+        c->h_srcb[p] = c->src[src_idx[p]];
+        c->h_trgb[p] = c->trg[trg_idx[p]];
+        c->h_idx[p] = src_idx[p];
+        c->h_idx[n_pairs + p] = trg_idx[p];
+    }
+    const int per_level = c->P.max_iters + 2;
+    const size_t n_rec = (size_t)n_pairs * c->L * per_level;
+    if (trace && c->trace_cap < n_rec) {
+        if (c->d_trace) cudaFree(c->d_trace);
+        c->d_trace = nullptr; c->trace_cap = 0;
+        CK(c, cudaMalloc(&c->d_trace, sizeof(r360_iter_record) * n_rec));
+        c->trace_cap = n_rec;
+    }
+    CK(c, cudaEventRecord(c->ev_t0, c->st));
+    CK(c, cudaMemcpyAsync(c->d_srcb, c->h_srcb, sizeof(void*) * n_pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_trgb, c->h_trgb, sizeof(void*) * n_pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_idx, c->h_idx, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyHostToDevice, c->st));
+    if (init_pose) {
+        memcpy(c->h_pose, init_pose, sizeof(float) * 16 * n_pairs);
+        CK(c, cudaMemcpyAsync(c->d_pose, c->h_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyHostToDevice, c->st));
+    }
+    if (trace) CK(c, cudaMemsetAsync(c->d_trace, 0, sizeof(r360_iter_record) * n_rec, c->st));
+    R360GnArgs g = gn_args(c, n_pairs, trace ? c->d_trace : nullptr);
+    r360_launch_pairs_init(c->st, g, c->d_idx, c->d_idx + n_pairs, init_pose ? c->d_pose : nullptr);
+    ++c->launches;
+    int n_ev = 0;
+    for (int level = c->L - 1; level >= 0; --level) {                 // RPI.h:4531
+        r360_launch_level_begin(c->st, g, level);
+        c->launches += 2;
+        R360PassArgs a = pass_args(c, level, n_pairs);
+        for (int k = 0; k <= c->P.max_iters; ++k) {                   // 1 initial + <= max_iters loop bodies
+            CK(c, cudaEventRecord(c->ev_pass[n_ev++], c->st));
+            r360_launch_pass(c->st, a, c->pass_grid);
+            CK(c, cudaEventRecord(c->ev_pass[n_ev++], c->st));
+            r360_launch_gn_step(c->st, g, level);
+            c->launches += 3;
+        }
+    }
+    r360_launch_finalize(c->st, g, c->d_res, c->rows, c->cols);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(c->h_res, c->d_res, sizeof(r360_result) * n_pairs, cudaMemcpyDeviceToHost, c->st));
+    if (trace) CK(c, cudaMemcpyAsync(trace, c->d_trace, sizeof(r360_iter_record) * n_rec, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaEventRecord(c->ev_t1, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    memcpy(out, c->h_res, sizeof(r360_result) * n_pairs);
+    CK(c, cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1));
+    // pass statistics: device time of the fused kernel and the algorithmic bytes it moved
+    // (32 B per source pixel per executed pass)
+    c->pass_ms = 0.f; c->pass_launches = n_ev / 2; c->pass_bytes = 0.0;
+    for (int k = 0; k < n_ev; k += 2) {
+        float ms = 0.f;
+        CK(c, cudaEventElapsedTime(&ms, c->ev_pass[k], c->ev_pass[k + 1]));
+        c->pass_ms += ms;
+    }
+    for (int p = 0; p < n_pairs; ++p)
+        for (int l = 0; l < c->L; ++l) c->pass_bytes += 32.0 * (double)c->lv[l].n * out[p].passes[l];
+    return R360_OK;
+}
+
+int r360_eval_error(r360_ctx* c, int src, int trg, int level, const float pose[16], double* err2, int32_t* n_valid) {
+    if (!c) return R360_E_ARG;
+    double acc[R360_ACC_DOUBLES]; int cnt[R360_ACC_INTS];
+    int rc = eval_pass(c, src, trg, level, pose, acc, cnt);
+    if (rc) return rc;
+    if (err2) *err2 = acc[27];
+    if (n_valid) *n_valid = cnt[1] + cnt[2];
+    return R360_OK;
+}
+
+int r360_eval_hessgrad(r360_ctx* c, int src, int trg, int level, const float pose[16], float H[36], float g[6], int32_t* n_visible) {
+    if (!c) return R360_E_ARG;
+    double acc[R360_ACC_DOUBLES]; int cnt[R360_ACC_INTS];
+    int rc = eval_pass(c, src, trg, level, pose, acc, cnt);
+    if (rc) return rc;
+    if (H) {
+        int q = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b, ++q) H[a + 6 * b] = H[b + 6 * a] = (float)acc[q];
+    }
+    if (g) for (int a = 0; a < 6; ++a) g[a] = (float)acc[21 + a];
+    if (n_visible) *n_visible = cnt[0];
+    return R360_OK;
+}
+
+int r360_dump_level(r360_ctx* c, int frame, int level, float* gray, float* depth, float* ggx, float* ggy, float* dgx, float* dgy) {
+    if (!c) return R360_E_ARG;
+    if (frame < 0 || frame >= c->max_frames || level < 0 || level >= c->L) return fail(c, R360_E_ARG, "dump_level: bad frame %d / level %d", frame, level);
+    CK(c, cudaSetDevice(c->device));
+    const R360Level& v = c->lv[level];
+    const bool want_grad = ggx || ggy || dgx || dgy;
+    if (want_grad && !c->trg[frame]) return fail(c, R360_E_STATE, "dump_level: frame %d has no target pyramid", frame);
+    if (c->trg[frame]) {
+        std::vector<float> buf((size_t)v.n * R360_TEXEL_FLOATS);
+        CK(c, cudaMemcpy(buf.data(), c->trg[frame] + v.px_off * R360_TEXEL_FLOATS, buf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < v.n; ++i) {
+            const float* t = &buf[(size_t)i * R360_TEXEL_FLOATS];
+            if (gray) gray[i] = t[0];
+            if (depth) depth[i] = t[1];
+            if (ggx) ggx[i] = t[2];
+            if (ggy) ggy[i] = t[3];
+            if (dgx) dgx[i] = t[4];
+            if (dgy) dgy[i] = t[5];
+        }
+    } else if (c->src[frame]) {
+        std::vector<float2> buf(v.n);
+        CK(c, cudaMemcpy(buf.data(), c->src[frame] + v.px_off, buf.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < v.n; ++i) { if (depth) depth[i] = buf[i].x; if (gray) gray[i] = buf[i].y; }
+    } else {
+        return fail(c, R360_E_STATE, "dump_level: frame %d was never set", frame);
+    }
+    return R360_OK;
+}
+
+// Source-role planes of a frame (the {depth, gray} pyramid the warp reads).
+int r360_dump_source_level(r360_ctx* c, int frame, int level, float* gray, float* depth) {
+    if (!c) return R360_E_ARG;
+    if (frame < 0 || frame >= c->max_frames || level < 0 || level >= c->L) return fail(c, R360_E_ARG, "dump_source_level: bad frame/level");
+    if (!c->src[frame]) return fail(c, R360_E_STATE, "dump_source_level: frame %d has no source pyramid", frame);
+    CK(c, cudaSetDevice(c->device));
+    const R360Level& v = c->lv[level];
+    std::vector<float2> buf(v.n);
+    CK(c, cudaMemcpy(buf.data(), c->src[frame] + v.px_off, buf.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < v.n; ++i) { if (depth) depth[i] = buf[i].x; if (gray) gray[i] = buf[i].y; }
+    return R360_OK;
+}
+
+int r360_dump_warp(r360_ctx* c, int src, int trg, int level, const float pose[16], int32_t* r_idx, int32_t* c_idx,
+                   uint8_t* valid_photo, uint8_t* valid_depth) {
+    if (!c) return R360_E_ARG;
+    R360PassArgs a;
+    int rc = eval_setup(c, src, trg, level, pose, &a);
+    if (rc) return rc;
+    const int n = c->lv[level].n;
+    int32_t* d_r = nullptr; int32_t* d_c = nullptr; uint8_t* d_vp = nullptr; uint8_t* d_vd = nullptr;
+    CK(c, cudaMalloc(&d_r, sizeof(int32_t) * n)); CK(c, cudaMalloc(&d_c, sizeof(int32_t) * n));
+    CK(c, cudaMalloc(&d_vp, n)); CK(c, cudaMalloc(&d_vd, n));
+    r360_launch_warp_dump(c->st, a, c->max_pairs, d_r, d_c, d_vp, d_vd, c->sm_count);
+    ++c->launches;
+    cudaError_t e = cudaStreamSynchronize(c->st);
+    if (e == cudaSuccess && r_idx) e = cudaMemcpy(r_idx, d_r, sizeof(int32_t) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && c_idx) e = cudaMemcpy(c_idx, d_c, sizeof(int32_t) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && valid_photo) e = cudaMemcpy(valid_photo, d_vp, n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && valid_depth) e = cudaMemcpy(valid_depth, d_vd, n, cudaMemcpyDeviceToHost);
+    cudaFree(d_r); cudaFree(d_c); cudaFree(d_vp); cudaFree(d_vd);
+    if (e != cudaSuccess) return fail(c, R360_E_CUDA, "dump_warp: %s", cudaGetErrorString(e));
+    return R360_OK;
+}
+
+int r360_synth_frames_dev(r360_ctx* c, int kind, int first_id, int n, uint8_t* rgb_dev, uint16_t* depth_mm_dev) {
+    if (!c) return R360_E_ARG;
+    if (n < 0 || !rgb_dev || !depth_mm_dev || kind < 0 || kind > 1) return fail(c, R360_E_ARG, "synth_frames: bad arguments");
+    CK(c, cudaSetDevice(c->device));
+    const size_t npx = (size_t)c->rows * c->cols;
+    for (int off = 0; off < n; off += kChunkFrames) {
+        const int m = std::min(kChunkFrames, n - off);
+        CK(c, cudaStreamSynchronize(c->st));       // h_cams reuse
+        for (int k = 0; k < m; ++k) {
+            double R[9], t[3];
+            r360_synth_pose(kind, first_id + off + k, R, t);
+            for (int q = 0; q < 9; ++q) c->h_cams[12 * k + q] = (float)R[q];
+            for (int q = 0; q < 3; ++q) c->h_cams[12 * k + 9 + q] = (float)t[q];
+        }
+        CK(c, cudaMemcpyAsync(c->d_cams, c->h_cams, sizeof(float) * 12 * m, cudaMemcpyHostToDevice, c->st));
+        r360_launch_synth(c->st, kind, first_id + off, c->rows, c->cols, c->d_cams, m, rgb_dev + (size_t)off * npx * 3,
+                          depth_mm_dev + (size_t)off * npx, c->sm_count);
+        ++c->launches;
+    }
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->st));
+    return R360_OK;
+}
+
+int r360_synth_frames(r360_ctx* c, int kind, int first_id, int n, uint8_t* rgb, uint16_t* depth_mm) {
+    if (!c) return R360_E_ARG;
+    if (n < 0 || !rgb || !depth_mm) return fail(c, R360_E_ARG, "synth_frames: bad arguments");
+    const size_t npx = (size_t)c->rows * c->cols;
+    for (int off = 0; off < n; off += kChunkFrames) {
+        const int m = std::min(kChunkFrames, n - off);
+        int rc = r360_synth_frames_dev(c, kind, first_id + off, m, c->stage_rgb[0], c->stage_depth[0]);
+        if (rc) return rc;
+        CK(c, cudaMemcpy(rgb + (size_t)off * npx * 3, c->stage_rgb[0], (size_t)m * npx * 3, cudaMemcpyDeviceToHost));
+        CK(c, cudaMemcpy(depth_mm + (size_t)off * npx, c->stage_depth[0], (size_t)m * npx * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    }
+    return R360_OK;
+}
+
+void r360_synth_gt_pose(int kind, int src_id, int trg_id, double T[16]) { r360_synth_relpose(kind, src_id, trg_id, T); }
+
+int r360_device_alloc(r360_ctx* c, size_t bytes, void** ptr_dev) {
+    if (!c || !ptr_dev) return R360_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMalloc(ptr_dev, bytes));
+    return R360_OK;
+}
+int r360_device_free(r360_ctx* c, void* ptr_dev) {
+    if (!c) return R360_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaFree(ptr_dev));
+    return R360_OK;
+}
+int r360_synchronize(r360_ctx* c) {
+    if (!c) return R360_E_ARG;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->cs));
+    CK(c, cudaStreamSynchronize(c->st));
+    return R360_OK;
+}
+float r360_last_device_ms(const r360_ctx* c) { return c ? c->last_ms : 0.f; }
+int64_t r360_kernel_launches(const r360_ctx* c) { return c ? c->launches : 0; }
+int r360_last_pass_stats(const r360_ctx* c, float* total_ms, int32_t* launches, double* alg_bytes) {
+    if (!c) return R360_E_ARG;
+    if (total_ms) *total_ms = c->pass_ms;
+    if (launches) *launches = c->pass_launches;
+    if (alg_bytes) *alg_bytes = c->pass_bytes;
+    return R360_OK;
+}
+
+}  // extern "C"

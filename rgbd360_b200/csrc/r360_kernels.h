@@ -1,0 +1,47 @@
+// r360_kernels.h -- launch interface between the host API (r360_api.cu) and the kernels.
+#pragma once
+#include "r360_device.cuh"
+
+#define R360_PASS_THREADS 256
+
+struct R360PassArgs {
+    R360Level lv;
+    r360_params params;
+    float inv_std_photo;                // (float)(1./stdDevPhoto), RPI.h:2774
+    int items_per_pair, px_per_item;
+    const int* n_active;                // device
+    const int* active_list;             // device
+    const R360Pair* pairs;              // device
+    const float2* const* src_base;      // device: per pair, source pyramid {depth, gray}
+    const float* const* trg_base;       // device: per pair, target texel pyramid
+    double* acc;                        // device: per pair R360_ACC_DOUBLES
+    int* cnt;                           // device: per pair R360_ACC_INTS
+};
+
+struct R360GnArgs {
+    r360_params params;
+    int n_pairs;
+    R360Pair* pairs;
+    double* acc;
+    int* cnt;
+    int* active_list;
+    int* n_active;
+    r360_iter_record* trace;            // device or nullptr
+};
+
+void r360_launch_level0(cudaStream_t st, const uint8_t* rgb, const uint16_t* depth_mm, const float* depth_m,
+                        float2* const* dst, int n_frames, int n_px, int sm_count);
+void r360_launch_down(cudaStream_t st, float2* const* pyr, long long off_src, long long off_dst, int rows,
+                      int cols, float min_d, float max_d, int n_frames, int sm_count);
+void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, long long off, int rows, int cols,
+                       int n_sensors, int n_frames, int sm_count);
+void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid);
+void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
+                           uint8_t* vp, uint8_t* vd, int sm_count);
+void r360_launch_pairs_init(cudaStream_t st, const R360GnArgs& g, const int32_t* src_idx, const int32_t* trg_idx,
+                            const float* init_pose);
+void r360_launch_level_begin(cudaStream_t st, const R360GnArgs& g, int level);
+void r360_launch_gn_step(cudaStream_t st, const R360GnArgs& g, int level);
+void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols);
+void r360_launch_synth(cudaStream_t st, int kind, int first_id, int rows, int cols, const float* cams, int n_frames,
+                       uint8_t* rgb, uint16_t* depth_mm, int sm_count);

@@ -1,0 +1,269 @@
+"""ctypes loader + thin object wrapper over include/r360.h (one Context per GPU)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "librgbd360_b200.so")
+
+R360_MAX_LEVELS = 8
+PHOTO_CONSISTENCY, DEPTH_CONSISTENCY, PHOTO_DEPTH = 0, 1, 2
+ROLE_SOURCE, ROLE_TARGET, ROLE_BOTH = 1, 2, 3
+
+EXPORTS = [
+    "r360_default_params", "r360_last_error", "r360_create", "r360_destroy", "r360_set_frames",
+    "r360_set_frames_dev", "r360_set_frames_f32", "r360_register_pairs", "r360_eval_error",
+    "r360_eval_hessgrad", "r360_dump_level", "r360_dump_source_level", "r360_dump_warp",
+    "r360_synth_frames_dev", "r360_synth_frames", "r360_synth_gt_pose", "r360_device_alloc",
+    "r360_device_free", "r360_synchronize", "r360_last_device_ms", "r360_kernel_launches",
+    "r360_last_pass_stats", "r360_version",
+]
+
+
+class R360Error(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("n_levels", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float),
+        ("std_photo", C.c_float), ("std_depth", C.c_float), ("thres_sal_int", C.c_float),
+        ("thres_sal_depth", C.c_float), ("max_iters", C.c_int32), ("tol_residual", C.c_double),
+        ("tol_update", C.c_double), ("method", C.c_int32), ("occlusion", C.c_int32),
+        ("n_sensors_mask", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("pose", C.c_float * 16), ("hessian", C.c_float * 36), ("gradient", C.c_float * 6),
+        ("sso", C.c_float), ("n_visible", C.c_int32), ("final_error", C.c_double),
+        ("final_err2", C.c_double), ("final_n_valid", C.c_int32), ("status", C.c_int32),
+        ("iters", C.c_int32 * R360_MAX_LEVELS), ("passes", C.c_int32 * R360_MAX_LEVELS),
+        ("pair_id", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class IterRecord(C.Structure):
+    _fields_ = [
+        ("err2", C.c_double), ("n_valid", C.c_int32), ("n_visible", C.c_int32),
+        ("level", C.c_int32), ("it", C.c_int32), ("accepted", C.c_int32), ("used", C.c_int32),
+        ("pose", C.c_float * 16), ("hessian", C.c_float * 21), ("gradient", C.c_float * 6),
+        ("pad", C.c_float),
+    ]
+
+
+RESULT_DTYPE = np.dtype([
+    ("pose", np.float32, 16), ("hessian", np.float32, 36), ("gradient", np.float32, 6),
+    ("sso", np.float32), ("n_visible", np.int32), ("final_error", np.float64),
+    ("final_err2", np.float64), ("final_n_valid", np.int32), ("status", np.int32),
+    ("iters", np.int32, R360_MAX_LEVELS), ("passes", np.int32, R360_MAX_LEVELS),
+    ("pair_id", np.int32), ("reserved", np.int32)])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+
+def build_native(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout, out.stderr)
+    if out.returncode:
+        raise R360Error("building librgbd360_b200.so failed")
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    """Load librgbd360_b200.so; fails loudly when the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise R360Error(f"{_SO} not found: build it with __graft_entry__.build() "
+                        "(there is no CPU fallback for this path)")
+    L = C.CDLL(_SO)
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    L.r360_default_params.argtypes = [C.POINTER(Params)]
+    L.r360_last_error.restype = C.c_char_p
+    L.r360_last_error.argtypes = [vp]
+    L.r360_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, C.POINTER(Params)]
+    L.r360_destroy.argtypes = [vp]
+    L.r360_destroy.restype = None
+    L.r360_set_frames.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.r360_set_frames_dev.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.r360_set_frames_f32.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.r360_register_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.r360_eval_error.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    L.r360_eval_hessgrad.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.POINTER(C.c_int32)]
+    L.r360_dump_level.argtypes = [vp, i32, i32] + [vp] * 6
+    L.r360_dump_source_level.argtypes = [vp, i32, i32, vp, vp]
+    L.r360_dump_warp.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.r360_synth_frames_dev.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.r360_synth_frames.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.r360_synth_gt_pose.argtypes = [i32, i32, i32, vp]
+    L.r360_synth_gt_pose.restype = None
+    L.r360_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.r360_device_free.argtypes = [vp, vp]
+    L.r360_synchronize.argtypes = [vp]
+    L.r360_last_device_ms.argtypes = [vp]
+    L.r360_last_device_ms.restype = f32
+    L.r360_kernel_launches.argtypes = [vp]
+    L.r360_kernel_launches.restype = C.c_int64
+    L.r360_last_pass_stats.argtypes = [vp, C.POINTER(f32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def default_params(**kw):
+    p = Params()
+    lib().r360_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def pose_to_colmajor(pose):
+    """4x4 matrix -> 16 floats column-major (Eigen::Matrix4f layout)."""
+    return np.ascontiguousarray(np.asarray(pose, np.float32).reshape(4, 4).T).reshape(16)
+
+
+def pose_from_colmajor(buf):
+    return np.array(buf, np.float32).reshape(4, 4).T.copy()
+
+
+def synth_gt_pose(kind, src_id, trg_id):
+    T = np.zeros(16, np.float64)
+    lib().r360_synth_gt_pose(kind, src_id, trg_id, T.ctypes.data_as(C.c_void_p))
+    return T.reshape(4, 4).T.copy()
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One r360_ctx: frame slots + pair batch on one GPU."""
+
+    def __init__(self, rows, cols, max_frames, max_pairs, params=None, device=0):
+        self.L = lib()
+        self.params = params if params is not None else default_params()
+        self.rows, self.cols = rows, cols
+        self.max_frames, self.max_pairs = max_frames, max_pairs
+        self.h = C.c_void_p()
+        rc = self.L.r360_create(C.byref(self.h), device, rows, cols, max_frames, max_pairs, C.byref(self.params))
+        if rc:
+            raise R360Error(f"r360_create failed ({rc}): {self.L.r360_last_error(None).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.L.r360_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise R360Error(f"r360 error {rc}: {self.L.r360_last_error(self.h).decode()}")
+
+    # ---- frames
+    def set_frames(self, first, rgb, depth, roles=None):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        n = rgb.shape[0] if rgb.ndim == 4 else 1
+        r = None if roles is None else np.ascontiguousarray(roles, np.uint8)
+        if depth.dtype == np.uint16:
+            d = np.ascontiguousarray(depth)
+            self._ck(self.L.r360_set_frames(self.h, first, n, _p(rgb), _p(d), _p(r)))
+        else:
+            d = np.ascontiguousarray(depth, np.float32)
+            self._ck(self.L.r360_set_frames_f32(self.h, first, n, _p(rgb), _p(d), _p(r)))
+
+    def set_frames_ptr(self, first, n, rgb_ptr, depth_ptr, roles=None, device=False):
+        """Raw-pointer form (host pinned buffers or device pointers)."""
+        r = None if roles is None else np.ascontiguousarray(roles, np.uint8)
+        fn = self.L.r360_set_frames_dev if device else self.L.r360_set_frames
+        self._ck(fn(self.h, first, n, _p(rgb_ptr), _p(depth_ptr), _p(r)))
+
+    def synth_frames(self, kind, first_id, n):
+        rgb = np.zeros((n, self.rows, self.cols, 3), np.uint8)
+        d = np.zeros((n, self.rows, self.cols), np.uint16)
+        self._ck(self.L.r360_synth_frames(self.h, kind, first_id, n, _p(rgb), _p(d)))
+        return rgb, d
+
+    def synth_frames_dev(self, kind, first_id, n, rgb_ptr, depth_ptr):
+        self._ck(self.L.r360_synth_frames_dev(self.h, kind, first_id, n, _p(rgb_ptr), _p(depth_ptr)))
+
+    # ---- registration
+    def register_pairs(self, src_idx, trg_idx, init_pose=None, trace=False, out=None):
+        s = np.ascontiguousarray(src_idx, np.int32)
+        t = np.ascontiguousarray(trg_idx, np.int32)
+        n = s.size
+        res = out if out is not None else np.zeros(n, RESULT_DTYPE)
+        ip = None
+        if init_pose is not None:
+            ip = np.ascontiguousarray(init_pose, np.float32).reshape(n, 16)
+        tr = None
+        if trace:
+            tr = (IterRecord * (n * self.params.n_levels * (self.params.max_iters + 2)))()
+        self._ck(self.L.r360_register_pairs(self.h, n, _p(s), _p(t), _p(ip), _p(res),
+                                            C.cast(tr, C.c_void_p) if trace else None))
+        return (res, tr) if trace else res
+
+    def eval_error(self, src, trg, level, pose):
+        e2, n = C.c_double(), C.c_int32()
+        T = pose_to_colmajor(pose)
+        self._ck(self.L.r360_eval_error(self.h, src, trg, level, _p(T), C.byref(e2), C.byref(n)))
+        return e2.value, n.value
+
+    def eval_hessgrad(self, src, trg, level, pose):
+        H = np.zeros(36, np.float32); g = np.zeros(6, np.float32); nv = C.c_int32()
+        T = pose_to_colmajor(pose)
+        self._ck(self.L.r360_eval_hessgrad(self.h, src, trg, level, _p(T), _p(H), _p(g), C.byref(nv)))
+        return H.reshape(6, 6), g, nv.value
+
+    def dump_level(self, frame, level, grads=True):
+        r, c = self.rows >> level, self.cols >> level
+        names = ["gray", "depth"] + (["ggx", "ggy", "dgx", "dgy"] if grads else [])
+        out = {k: np.zeros((r, c), np.float32) for k in names}
+        args = [_p(out[k]) if k in out else None for k in ["gray", "depth", "ggx", "ggy", "dgx", "dgy"]]
+        self._ck(self.L.r360_dump_level(self.h, frame, level, *args))
+        return out
+
+    def dump_source_level(self, frame, level):
+        r, c = self.rows >> level, self.cols >> level
+        g = np.zeros((r, c), np.float32); d = np.zeros((r, c), np.float32)
+        self._ck(self.L.r360_dump_source_level(self.h, frame, level, _p(g), _p(d)))
+        return dict(gray=g, depth=d)
+
+    def dump_warp(self, src, trg, level, pose):
+        n = (self.rows >> level) * (self.cols >> level)
+        ri = np.zeros(n, np.int32); ci = np.zeros(n, np.int32)
+        vp = np.zeros(n, np.uint8); vd = np.zeros(n, np.uint8)
+        T = pose_to_colmajor(pose)
+        self._ck(self.L.r360_dump_warp(self.h, src, trg, level, _p(T), _p(ri), _p(ci), _p(vp), _p(vd)))
+        return ri, ci, vp, vd
+
+    # ---- plumbing
+    def synchronize(self):
+        self._ck(self.L.r360_synchronize(self.h))
+
+    def last_device_ms(self):
+        return float(self.L.r360_last_device_ms(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.r360_kernel_launches(self.h))
+
+    def last_pass_stats(self):
+        ms, n, b = C.c_float(), C.c_int32(), C.c_double()
+        self._ck(self.L.r360_last_pass_stats(self.h, C.byref(ms), C.byref(n), C.byref(b)))
+        return dict(ms=ms.value, launches=n.value, alg_bytes=b.value)

@@ -1,0 +1,232 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): integer work (index maps, masks, counts) bit-exact; float
+pyramid planes bit-exact (same IEEE op sequence); per-iteration residual sums within 1e-4
+relative; final poses within 1e-4 rad / 1e-4 m.
+"""
+import numpy as np
+import pytest
+from util import pose_err, small_pose, upper21
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4          # tolerance on sums (north_star)
+POSE_RAD = 1e-4
+POSE_M = 1e-4
+
+
+@pytest.fixture(scope="module")
+def pair_small(orc, r360):
+    """Synthetic 512x256 pair, 3 levels: oracle frames + GPU context."""
+    rows, cols, L = 256, 512, 3
+    P = orc.default_params(n_levels=L)
+    rgb_t, d_t = orc.synth_frame(0, 0, rows, cols)
+    rgb_s, d_s = orc.synth_frame(0, 1, rows, cols)
+    trg = orc.Frame(rgb_t, d_t, P, True)
+    src = orc.Frame(rgb_s, d_s, P, False)
+    gp = r360.default_params(n_levels=L)
+    ctx = r360.Context(rows, cols, 4, 2, gp)
+    ctx.set_frames(0, np.stack([rgb_s, rgb_t]), np.stack([d_s, d_t]), [r360.ROLE_SOURCE, r360.ROLE_TARGET])
+    yield dict(orc=orc, ctx=ctx, src=src, trg=trg, P=P, L=L, rows=rows, cols=cols,
+               rgb=(rgb_s, rgb_t), depth=(d_s, d_t))
+    ctx.close()
+
+
+def test_synth_frames_bit_exact(pair_small):
+    """GPU-rendered synthetic frames == host-rendered (same pinned math)."""
+    ctx = pair_small["ctx"]
+    rgb, d = ctx.synth_frames(0, 0, 2)
+    assert np.array_equal(rgb[1], pair_small["rgb"][0])
+    assert np.array_equal(rgb[0], pair_small["rgb"][1])
+    assert np.array_equal(d[1], pair_small["depth"][0])
+    assert np.array_equal(d[0], pair_small["depth"][1])
+
+
+def test_pyramids_bit_exact(pair_small):
+    """a1-a5: gray/depth pyramids, gradient planes and joint mask, every level."""
+    ctx, trg, src = pair_small["ctx"], pair_small["trg"], pair_small["src"]
+    for level in range(pair_small["L"]):
+        g = ctx.dump_level(1, level)
+        o = trg.level(level)
+        for k in ("gray", "depth", "ggx", "ggy", "dgx", "dgy"):
+            assert np.array_equal(g[k].view(np.int32), o[k].view(np.int32)), (level, k)
+        gs = ctx.dump_source_level(0, level)
+        os_ = src.level(level)
+        for k in ("gray", "depth"):
+            assert np.array_equal(gs[k].view(np.int32), os_[k].view(np.int32)), (level, k)
+
+
+POSES = [small_pose(), small_pose(0.01, -0.02, 0.015, 0.03, -0.02, 0.05),
+         small_pose(0.3, 0.1, -0.2, 0.2, 0.1, -0.3), small_pose(-3.0, 0.0, 0.0, 0.0, 0.0, 0.0)]
+
+
+@pytest.mark.parametrize("pi", range(len(POSES)))
+def test_warp_maps_bit_exact(pair_small, pi):
+    """Index maps (r', c') and validPixelsPhoto/Depth masks, every level."""
+    orc, ctx = pair_small["orc"], pair_small["ctx"]
+    for level in range(pair_small["L"]):
+        ro, co, vpo, vdo = orc.warp(pair_small["src"], pair_small["trg"], level, POSES[pi], pair_small["P"])
+        rg, cg, vpg, vdg = ctx.dump_warp(0, 1, level, POSES[pi])
+        assert np.array_equal(ro, rg), (level, int(np.count_nonzero(ro != rg)))
+        assert np.array_equal(co, cg), (level, int(np.count_nonzero(co != cg)))
+        assert np.array_equal(vpo, vpg)
+        assert np.array_equal(vdo, vdg)
+
+
+@pytest.mark.parametrize("pi", range(len(POSES)))
+def test_error_and_hessgrad(pair_small, pi):
+    """a8/a9: counts bit-exact, sums within 1e-4 relative."""
+    orc, ctx, P = pair_small["orc"], pair_small["ctx"], pair_small["P"]
+    for level in range(pair_small["L"]):
+        e2o, nvo = orc.error(pair_small["src"], pair_small["trg"], level, POSES[pi], P)
+        e2g, nvg = ctx.eval_error(0, 1, level, POSES[pi])
+        assert nvo == nvg
+        assert abs(e2g - e2o) <= REL * abs(e2o)
+        ho = orc.hessgrad(pair_small["src"], pair_small["trg"], level, POSES[pi], P)
+        Hg, gg, nvis = ctx.eval_hessgrad(0, 1, level, POSES[pi])
+        assert nvis == ho["n_visible"]
+        Ho = ho["H"].astype(np.float64)
+        scale = np.sqrt(np.outer(np.diag(Ho), np.diag(Ho)))
+        assert np.all(np.abs(Hg - Ho) <= REL * scale), np.max(np.abs(Hg - Ho) / scale)
+        # g_a is a sum of J_a * r terms: bound by sqrt(H_aa * err2) (Cauchy-Schwarz)
+        gscale = np.sqrt(np.diag(Ho) * e2o)
+        assert np.all(np.abs(gg - ho["g"]) <= REL * gscale), np.max(np.abs(gg - ho["g"]) / gscale)
+
+
+def _check_align(orc, res_g, tr_g, res_o, tr_o, P):
+    L = P.n_levels
+    assert list(res_g["iters"][:L]) == list(res_o.iters)[:L]
+    assert res_g["status"] == res_o.status
+    per = P.max_iters + 2
+    for lvl in range(L):
+        for k in range(per):
+            o, g = tr_o[lvl * per + k], tr_g[lvl * per + k]
+            assert bool(o.used) == bool(g.used), (lvl, k)
+            if not o.used:
+                continue
+            assert o.n_valid == g.n_valid, (lvl, k)          # integer work: bit-exact
+            assert o.accepted == g.accepted and o.it == g.it
+            assert abs(g.err2 - o.err2) <= REL * abs(o.err2), (lvl, k)
+            if o.used & 2:
+                assert o.n_visible == g.n_visible
+                Ho = np.array(o.hessian, np.float64); Hg = np.array(g.hessian, np.float64)
+                d = upper21(np.sqrt(np.outer(*(2 * [np.array([Ho[i] for i in (0, 6, 11, 15, 18, 20)])]))))
+                assert np.all(np.abs(Hg - Ho) <= REL * d)
+    To = orc.pose_from(res_o.pose)
+    Tg = np.array(res_g["pose"], np.float32).reshape(4, 4).T
+    ang, dist = pose_err(Tg, To)
+    assert ang <= POSE_RAD and dist <= POSE_M, (ang, dist)
+    assert abs(res_g["final_err2"] - res_o.final_err2) <= REL * res_o.final_err2
+    assert res_g["final_n_valid"] == res_o.final_n_valid
+    assert res_g["n_visible"] == res_o.n_visible
+    assert abs(res_g["sso"] - res_o.sso) < 1e-6
+    Ho = np.array(res_o.hessian, np.float64).reshape(6, 6)
+    Hg = np.array(res_g["hessian"], np.float64).reshape(6, 6)
+    sc = np.sqrt(np.outer(np.diag(Ho), np.diag(Ho)))
+    assert np.all(np.abs(Hg - Ho) <= REL * sc)
+
+
+def test_align_identity_guess(pair_small):
+    """alignFrames360 end to end with per-iteration trace: same control flow, sums, pose."""
+    orc, ctx, P = pair_small["orc"], pair_small["ctx"], pair_small["P"]
+    res_o, tr_o = orc.align(pair_small["src"], pair_small["trg"], None, P, trace=True)
+    res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    gt = orc.synth_gt_pose(0, 1, 0)
+    ang, dist = pose_err(np.array(res_g[0]["pose"]).reshape(4, 4).T, gt)
+    assert ang < 2e-3 and dist < 5e-3          # converged to the analytic ground truth
+
+
+def test_align_with_guess_and_batch(pair_small, r360):
+    """A batch of pairs with different initial guesses == one-by-one oracle runs."""
+    orc, ctx, P = pair_small["orc"], pair_small["ctx"], pair_small["P"]
+    guesses = [small_pose(0.01, 0.0, -0.01, 0.02, 0.0, -0.02), small_pose()]
+    gp = np.stack([r360.pose_to_colmajor(g) for g in guesses])
+    res_g, tr_g = ctx.register_pairs([0, 0], [1, 1], gp, trace=True)
+    per = P.n_levels * (P.max_iters + 2)
+    for k, g in enumerate(guesses):
+        res_o, tr_o = orc.align(pair_small["src"], pair_small["trg"], g, P, trace=True)
+        _check_align(orc, res_g[k], tr_g[k * per:(k + 1) * per], res_o, tr_o, P)
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_photo_only_and_depth_only(orc, r360, method):
+    rows, cols, L = 128, 256, 2
+    P = orc.default_params(n_levels=L, method=method)
+    rgb_t, d_t = orc.synth_frame(0, 4, rows, cols)
+    rgb_s, d_s = orc.synth_frame(0, 5, rows, cols)
+    trg = orc.Frame(rgb_t, d_t, P, True); src = orc.Frame(rgb_s, d_s, P, False)
+    ctx = r360.Context(rows, cols, 2, 1, r360.default_params(n_levels=L, method=method))
+    ctx.set_frames(0, np.stack([rgb_s, rgb_t]), np.stack([d_s, d_t]))
+    res_o, tr_o = orc.align(src, trg, None, P, trace=True)
+    res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    ctx.close()
+
+
+def test_invalid_depth_and_float_depth(orc, r360):
+    """Zero / out-of-range depth (INVALID_POINT path, zero-depth target texels) and CV_32F depth."""
+    rows, cols, L = 128, 256, 3
+    P = orc.default_params(n_levels=L)
+    rng = np.random.default_rng(3)
+    fr = []
+    for fid in (8, 9):
+        rgb, d = orc.synth_frame(0, fid, rows, cols)
+        d = d.copy()
+        d[rng.random(d.shape) < 0.15] = 0                     # holes
+        d[10:20, 30:90] = 7000                                # beyond maxDepth
+        d[40:44, :] = 200                                     # below minDepth
+        fr.append((rgb, d))
+    trg = orc.Frame(fr[0][0], fr[0][1], P, True); src = orc.Frame(fr[1][0], fr[1][1], P, False)
+    ctx = r360.Context(rows, cols, 4, 1, r360.default_params(n_levels=L))
+    ctx.set_frames(0, np.stack([fr[1][0], fr[0][0]]), np.stack([fr[1][1], fr[0][1]]))
+    for level in range(L):
+        g = ctx.dump_level(1, level); o = trg.level(level)
+        for k in o:
+            assert np.array_equal(g[k].view(np.int32), o[k].view(np.int32)), (level, k)
+        ro, co, vpo, vdo = orc.warp(src, trg, level, POSES[1], P)
+        rg, cg, vpg, vdg = ctx.dump_warp(0, 1, level, POSES[1])
+        assert np.array_equal(ro, rg) and np.array_equal(co, cg)
+        assert np.array_equal(vpo, vpg) and np.array_equal(vdo, vdg)
+    res_o, tr_o = orc.align(src, trg, None, P, trace=True)
+    res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    # float depth in metres: same planes as the u16 path after * 0.001f
+    dm = [(f[1].astype(np.float32) * np.float32(0.001)) for f in fr]
+    ctx.set_frames(2, np.stack([fr[1][0], fr[0][0]]), np.stack([dm[1], dm[0]]))
+    for level in range(L):
+        a = ctx.dump_level(1, level); b = ctx.dump_level(3, level)
+        for k in a:
+            assert np.array_equal(a[k].view(np.int32), b[k].view(np.int32))
+    ctx.close()
+
+
+def test_non_power_of_two_width(orc, r360):
+    """1920x320-like geometry (the sample pair's shape, scaled): generic row/col split."""
+    rows, cols, L = 80, 480, 3
+    P = orc.default_params(n_levels=L)
+    rgb_t, d_t = orc.synth_frame(0, 2, rows, cols)
+    rgb_s, d_s = orc.synth_frame(0, 3, rows, cols)
+    trg = orc.Frame(rgb_t, d_t, P, True); src = orc.Frame(rgb_s, d_s, P, False)
+    ctx = r360.Context(rows, cols, 2, 1, r360.default_params(n_levels=L))
+    ctx.set_frames(0, np.stack([rgb_s, rgb_t]), np.stack([d_s, d_t]))
+    for level in range(L):
+        ro, co, vpo, vdo = orc.warp(src, trg, level, POSES[1], P)
+        rg, cg, vpg, vdg = ctx.dump_warp(0, 1, level, POSES[1])
+        assert np.array_equal(ro, rg) and np.array_equal(co, cg)
+        assert np.array_equal(vpo, vpg) and np.array_equal(vdo, vdg)
+    res_o, tr_o = orc.align(src, trg, None, P, trace=True)
+    res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    ctx.close()
+
+
+def test_errors_are_loud(r360):
+    ctx = r360.Context(64, 128, 2, 1, r360.default_params(n_levels=2))
+    with pytest.raises(r360.R360Error):
+        ctx.register_pairs([0], [1])                  # frames never set
+    with pytest.raises(r360.R360Error):
+        r360.Context(64, 128, 2, 1, r360.default_params(n_levels=2, occlusion=1))
+    with pytest.raises(r360.R360Error):
+        r360.Context(65, 128, 2, 1, r360.default_params(n_levels=2))
+    ctx.close()
