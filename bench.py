@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- sphere-pair registrations/s of the B200 spherical dense registration path.
+
+One "step" = one pass of the hot path over one batch of synthetic sphere pairs:
+pyramid build of every frame (setSourceFrame / setTargetFrame) + batched alignFrames360.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload A|B] [--pairs P]
+
+Workload A (default, the configuration BASELINE.json's metric is quoted on): synthetic
+2048x1024 sphere pairs, 4-level pyramid, photometric + depth with Huber weights, 512 pairs
+per GPU (weak scaling).  Workload B: 1024x512, 3 levels, 256 pairs.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: same metric through the
+C ABI with HOST (pinned) buffers, H2D of the frames and D2H of the results inside the timed
+region.  `--impl reference` times the CPU oracle (port of the reference's own CPU path, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "A": dict(rows=1024, cols=2048, levels=4, pairs=512,
+              name="synthetic 2048x1024 sphere pairs, 4-level pyramid, photo+depth Huber, batch 512 per GPU"),
+    "B": dict(rows=512, cols=1024, levels=3, pairs=256,
+              name="synthetic 1024x512 sphere pairs, 3-level pyramid, photo+depth Huber, batch 256 per GPU"),
+}
+METRIC = "sphere-pair registrations/s @2048x1024"
+UNIT = "pairs/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args):
+    w = dict(WORKLOADS[args.workload])
+    if args.pairs:
+        w["pairs"] = args.pairs
+    return w
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_run(w, n_pairs, first_pair=0):
+    """Oracle (port of the reference CPU path, FAITHFUL accumulation, all host threads) on
+    n_pairs pairs of the workload: set{Target,Source}Frame + alignFrames360 per pair."""
+    from oracle import orc
+    orc.build()
+    orc.set_math(orc.MATH_LIBM)          # what a g++/glibc build of the reference calls
+    P = orc.default_params(n_levels=w["levels"])
+    frames = [orc.synth_frame(0, 2 * (first_pair + k) + j, w["rows"], w["cols"]) for k in range(n_pairs) for j in (0, 1)]
+    t0 = time.perf_counter()
+    for k in range(n_pairs):
+        trg = orc.Frame(frames[2 * k][0], frames[2 * k][1], P, True)        # setTargetFrame
+        src = orc.Frame(frames[2 * k + 1][0], frames[2 * k + 1][1], P, False)  # setSourceFrame
+        orc.align(src, trg, None, P, accum=orc.ACC_FAITHFUL)                 # alignFrames360
+    dt = time.perf_counter() - t0
+    orc.set_math(orc.MATH_PINNED)
+    return n_pairs / dt, orc.omp_threads(), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args)
+    sample = 2 if args.workload == "A" else 4
+    for _ in range(args.warmup):
+        cpu_reference_run(w, 1)
+    t0 = time.perf_counter()
+    cores = 1
+    for s in range(args.steps):
+        _, cores, _ = cpu_reference_run(w, sample, first_pair=s * sample)
+    dt = time.perf_counter() - t0
+    v = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": w["name"], "rows": w["rows"], "cols": w["cols"], "levels": w["levels"],
+                   "pairs_per_step": sample, "note": "CPU oracle (port of the reference; the reference itself "
+                   "needs Eigen/OpenCV/PCL/MRPT and cannot be built here), FAITHFUL accumulation, glibc math"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} pairs per step x {args.steps} steps, frame build + alignFrames360"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rgbd360_b200 as r360
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the registration path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = workload(args)
+    rows, cols, L, n_pairs = w["rows"], w["cols"], w["levels"], w["pairs"]
+    n_frames = 2 * n_pairs
+    npx = rows * cols
+
+    params = r360.default_params(n_levels=L)
+    ctx = r360.Context(rows, cols, n_frames, n_pairs, params, device=local)
+    # synthetic frames rendered on the device: pair j = (target frame 2j, source frame 2j+1),
+    # frame ids offset per rank so every GPU registers different pairs (weak scaling)
+    rgb_dev = torch.empty((n_frames, rows, cols, 3), dtype=torch.uint8, device="cuda")
+    dep_dev = torch.empty((n_frames, rows, cols), dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    ctx.synth_frames_dev(0, rank * n_frames, n_frames, rgb_dev.data_ptr(), dep_dev.data_ptr())
+    roles = np.array([r360.ROLE_TARGET, r360.ROLE_SOURCE] * n_pairs, np.uint8)
+    trg_idx = np.arange(0, n_frames, 2, dtype=np.int32)
+    src_idx = trg_idx + 1
+    res = np.zeros(n_pairs, r360.native.RESULT_DTYPE)
+    res_bytes = res.nbytes
+    gather_in = torch.empty(res_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+    gather_out = torch.empty(res_bytes * world, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def gather_results():
+        if world > 1:
+            gather_in.copy_(torch.from_numpy(res.view(np.uint8)), non_blocking=False)
+            dist.all_gather_into_tensor(gather_out, gather_in)
+
+    def step_resident():
+        ctx.set_frames_ptr(0, n_frames, rgb_dev.data_ptr(), dep_dev.data_ptr(), roles, device=True)
+        ms = ctx.last_device_ms()
+        ctx.register_pairs(src_idx, trg_idx, None, out=res)
+        ms += ctx.last_device_ms()
+        gather_results()
+        return ms
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches()
+    dev_ms, pass_ms, pass_bytes, pass_launches = 0.0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_ms += step_resident()
+        ps = ctx.last_pass_stats()
+        pass_ms += ps["ms"]; pass_bytes += ps["alg_bytes"]; pass_launches += ps["launches"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host pinned frames -> C ABI -> host results (H2D / D2H inside the timed region)
+    rgb_host = torch.empty((n_frames, rows, cols, 3), dtype=torch.uint8, pin_memory=True)
+    dep_host = torch.empty((n_frames, rows, cols), dtype=torch.int16, pin_memory=True)
+    rgb_host.copy_(rgb_dev); dep_host.copy_(dep_dev)
+    torch.cuda.synchronize()
+
+    def step_e2e():
+        ctx.set_frames_ptr(0, n_frames, rgb_host.data_ptr(), dep_host.data_ptr(), roles, device=False)
+        ctx.register_pairs(src_idx, trg_idx, None, out=res)
+        gather_results()
+
+    step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms, pass_ms], dtype=torch.float64, device="cuda")
+    s = torch.tensor([pass_bytes, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms, e2e_ms, pass_ms_max = [float(x) for x in t.tolist()]
+    total_pairs = n_pairs * world
+    value = total_pairs * args.steps / (wall_ms / 1e3)
+    e2e_value = total_pairs * e2e_steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = (pass_bytes / 1e9) / (pass_ms / 1e3) if pass_ms > 0 else 0.0     # rank 0's kernel
+        iters = res["iters"][:, :L].astype(np.float64)
+        passes = res["passes"][:, :L].astype(np.float64)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": wall_ms / args.steps,
+            "device_ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "rows": rows, "cols": cols, "levels": L,
+                       "pairs_per_gpu": n_pairs, "frames_per_gpu": n_frames, "method": "PHOTO_DEPTH",
+                       "sampling": "nearest-neighbour (reference semantics)",
+                       "l2": "inputs larger than L2 (pyramids %.1f GB per GPU)" % (
+                           (8 + 24) * ctx.rows * ctx.cols * sum(0.25 ** l for l in range(L)) * n_pairs / 1e9),
+                       "step": "pyramid build of all frames + batched alignFrames360" + (" + NCCL allgather of results" if world > 1 else ""),
+                       "mean_accepted_iters_per_level": [float(x) for x in iters.mean(0)],
+                       "mean_passes_per_level": [float(x) for x in passes.mean(0)],
+                       "pairs_ok": int((res["status"] == 0).sum())},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(n_frames * npx * 5 + n_pairs * 8 * 3),
+                    "d2h_bytes_per_step": int(res_bytes), "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_pass<PHOTO_DEPTH> (fused warp/residual/normal-equation pass)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "alg_bytes_per_launch": pass_bytes / max(pass_launches, 1),
+                         "avg_launch_ms": pass_ms / max(pass_launches, 1), "launches": pass_launches,
+                         "kernel_share_of_step": pass_ms / dev_ms if dev_ms else None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, dt = cpu_reference_run(w, 2 if args.workload == "A" else 4)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d pairs of the same workload (frame build + alignFrames360, "
+                                              "FAITHFUL accumulation, glibc math), %.1f s" % (2 if args.workload == "A" else 4, dt)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="A", choices=list(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -179,26 +179,60 @@ k_pass(R360PassArgs a) {
         int n_vis = 0, n_photo = 0, n_depth = 0;
 
         const int i_end = min(lv.n, (sub + 1) * a.px_per_item);
-#pragma unroll 2
-        for (int i = sub * a.px_per_item + threadIdx.x; i < i_end; i += R360_PASS_THREADS) {
-            const float2 sd = __ldg(&src[i]);                 // {depth, gray} of the source pixel
-            const float d = sd.x;
-            if (!(P.min_depth < d && d < P.max_depth)) continue;     // LUT INVALID_POINT (RPI.h:4575,4585)
-            const int r = (int)(((unsigned long long)i * lv.div_magic) >> 40);
-            const int c = i - r * lv.cols;
-            float X[3];
-            r360_backproject(d, __ldg(&lv.sin_p[r]), __ldg(&lv.cos_p[r]), __ldg(&lv.sin_t[c]),
-                             __ldg(&lv.cos_t[c]), X);
-            R360Warp w;
-            if (!r360_warp_point(T, X, lv.res_inv, lv.half_rows, lv.rows, lv.cols, w)) continue;
-            ++n_vis;
-            const float2* tx = trg + 3 * ((size_t)w.r * lv.cols + w.c);
-            const float2 t0 = __ldg(tx), t1 = __ldg(tx + 1), t2 = __ldg(tx + 2);
-            float Jp[6], Jd[6], rp = 0.f, rd = 0.f;
-            const int v = r360_rows<METHOD>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P,
-                                            inv_std_photo, Jp, rp, Jd, rd);
-            if (v & 1) { r360_accumulate(acc, Jp, rp); ++n_photo; }
-            if (v & 2) { r360_accumulate(acc, Jd, rd); ++n_depth; }
+        // Batches of R360_PASS_U pixels per thread, staged so that the U source loads, then the U
+        // texel gathers, are in flight together (the two dependent HBM round trips per pixel are
+        // what bounds this kernel); the source loads of the next batch are prefetched.
+        int i0 = sub * a.px_per_item + threadIdx.x;
+        float2 sd[R360_PASS_U];
+#pragma unroll
+        for (int u = 0; u < R360_PASS_U; ++u) {
+            const int i = i0 + u * R360_PASS_THREADS;
+            sd[u] = i < i_end ? __ldg(&src[i]) : make_float2(0.f, 0.f);
+        }
+        for (; i0 < i_end; i0 += R360_PASS_THREADS * R360_PASS_U) {
+            float2 sdn[R360_PASS_U];
+#pragma unroll
+            for (int u = 0; u < R360_PASS_U; ++u) {
+                const int i = i0 + (u + R360_PASS_U) * R360_PASS_THREADS;
+                sdn[u] = i < i_end ? __ldg(&src[i]) : make_float2(0.f, 0.f);
+            }
+            R360Warp w[R360_PASS_U];
+            bool ok[R360_PASS_U];
+            const float2* tx[R360_PASS_U];
+#pragma unroll
+            for (int u = 0; u < R360_PASS_U; ++u) {
+                const int i = i0 + u * R360_PASS_THREADS;
+                const float d = sd[u].x;
+                // LUT INVALID_POINT (RPI.h:4575,4585); out-of-range lanes of the tail carry d = 0
+                ok[u] = i < i_end && (P.min_depth < d && d < P.max_depth);
+                const int ii = ok[u] ? i : 0;
+                const int r = (int)(((unsigned long long)ii * lv.div_magic) >> 40);
+                const int c = ii - r * lv.cols;
+                float X[3];
+                r360_backproject(d, __ldg(&lv.sin_p[r]), __ldg(&lv.cos_p[r]), __ldg(&lv.sin_t[c]),
+                                 __ldg(&lv.cos_t[c]), X);
+                const bool inb = r360_warp_point(T, X, lv.res_inv, lv.half_rows, lv.rows, lv.cols, w[u]);
+                ok[u] = ok[u] && inb;
+                tx[u] = trg + 3 * (ok[u] ? ((size_t)w[u].r * lv.cols + w[u].c) : 0);
+            }
+            float2 t0[R360_PASS_U], t1[R360_PASS_U], t2[R360_PASS_U];
+#pragma unroll
+            for (int u = 0; u < R360_PASS_U; ++u) {
+                t0[u] = __ldg(tx[u]); t1[u] = __ldg(tx[u] + 1); t2[u] = __ldg(tx[u] + 2);
+            }
+#pragma unroll
+            for (int u = 0; u < R360_PASS_U; ++u) {
+                if (ok[u]) {
+                    ++n_vis;
+                    float Jp[6], Jd[6], rp = 0.f, rd = 0.f;
+                    const int v = r360_rows<METHOD>(w[u], lv.res_inv, sd[u].y, t0[u].x, t0[u].y, t1[u].x, t1[u].y,
+                                                    t2[u].x, t2[u].y, P, inv_std_photo, Jp, rp, Jd, rd);
+                    if (v & 1) { r360_accumulate(acc, Jp, rp); ++n_photo; }
+                    if (v & 2) { r360_accumulate(acc, Jd, rd); ++n_depth; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < R360_PASS_U; ++u) sd[u] = sdn[u];
         }
 
         // ---- block reduction

@@ -3,6 +3,7 @@
 #include "r360_device.cuh"
 
 #define R360_PASS_THREADS 256
+#define R360_PASS_U 4        // pixels per thread per batch in k_pass
 
 struct R360PassArgs {
     R360Level lv;

