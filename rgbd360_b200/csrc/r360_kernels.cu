@@ -173,9 +173,8 @@ k_pass(R360PassArgs a) {
         const float2* __restrict__ src = a.src_base[pair] + lv.px_off;
         const float2* __restrict__ trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
 
-        float acc[R360_ACC_DOUBLES];
-#pragma unroll
-        for (int k = 0; k < R360_ACC_DOUBLES; ++k) acc[k] = 0.f;
+        R360Acc A;
+        r360_acc_zero(A);
         int n_vis = 0, n_photo = 0, n_depth = 0;
 
         const int i_end = min(lv.n, (sub + 1) * a.px_per_item);
@@ -224,11 +223,11 @@ k_pass(R360PassArgs a) {
             for (int u = 0; u < R360_PASS_U; ++u) {
                 if (ok[u]) {
                     ++n_vis;
-                    float Jp[6], Jd[6], rp = 0.f, rd = 0.f;
+                    R360Row ph, dp;
                     const int v = r360_rows<METHOD>(w[u], lv.res_inv, sd[u].y, t0[u].x, t0[u].y, t1[u].x, t1[u].y,
-                                                    t2[u].x, t2[u].y, P, inv_std_photo, Jp, rp, Jd, rd);
-                    if (v & 1) { r360_accumulate(acc, Jp, rp); ++n_photo; }
-                    if (v & 2) { r360_accumulate(acc, Jd, rd); ++n_depth; }
+                                                    t2[u].x, t2[u].y, P, inv_std_photo, ph, dp);
+                    if (v & 1) { r360_accumulate(A, ph); ++n_photo; }
+                    if (v & 2) { r360_accumulate(A, dp); ++n_depth; }
                 }
             }
 #pragma unroll
@@ -236,6 +235,8 @@ k_pass(R360PassArgs a) {
         }
 
         // ---- block reduction
+        float acc[R360_ACC_DOUBLES];
+        r360_acc_unpack(A, acc);
 #pragma unroll
         for (int k = 0; k < R360_ACC_DOUBLES; ++k) {
             float v = acc[k];
@@ -288,13 +289,13 @@ k_warp_dump(R360PassArgs a, int pair, int method, int32_t* __restrict__ r_idx, i
             if (inb) {
                 const float2* tx = trg + 3 * ((size_t)w.r * lv.cols + w.c);
                 const float2 t0 = tx[0], t1 = tx[1], t2 = tx[2];
-                float Jp[6], Jd[6], rp, rd;
+                R360Row ph, dp;
                 if (method == R360_PHOTO_CONSISTENCY)
-                    v = r360_rows<R360_PHOTO_CONSISTENCY>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, Jp, rp, Jd, rd);
+                    v = r360_rows<R360_PHOTO_CONSISTENCY>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, ph, dp);
                 else if (method == R360_DEPTH_CONSISTENCY)
-                    v = r360_rows<R360_DEPTH_CONSISTENCY>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, Jp, rp, Jd, rd);
+                    v = r360_rows<R360_DEPTH_CONSISTENCY>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, ph, dp);
                 else
-                    v = r360_rows<R360_PHOTO_DEPTH>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, Jp, rp, Jd, rd);
+                    v = r360_rows<R360_PHOTO_DEPTH>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, ph, dp);
             }
         }
         if (r_idx) r_idx[i] = rr;

@@ -1,0 +1,43 @@
+// Drop-in check of include/RegisterPhotoICP_b200.hpp: the call sequence of
+// Registration/OdometryRGBD360.cpp:189-193 (setNumPyr, setTargetFrame, setSourceFrame,
+// alignFrames360(guess, PHOTO_DEPTH), getOptimalPose) against r360_register_pairs on the same frames.
+#include <cstdio>
+#include <cmath>
+#include <vector>
+#include "RegisterPhotoICP_b200.hpp"
+
+int main() {
+    const int rows = 128, cols = 256, L = 3;
+    r360_params P; r360_default_params(&P); P.n_levels = L;
+    r360_ctx* ctx = nullptr;
+    if (r360_create(&ctx, 0, rows, cols, 2, 1, &P)) { std::printf("create failed: %s\n", r360_last_error(nullptr)); return 2; }
+    std::vector<uint8_t> rgb((size_t)2 * rows * cols * 3);
+    std::vector<uint16_t> depth((size_t)2 * rows * cols);
+    if (r360_synth_frames(ctx, 0, 0, 2, rgb.data(), depth.data())) { std::printf("synth failed\n"); return 2; }
+    const uint8_t roles[2] = {R360_ROLE_TARGET, R360_ROLE_SOURCE};      // frame 0 target, frame 1 source
+    r360_set_frames(ctx, 0, 2, rgb.data(), depth.data(), roles);
+    const int32_t s = 1, t = 0;
+    r360_result ref;
+    if (r360_register_pairs(ctx, 1, &s, &t, nullptr, &ref, nullptr)) { std::printf("register failed: %s\n", r360_last_error(ctx)); return 2; }
+
+    RegisterPhotoICP reg;
+    reg.setNumPyr(L);
+    r360::Image rgb0{rgb.data(), rows, cols, 3, 1, 0}, rgb1{rgb.data() + (size_t)rows * cols * 3, rows, cols, 3, 1, 0};
+    r360::Image d0{depth.data(), rows, cols, 1, 2, 0}, d1{depth.data() + (size_t)rows * cols, rows, cols, 1, 2, 0};
+    reg.setTargetFrame(rgb0, d0);
+    reg.setSourceFrame(rgb1, d1);
+    reg.alignFrames360(RegisterPhotoICP::identity(), RegisterPhotoICP::PHOTO_DEPTH);
+    auto pose = reg.getOptimalPoseArray();
+    double dmax = 0;
+    for (int k = 0; k < 16; ++k) dmax = std::fmax(dmax, std::fabs(pose[k] - ref.pose[k]));
+    double T[16]; r360_synth_gt_pose(0, 1, 0, T);
+    double terr = 0; for (int k = 12; k < 15; ++k) terr = std::fmax(terr, std::fabs(T[k] - pose[k]));
+    std::printf("class vs C ABI max |dPose| = %g, |t - t_gt| = %g, SSO = %g, iters = %d %d %d\n", dmax, terr, reg.SSO,
+                reg.result().iters[0], reg.result().iters[1], reg.result().iters[2]);
+    double e = reg.errorPhotoICP_sphere(0, pose, RegisterPhotoICP::PHOTO_DEPTH);
+    std::printf("rms at optimum = %g (final_error %g)\n", e, reg.result().final_error);
+    r360_destroy(ctx);
+    const bool ok = dmax == 0.0 && terr < 2e-2 && std::fabs(e - reg.result().final_error) < 1e-6 * e;
+    std::printf(ok ? "OK\n" : "FAIL\n");
+    return ok ? 0 : 1;
+}

@@ -240,3 +240,81 @@ def test_errors_are_loud(r360):
     with pytest.raises(r360.R360Error):
         r360.Context(65, 128, 2, 1, r360.default_params(n_levels=2))
     ctx.close()
+
+
+def test_cpp_class_drop_in(tmp_path):
+    """The C++ mirror of the reference class (include/RegisterPhotoICP_b200.hpp) gives the same pose
+    as the batched C ABI call on the same frames."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "class_demo"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "class_demo.cpp"), "-o", str(exe),
+                           "-L", os.path.join(root, "rgbd360_b200"), "-lrgbd360_b200",
+                           "-Wl,-rpath," + os.path.join(root, "rgbd360_b200")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_sample_pair_config1(orc, r360):
+    """Config #1: the reference's sample pair (1920x320, 4 levels, PHOTO_DEPTH, guess Identity):
+    GPU vs the oracle run on the same stitched frames and vs the committed golden vector."""
+    import json, os
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = np.load(os.path.join(gold_dir, "sample_pair.npz"))
+    gold = json.load(open(os.path.join(gold_dir, "sample_pair_oracle.json")))["pinned"]
+    P = orc.default_params(n_levels=4)
+    trg = orc.Frame(d["trg_rgb"], d["trg_depth"], P, True)
+    src = orc.Frame(d["src_rgb"], d["src_depth"], P, False)
+    ctx = r360.Context(320, 1920, 2, 1, r360.default_params(n_levels=4))
+    ctx.set_frames(0, np.stack([d["src_rgb"], d["trg_rgb"]]), np.stack([d["src_depth"], d["trg_depth"]]),
+                   [r360.ROLE_SOURCE, r360.ROLE_TARGET])
+    for level in range(4):                                   # real data: holes, sensor joints, borders
+        g = ctx.dump_level(1, level); o = trg.level(level)
+        for k in o:
+            assert np.array_equal(g[k].view(np.int32), o[k].view(np.int32)), (level, k)
+        ro, co, vpo, vdo = orc.warp(src, trg, level, POSES[1], P)
+        rg, cg, vpg, vdg = ctx.dump_warp(0, 1, level, POSES[1])
+        assert np.array_equal(ro, rg) and np.array_equal(co, cg)
+        assert np.array_equal(vpo, vpg) and np.array_equal(vdo, vdg)
+    res_o, tr_o = orc.align(src, trg, None, P, trace=True)
+    res_g, tr_g = ctx.register_pairs([0], [1], None, trace=True)
+    _check_align(orc, res_g[0], tr_g, res_o, tr_o, P, src, trg)
+    assert list(res_g[0]["iters"][:4]) == gold["iters"]
+    Tg = np.array(res_g[0]["pose"], np.float32).reshape(4, 4).T
+    ang, dist = pose_err(Tg, np.array(gold["pose"], np.float32).reshape(4, 4).T)
+    assert ang <= POSE_RAD and dist <= POSE_M
+    ctx.close()
+
+
+def test_full_size_properties(orc, r360):
+    """BASELINE.json's full size (2048x1024, 4 levels): size-independent properties on a small
+    batch -- convergence to the analytic ground truth, oracle replay of the final pose (counts
+    exact, sum 1e-4), and batch independence (a pair's result does not depend on its neighbours)."""
+    rows, cols, L, n = 1024, 2048, 4, 3
+    ctx = r360.Context(rows, cols, 2 * n, n, r360.default_params(n_levels=L))
+    rgb, dep = ctx.synth_frames(0, 0, 2 * n)
+    roles = np.array([r360.ROLE_TARGET, r360.ROLE_SOURCE] * n, np.uint8)
+    ctx.set_frames(0, rgb, dep, roles)
+    trg_idx = np.arange(0, 2 * n, 2); src_idx = trg_idx + 1
+    res = ctx.register_pairs(src_idx, trg_idx)
+    P = orc.default_params(n_levels=L)
+    for k in range(n):
+        assert res[k]["status"] == 0 and res[k]["pair_id"] == k
+        T = np.array(res[k]["pose"], np.float32).reshape(4, 4).T
+        ang, dist = pose_err(T, orc.synth_gt_pose(0, 2 * k + 1, 2 * k))
+        assert ang < 5e-4 and dist < 1.5e-3, (k, ang, dist)
+        single = ctx.register_pairs([src_idx[k]], [trg_idx[k]])[0]
+        assert np.allclose(single["pose"], res[k]["pose"], atol=1e-6)
+        assert list(single["iters"]) == list(res[k]["iters"])
+    k = 1
+    trg = orc.Frame(rgb[2 * k], dep[2 * k], P, True); src = orc.Frame(rgb[2 * k + 1], dep[2 * k + 1], P, False)
+    T = np.array(res[k]["pose"], np.float32).reshape(4, 4).T
+    e2, nv = orc.error(src, trg, 0, T, P)
+    assert nv == res[k]["final_n_valid"]
+    assert abs(e2 - res[k]["final_err2"]) <= REL * e2
+    res_o = orc.align(src, trg, None, P)
+    ang, dist = pose_err(T, orc.pose_from(res_o.pose))
+    assert ang <= POSE_RAD and dist <= POSE_M, (ang, dist)
+    assert list(res_o.iters)[:L] == list(res[k]["iters"][:L])
+    ctx.close()
