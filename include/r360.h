@@ -137,6 +137,13 @@ int r360_dump_source_level(r360_ctx* ctx, int frame, int level, float* gray, flo
 int r360_dump_warp(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
                    int32_t* r_idx, int32_t* c_idx, uint8_t* valid_photo, uint8_t* valid_depth);
 
+/* The warp kernels evaluate the pinned index sequence on two pixels at once with packed fp32x2
+ * instructions and send pixels outside the range where that is exact (denormal/huge operands,
+ * exact .5 ties) to the scalar pinned code.  r360_index_stats cross-checks the two over every
+ * valid source pixel of a pair: out[0] valid pixels, out[1] pixels sent to the scalar code,
+ * out[2] pixels kept by the packed code whose (r', c') differ from the scalar result (must be 0). */
+int r360_index_stats(r360_ctx* ctx, int src, int trg, int level, const float pose[16], uint64_t out[3]);
+
 /* Synthetic sphere frames of SURVEY 8(d) rendered straight into device buffers
  * (convex box room, procedural texture); frame ids and the scene kind select poses.
  * kind 0: odometry / batch trajectory, 1: loop-closure keyframes. */

@@ -77,7 +77,8 @@ int fail(Ctx* c, int code, const char* fmt, ...) {
     } while (0)
 
 int ensure_src(Ctx* c, int slot) {
-    if (!c->src[slot]) CK(c, cudaMalloc(&c->src[slot], sizeof(float2) * c->px_total));
+    // + 2: the pass kernel reads pixel pairs as float4, an odd-sized last level reads one pixel past its end
+    if (!c->src[slot]) CK(c, cudaMalloc(&c->src[slot], sizeof(float2) * (c->px_total + 2)));
     return R360_OK;
 }
 int ensure_trg(Ctx* c, int slot) {
@@ -90,10 +91,13 @@ R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint) {
     a.lv = c->lv[level];
     a.params = c->P;
     a.inv_std_photo = (float)(1. / c->P.std_photo);
+    a.one = 1.0f;
+    // items: the granularity of the contiguous per-CTA runs (>= 8 items per CTA when there is enough work)
     const long long n = c->lv[level].n;
+    const long long blk = 2LL * R360_PASS_THREADS;                  // pixels per CTA iteration
     long long want = n * (long long)std::max(n_pairs_hint, 1) / (8LL * c->pass_grid);
-    long long ppi = ((want + 1023) / 1024) * 1024;
-    ppi = std::min<long long>(std::max<long long>(ppi, 2048), 16384);
+    long long ppi = ((want + blk - 1) / blk) * blk;
+    ppi = std::min<long long>(std::max<long long>(ppi, blk), 16 * blk);
     a.px_per_item = (int)ppi;
     a.items_per_pair = (int)((n + ppi - 1) / ppi);
     a.n_active = c->d_nactive;
@@ -322,6 +326,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->pass_grid = c->sm_count * 2;
+    CK(c, r360_pass_init());
     CK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
     CK(c, cudaEventCreate(&c->ev_t0));
@@ -353,9 +358,20 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     size_t t = 0;
     for (int l = 0; l < c->L; ++l) {
         R360Level& v = c->lv[l];
-        v.sin_t = c->d_tables + t; v.cos_t = v.sin_t + v.cols; v.sin_p = v.cos_t + v.cols; v.cos_p = v.sin_p + v.rows;
-        for (int k = 0; k < v.cols; ++k) { float th = k * v.res; r360_sincosf(th, &tab[t + k], &tab[t + v.cols + k]); }
-        for (int r = 0; r < v.rows; ++r) { float ph = (v.half_rows - r) * v.res; r360_sincosf(ph, &tab[t + 2 * v.cols + r], &tab[t + 2 * v.cols + v.rows + r]); }
+        // {sin c, sin c+1, cos c, cos c+1}(theta) per column pair and {sin, -cos}(phi_r) per row:
+        // one 16-byte + one 8-byte load per pixel pair
+        v.tab_t = reinterpret_cast<const float4*>(c->d_tables + t);
+        v.tab_p = reinterpret_cast<const float2*>(c->d_tables + t + 2 * (size_t)v.cols);
+        for (int k = 0; k < v.cols; ++k) {
+            float th = k * v.res;
+            r360_sincosf(th, &tab[t + 4 * (k >> 1) + (k & 1)], &tab[t + 4 * (k >> 1) + 2 + (k & 1)]);
+        }
+        for (int r = 0; r < v.rows; ++r) {
+            float ph = (v.half_rows - r) * v.res, sp, cp;
+            r360_sincosf(ph, &sp, &cp);
+            tab[t + 2 * (size_t)v.cols + 2 * r] = sp;
+            tab[t + 2 * (size_t)v.cols + 2 * r + 1] = -cp;
+        }
         t += 2 * (size_t)(v.rows + v.cols);
     }
     CK(c, cudaMemcpy(c->d_tables, tab.data(), sizeof(float) * n_tab, cudaMemcpyHostToDevice));
@@ -397,8 +413,9 @@ int r360_create(r360_ctx** out, int device, int rows, int cols, int max_frames, 
         return fail(nullptr, R360_E_ARG, "r360_create: rows/cols/max_frames/max_pairs must be positive");
     if (params->n_levels < 1 || params->n_levels > R360_MAX_LEVELS)
         return fail(nullptr, R360_E_ARG, "r360_create: n_levels %d not in [1,%d]", params->n_levels, R360_MAX_LEVELS);
-    if ((rows % (1 << (params->n_levels - 1))) || (cols % (1 << (params->n_levels - 1))))
-        return fail(nullptr, R360_E_ARG, "r360_create: %dx%d is not divisible by 2^(n_levels-1)", cols, rows);
+    if ((rows % (1 << (params->n_levels - 1))) || (cols % (1 << params->n_levels)))
+        return fail(nullptr, R360_E_ARG, "r360_create: %dx%d: rows must be divisible by 2^(n_levels-1) and cols by 2^n_levels "
+                                         "(every level keeps an even width)", cols, rows);
     if (params->occlusion != 0)
         return fail(nullptr, R360_E_ARG, "r360_create: occlusion variants 1/2 (RPI.h:3232-4249) are not built; use 0");
     if (params->method < 0 || params->method > 2) return fail(nullptr, R360_E_ARG, "r360_create: bad method %d", params->method);
@@ -577,6 +594,25 @@ int r360_dump_warp(r360_ctx* c, int src, int trg, int level, const float pose[16
     if (e == cudaSuccess && valid_depth) e = cudaMemcpy(valid_depth, d_vd, n, cudaMemcpyDeviceToHost);
     cudaFree(d_r); cudaFree(d_c); cudaFree(d_vp); cudaFree(d_vd);
     if (e != cudaSuccess) return fail(c, R360_E_CUDA, "dump_warp: %s", cudaGetErrorString(e));
+    return R360_OK;
+}
+
+int r360_index_stats(r360_ctx* c, int src, int trg, int level, const float pose[16], uint64_t out[3]) {
+    if (!c || !out) return R360_E_ARG;
+    R360PassArgs a;
+    int rc = eval_setup(c, src, trg, level, pose, &a);
+    if (rc) return rc;
+    unsigned long long* d_out = nullptr;
+    CK(c, cudaMalloc(&d_out, 4 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_out, 0, 4 * sizeof(unsigned long long), c->st);
+    r360_launch_index_stats(c->st, a, c->max_pairs, d_out, c->sm_count);
+    ++c->launches;
+    unsigned long long h[4] = { 0, 0, 0, 0 };
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(c, R360_E_CUDA, "index_stats: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 3; ++k) out[k] = h[k];
     return R360_OK;
 }
 

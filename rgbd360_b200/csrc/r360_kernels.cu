@@ -147,94 +147,184 @@ k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long lo
 }
 
 // =========================================================================== K3: fused pixel pass
-// One work item = `px_per_item` consecutive source pixels of one active pair.  A persistent grid
-// strides over the (active pair, item) space; per item the CTA keeps 28 float partial sums and
-// 3 counters per thread, reduces them with warp shuffles + one shared-memory stage and issues
-// one double atomicAdd per sum into the pair's accumulator.
+// Source pixel addressing shared by the pass, dump and statistics kernels: thread-local pixel
+// pair (i, i+1) of a level, its (row, col) and the back-projected points of both pixels.
+struct R360SrcPair {
+    float2 X0, X1, X2;       // back-projected points, packed {pixel 0, pixel 1}
+    float2 Is;               // source gray
+    bool v0, v1;             // LUT point valid (RPI.h:4575: minDepth < d < maxDepth) and inside the range
+};
+
+__device__ __forceinline__ void r360_load_src_pair(const R360Level& lv, const r360_params& P, float4 s, int r, int c,
+                                                   bool in0, bool in1, R360SrcPair& o) {
+    // cols is even at every level (r360_create) and c is even: pixel 1 = (r, c + 1)
+    o.v0 = in0 && (P.min_depth < s.x && s.x < P.max_depth);
+    o.v1 = in1 && (P.min_depth < s.z && s.z < P.max_depth);
+    // invalid pixels carry a finite dummy point (weight 0 later): keeps every packed lane finite
+    const float2 d = make_float2(o.v0 ? s.x : 1.f, o.v1 ? s.z : 1.f);
+    o.Is = make_float2(s.y, s.w);
+    const float2 tp = __ldg(&lv.tab_p[min((unsigned)r, (unsigned)(lv.rows - 1))]);   // tail lanes: r may be == rows
+    const float4 tt = __ldg(&lv.tab_t[(unsigned)c >> 1]);
+    o.X0 = f2mul(d, R360_F2(tp.x));                                     // d sin(phi)
+    const float2 m = f2mul(d, R360_F2(tp.y));                           // -d cos(phi)
+    o.X1 = f2mul(m, make_float2(tt.x, tt.y));
+    o.X2 = f2mul(m, make_float2(tt.z, tt.w));
+}
+
+// Bit-exact (r', c') of a pixel pair: packed pinned sequence + scalar recomputation of the rare
+// pixels it flags (out-of-range operands, exact .5 ties).  Must be called by all 32 lanes of the
+// warp (warp vote).  T: registers; Ts: same pose in shared or global memory for the out-of-line path.
+__device__ __forceinline__ void r360_index_pair(const float* __restrict__ T, const float* Ts, const R360Level& lv,
+                                                const R360SrcPair& sp, float one, R360Geo2& g, int r[2], int c[2],
+                                                unsigned& n_fallback) {
+    unsigned need = r360_index_pair_packed(T, sp.X0, sp.X1, sp.X2, lv.res_inv, lv.half_rows, one, g, r, c);
+    need &= (sp.v0 ? 1u : 0u) | (sp.v1 ? 2u : 0u);
+    if (__any_sync(0xffffffffu, need != 0)) {
+        if (need & 1) {
+            const int2 rc = r360_index_exact(Ts, sp.X0.x, sp.X1.x, sp.X2.x, lv.res_inv, lv.half_rows);
+            r[0] = rc.x; c[0] = rc.y;
+        }
+        if (need & 2) {
+            const int2 rc = r360_index_exact(Ts, sp.X0.y, sp.X1.y, sp.X2.y, lv.res_inv, lv.half_rows);
+            r[1] = rc.x; c[1] = rc.y;
+        }
+        n_fallback += __popc(need);
+    }
+}
+
+// Work decomposition: the (active pair, pixel block) space is cut into `items` of px_per_item
+// pixels; every CTA of the persistent grid takes one CONTIGUOUS run of items, so it touches one
+// or two pairs, keeps its 28 packed partial sums in registers across the whole run and flushes
+// them (warp shuffles + shared memory + 28 double atomics) once per pair it touched.
+//
+// Per thread and iteration one pixel pair, software-pipelined through shared memory in two stages:
+//   stage A (pair k+1): LDG.128 of {depth, gray} x 2 (loaded two iterations ahead), back-projection,
+//            packed pinned index sequence, then the six 8-byte texel gathers are issued as
+//            cp.async (LDGSTS) straight into the thread's shared-memory slot and the warped
+//            geometry is parked next to them -- no register is held across the HBM round trip;
+//   stage B (pair k):   cp.async.wait_group, 6 x LDS.128, residuals / Jacobians / 56 FFMA2 of
+//            normal-equation accumulation.
+// Every thread reads only what it wrote itself, so the pipeline needs no block barrier.
+#define R360_SLOT_BYTES 48                                   // texels of 2 pixels = geometry of 2 pixels = 48 B
+#define R360_PASS_DYN_SMEM (2 * 2 * R360_PASS_THREADS * R360_SLOT_BYTES)
+
+__device__ __forceinline__ void r360_cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void r360_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void r360_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <int METHOD>
 __global__ void __launch_bounds__(R360_PASS_THREADS, 2)
 k_pass(R360PassArgs a) {
+    extern __shared__ float4 s_pipe[];                       // [stage][texel | geometry][thread][3]
     __shared__ float s_red[R360_PASS_THREADS / 32][R360_ACC_DOUBLES];
     __shared__ int s_cnt[R360_PASS_THREADS / 32][R360_ACC_INTS];
+    __shared__ float s_T[16];
     const R360Level lv = a.lv;
     const r360_params P = a.params;
     const float inv_std_photo = a.inv_std_photo;
-    const int n_items = (*a.n_active) * a.items_per_pair;
+    const int ipp = a.items_per_pair, ppi = a.px_per_item;
+    const int n_items = (*a.n_active) * ipp;
+    const int per = n_items / (int)gridDim.x, rem = n_items - per * (int)gridDim.x;
+    const int bid = (int)blockIdx.x;
+    int item = bid * per + min(bid, rem);
+    const int item_end = item + per + (bid < rem ? 1 : 0);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int STRIDE = 2 * R360_PASS_THREADS;
+    float4* const my_tex = s_pipe + 3 * threadIdx.x;                               // + stage * 6 * THREADS
+    float4* const my_geo = s_pipe + 3 * R360_PASS_THREADS + 3 * threadIdx.x;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ap = item / a.items_per_pair;
-        const int sub = item - ap * a.items_per_pair;
+    int ap = item / ipp;
+    int sub = item - ap * ipp;
+    while (item < item_end) {
+        const int n_seg = min(ipp - sub, item_end - item);          // items of pair `ap` in this run
         const int pair = a.active_list[ap];
         const R360Pair* __restrict__ ps = a.pairs + pair;
+        __syncthreads();                                             // s_T / s_red of the previous segment
+        if (threadIdx.x < 16) s_T[threadIdx.x] = ps->pose_eval[threadIdx.x];
         float T[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) T[k] = __ldg(&ps->pose_eval[k]);
-        const float2* __restrict__ src = a.src_base[pair] + lv.px_off;
+        __syncthreads();
+        const float4* __restrict__ src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
         const float2* __restrict__ trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
 
-        R360Acc A;
+        R360Acc2 A;
         r360_acc_zero(A);
         int n_vis = 0, n_photo = 0, n_depth = 0;
+        unsigned n_fb = 0;
 
-        const int i_end = min(lv.n, (sub + 1) * a.px_per_item);
-        // Batches of R360_PASS_U pixels per thread, staged so that the U source loads, then the U
-        // texel gathers, are in flight together (the two dependent HBM round trips per pixel are
-        // what bounds this kernel); the source loads of the next batch are prefetched.
-        int i0 = sub * a.px_per_item + threadIdx.x;
-        float2 sd[R360_PASS_U];
-#pragma unroll
-        for (int u = 0; u < R360_PASS_U; ++u) {
-            const int i = i0 + u * R360_PASS_THREADS;
-            sd[u] = i < i_end ? __ldg(&src[i]) : make_float2(0.f, 0.f);
-        }
-        for (; i0 < i_end; i0 += R360_PASS_THREADS * R360_PASS_U) {
-            float2 sdn[R360_PASS_U];
-#pragma unroll
-            for (int u = 0; u < R360_PASS_U; ++u) {
-                const int i = i0 + (u + R360_PASS_U) * R360_PASS_THREADS;
-                sdn[u] = i < i_end ? __ldg(&src[i]) : make_float2(0.f, 0.f);
+        const int p_begin = sub * ppi;
+        const int p_end = min(lv.n, (sub + n_seg) * ppi);
+        const int n_it = (p_end - p_begin + STRIDE - 1) / STRIDE;   // uniform over the CTA
+        int i = p_begin + 2 * (int)threadIdx.x;                      // pixel pair of the next stage A
+        int r = (int)(((unsigned long long)i * lv.div_magic) >> 40);
+        int c = i - r * lv.cols;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 s_cur = i < p_end ? __ldg(&src4[i >> 1]) : zero4;
+        float4 s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
+
+        // stage A: index of pixel pair (i, i+1), async gathers + geometry into slot `st`
+        auto stage_a = [&](int st) {
+            R360SrcPair sp;
+            r360_load_src_pair(lv, P, s_cur, r, c, i < p_end, i + 1 < p_end, sp);
+            R360Geo2 g;
+            int rr[2], cc[2];
+            r360_index_pair(T, s_T, lv, sp, a.one, g, rr, cc, n_fb);
+            // RPI.h:2683 / 2989 (no c' >= 0 test upstream; c' is never negative, the unsigned compare
+            // only guards memory)
+            const bool ok0 = sp.v0 && (unsigned)rr[0] < (unsigned)lv.rows && (unsigned)cc[0] < (unsigned)lv.cols;
+            const bool ok1 = sp.v1 && (unsigned)rr[1] < (unsigned)lv.rows && (unsigned)cc[1] < (unsigned)lv.cols;
+            const float2* tx0 = trg + 3u * (ok0 ? (unsigned)(rr[0] * lv.cols + cc[0]) : 0u);
+            const float2* tx1 = trg + 3u * (ok1 ? (unsigned)(rr[1] * lv.cols + cc[1]) : 0u);
+            float2* dst = reinterpret_cast<float2*>(my_tex + st * (6 * R360_PASS_THREADS));
+            r360_cp_async8(dst + 0, tx0); r360_cp_async8(dst + 1, tx0 + 1); r360_cp_async8(dst + 2, tx0 + 2);
+            r360_cp_async8(dst + 3, tx1); r360_cp_async8(dst + 4, tx1 + 1); r360_cp_async8(dst + 5, tx1 + 2);
+            r360_cp_async_commit();
+            float4* geo = my_geo + st * (6 * R360_PASS_THREADS);
+            geo[0] = make_float4(g.px.x, g.px.y, g.py.x, g.py.y);
+            geo[1] = make_float4(g.pz.x, g.pz.y, g.dinv.x, g.dinv.y);
+            // |p| > 0: its sign carries the in-bounds flag of the pixel
+            geo[2] = make_float4(sp.Is.x, sp.Is.y, ok0 ? g.dist.x : -g.dist.x, ok1 ? g.dist.y : -g.dist.y);
+            n_vis += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
+            // next pixel pair of this thread
+            i += STRIDE;
+            c += STRIDE;
+            while (c >= lv.cols) { c -= lv.cols; ++r; }
+        };
+
+        stage_a(0);
+        for (int k = 0; k < n_it; ++k) {
+            if (k + 1 < n_it) {
+                s_cur = s_nxt;
+                s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
+                stage_a((k + 1) & 1);
+            } else {
+                r360_cp_async_commit();                              // keeps "all but the newest group" == group k
             }
-            R360Warp w[R360_PASS_U];
-            bool ok[R360_PASS_U];
-            const float2* tx[R360_PASS_U];
-#pragma unroll
-            for (int u = 0; u < R360_PASS_U; ++u) {
-                const int i = i0 + u * R360_PASS_THREADS;
-                const float d = sd[u].x;
-                // LUT INVALID_POINT (RPI.h:4575,4585); out-of-range lanes of the tail carry d = 0
-                ok[u] = i < i_end && (P.min_depth < d && d < P.max_depth);
-                const int ii = ok[u] ? i : 0;
-                const int r = (int)(((unsigned long long)ii * lv.div_magic) >> 40);
-                const int c = ii - r * lv.cols;
-                float X[3];
-                r360_backproject(d, __ldg(&lv.sin_p[r]), __ldg(&lv.cos_p[r]), __ldg(&lv.sin_t[c]),
-                                 __ldg(&lv.cos_t[c]), X);
-                const bool inb = r360_warp_point(T, X, lv.res_inv, lv.half_rows, lv.rows, lv.cols, w[u]);
-                ok[u] = ok[u] && inb;
-                tx[u] = trg + 3 * (ok[u] ? ((size_t)w[u].r * lv.cols + w[u].c) : 0);
-            }
-            float2 t0[R360_PASS_U], t1[R360_PASS_U], t2[R360_PASS_U];
-#pragma unroll
-            for (int u = 0; u < R360_PASS_U; ++u) {
-                t0[u] = __ldg(tx[u]); t1[u] = __ldg(tx[u] + 1); t2[u] = __ldg(tx[u] + 2);
-            }
-#pragma unroll
-            for (int u = 0; u < R360_PASS_U; ++u) {
-                if (ok[u]) {
-                    ++n_vis;
-                    R360Row ph, dp;
-                    const int v = r360_rows<METHOD>(w[u], lv.res_inv, sd[u].y, t0[u].x, t0[u].y, t1[u].x, t1[u].y,
-                                                    t2[u].x, t2[u].y, P, inv_std_photo, ph, dp);
-                    if (v & 1) { r360_accumulate(A, ph); ++n_photo; }
-                    if (v & 2) { r360_accumulate(A, dp); ++n_depth; }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < R360_PASS_U; ++u) sd[u] = sdn[u];
+            r360_cp_async_wait1();
+            // stage B: pixel pair k
+            const int st = k & 1;
+            const float4* tex = my_tex + st * (6 * R360_PASS_THREADS);
+            const float4* geo = my_geo + st * (6 * R360_PASS_THREADS);
+            const float4 q0 = tex[0], q1 = tex[1], q2 = tex[2];
+            const float4 g0 = geo[0], g1 = geo[1], g2 = geo[2];
+            const float2 ta[3] = { make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y) };
+            const float2 tb[3] = { make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w) };
+            R360Geo2 g;
+            g.px = make_float2(g0.x, g0.y); g.py = make_float2(g0.z, g0.w);
+            g.pz = make_float2(g1.x, g1.y); g.dinv = make_float2(g1.z, g1.w);
+            g.dist = make_float2(fabsf(g2.z), fabsf(g2.w));
+            g.rho2 = f2fma(g.py, g.py, f2mul(g.pz, g.pz));
+            const bool ok0 = g2.z > 0.f, ok1 = g2.w > 0.f;
+            const unsigned v = r360_rows_pair<METHOD>(g, lv.res_inv, make_float2(g2.x, g2.y), ta, tb, ok0, ok1, P,
+                                                      inv_std_photo, A);
+            n_photo += (int)(v & 1u) + (int)((v >> 1) & 1u);
+            n_depth += (int)((v >> 2) & 1u) + (int)((v >> 3) & 1u);
         }
 
-        // ---- block reduction
+        // ---- flush: warp shuffles, one shared-memory stage, 28 double atomics per CTA and pair
         float acc[R360_ACC_DOUBLES];
         r360_acc_unpack(A, acc);
 #pragma unroll
@@ -247,24 +337,28 @@ k_pass(R360PassArgs a) {
         n_vis = __reduce_add_sync(0xffffffffu, n_vis);
         n_photo = __reduce_add_sync(0xffffffffu, n_photo);
         n_depth = __reduce_add_sync(0xffffffffu, n_depth);
-        if (lane == 0) { s_cnt[wid][0] = n_vis; s_cnt[wid][1] = n_photo; s_cnt[wid][2] = n_depth; }
+        n_fb = __reduce_add_sync(0xffffffffu, n_fb);
+        if (lane == 0) { s_cnt[wid][0] = n_vis; s_cnt[wid][1] = n_photo; s_cnt[wid][2] = n_depth; s_cnt[wid][3] = (int)n_fb; }
         __syncthreads();
         if (threadIdx.x < R360_ACC_DOUBLES) {
-            double s = 0.0;
+            double sum = 0.0;
 #pragma unroll
-            for (int k = 0; k < R360_PASS_THREADS / 32; ++k) s += (double)s_red[k][threadIdx.x];
-            atomicAdd(&a.acc[(size_t)pair * R360_ACC_DOUBLES + threadIdx.x], s);
-        } else if (threadIdx.x >= 32 && threadIdx.x < 35) {
-            int s = 0;
+            for (int k = 0; k < R360_PASS_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
+            atomicAdd(&a.acc[(size_t)pair * R360_ACC_DOUBLES + threadIdx.x], sum);
+        } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
+            int sum = 0;
 #pragma unroll
-            for (int k = 0; k < R360_PASS_THREADS / 32; ++k) s += s_cnt[k][threadIdx.x - 32];
-            atomicAdd(&a.cnt[(size_t)pair * R360_ACC_INTS + threadIdx.x - 32], s);
+            for (int k = 0; k < R360_PASS_THREADS / 32; ++k) sum += s_cnt[k][threadIdx.x - 32];
+            atomicAdd(&a.cnt[(size_t)pair * R360_ACC_INTS + threadIdx.x - 32], sum);
         }
-        __syncthreads();
+        item += n_seg;
+        ++ap;
+        sub = 0;
     }
 }
 
-// Parity hook: per source pixel the rounded target index and the validPixelsPhoto/Depth masks.
+// Parity hook: per source pixel the rounded target index and the validPixelsPhoto/Depth masks,
+// through the same index function as k_pass.  One warp-uniform loop; 2 pixels per thread.
 __global__ void __launch_bounds__(256)
 k_warp_dump(R360PassArgs a, int pair, int method, int32_t* __restrict__ r_idx, int32_t* __restrict__ c_idx,
             uint8_t* __restrict__ vphoto, uint8_t* __restrict__ vdepth) {
@@ -273,36 +367,88 @@ k_warp_dump(R360PassArgs a, int pair, int method, int32_t* __restrict__ r_idx, i
     const R360Pair* ps = a.pairs + pair;
     float T[16];
     for (int k = 0; k < 16; ++k) T[k] = ps->pose_eval[k];
-    const float2* src = a.src_base[pair] + lv.px_off;
+    const float4* src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
     const float2* trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lv.n; i += gridDim.x * blockDim.x) {
-        int rr = INT_MIN, cc = INT_MIN, v = 0;
-        const float2 sd = src[i];
-        if (P.min_depth < sd.x && sd.x < P.max_depth) {
-            const int r = (int)(((unsigned long long)i * lv.div_magic) >> 40);
-            const int c = i - r * lv.cols;
-            float X[3];
-            r360_backproject(sd.x, lv.sin_p[r], lv.cos_p[r], lv.sin_t[c], lv.cos_t[c], X);
-            R360Warp w;
-            const bool inb = r360_warp_point(T, X, lv.res_inv, lv.half_rows, lv.rows, lv.cols, w);
-            rr = w.r; cc = w.c;
-            if (inb) {
-                const float2* tx = trg + 3 * ((size_t)w.r * lv.cols + w.c);
-                const float2 t0 = tx[0], t1 = tx[1], t2 = tx[2];
-                R360Row ph, dp;
-                if (method == R360_PHOTO_CONSISTENCY)
-                    v = r360_rows<R360_PHOTO_CONSISTENCY>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, ph, dp);
-                else if (method == R360_DEPTH_CONSISTENCY)
-                    v = r360_rows<R360_DEPTH_CONSISTENCY>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, ph, dp);
-                else
-                    v = r360_rows<R360_PHOTO_DEPTH>(w, lv.res_inv, sd.y, t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, P, a.inv_std_photo, ph, dp);
-            }
+    const int stride = 2 * gridDim.x * blockDim.x;
+    for (int base = 0; base < lv.n; base += stride) {
+        const int i = base + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+        const bool in0 = i < lv.n, in1 = i + 1 < lv.n;
+        const int r = in0 ? (int)(((unsigned long long)i * lv.div_magic) >> 40) : 0;
+        const int c = in0 ? i - r * lv.cols : 0;
+        const float4 s = in0 ? src4[i >> 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        R360SrcPair sp;
+        r360_load_src_pair(lv, P, s, r, c, in0, in1, sp);
+        R360Geo2 g;
+        int rr[2], cc[2];
+        unsigned n_fb = 0;
+        r360_index_pair(T, ps->pose_eval, lv, sp, a.one, g, rr, cc, n_fb);
+        const bool ok0 = sp.v0 && (unsigned)rr[0] < (unsigned)lv.rows && (unsigned)cc[0] < (unsigned)lv.cols;
+        const bool ok1 = sp.v1 && (unsigned)rr[1] < (unsigned)lv.rows && (unsigned)cc[1] < (unsigned)lv.cols;
+        const float2* tx0 = trg + 3u * (ok0 ? (unsigned)(rr[0] * lv.cols + cc[0]) : 0u);
+        const float2* tx1 = trg + 3u * (ok1 ? (unsigned)(rr[1] * lv.cols + cc[1]) : 0u);
+        const float2 ta[3] = { tx0[0], tx0[1], tx0[2] }, tb[3] = { tx1[0], tx1[1], tx1[2] };
+        R360Acc2 A;
+        r360_acc_zero(A);
+        unsigned v;
+        if (method == R360_PHOTO_CONSISTENCY)
+            v = r360_rows_pair<R360_PHOTO_CONSISTENCY>(g, lv.res_inv, sp.Is, ta, tb, ok0, ok1, P, a.inv_std_photo, A);
+        else if (method == R360_DEPTH_CONSISTENCY)
+            v = r360_rows_pair<R360_DEPTH_CONSISTENCY>(g, lv.res_inv, sp.Is, ta, tb, ok0, ok1, P, a.inv_std_photo, A);
+        else
+            v = r360_rows_pair<R360_PHOTO_DEPTH>(g, lv.res_inv, sp.Is, ta, tb, ok0, ok1, P, a.inv_std_photo, A);
+        if (in0) {
+            if (r_idx) r_idx[i] = sp.v0 ? rr[0] : INT_MIN;
+            if (c_idx) c_idx[i] = sp.v0 ? cc[0] : INT_MIN;
+            if (vphoto) vphoto[i] = (uint8_t)(v & 1u);
+            if (vdepth) vdepth[i] = (uint8_t)((v >> 2) & 1u);
         }
-        if (r_idx) r_idx[i] = rr;
-        if (c_idx) c_idx[i] = cc;
-        if (vphoto) vphoto[i] = (uint8_t)(v & 1);
-        if (vdepth) vdepth[i] = (uint8_t)((v >> 1) & 1);
+        if (in1) {
+            if (r_idx) r_idx[i + 1] = sp.v1 ? rr[1] : INT_MIN;
+            if (c_idx) c_idx[i + 1] = sp.v1 ? cc[1] : INT_MIN;
+            if (vphoto) vphoto[i + 1] = (uint8_t)((v >> 1) & 1u);
+            if (vdepth) vdepth[i + 1] = (uint8_t)((v >> 3) & 1u);
+        }
     }
+}
+
+// Cross-check of the packed index path against the scalar pinned sequence over every valid source
+// pixel of one pair: out[0] = valid pixels, out[1] = pixels the packed path sent to the scalar path,
+// out[2] = pixels it kept whose (r', c') differ from the scalar result (must be 0).
+__global__ void __launch_bounds__(256)
+k_index_stats(R360PassArgs a, int pair, unsigned long long* __restrict__ out) {
+    const R360Level lv = a.lv;
+    const r360_params P = a.params;
+    const R360Pair* ps = a.pairs + pair;
+    float T[16];
+    for (int k = 0; k < 16; ++k) T[k] = ps->pose_eval[k];
+    const float4* src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
+    unsigned long long n_valid = 0, n_fb = 0, n_bad = 0;
+    const int stride = 2 * gridDim.x * blockDim.x;
+    for (int base = 0; base < lv.n; base += stride) {
+        const int i = base + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+        const bool in0 = i < lv.n, in1 = i + 1 < lv.n;
+        const int r = in0 ? (int)(((unsigned long long)i * lv.div_magic) >> 40) : 0;
+        const int c = in0 ? i - r * lv.cols : 0;
+        const float4 s = in0 ? src4[i >> 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        R360SrcPair sp;
+        r360_load_src_pair(lv, P, s, r, c, in0, in1, sp);
+        R360Geo2 g;
+        int rf[2], cf[2];
+        const unsigned need = r360_index_pair_packed(T, sp.X0, sp.X1, sp.X2, lv.res_inv, lv.half_rows, a.one, g, rf, cf);
+        for (int q = 0; q < 2; ++q) {
+            if (!(q ? sp.v1 : sp.v0)) continue;
+            const float X[3] = { q ? sp.X0.y : sp.X0.x, q ? sp.X1.y : sp.X1.x, q ? sp.X2.y : sp.X2.x };
+            int re, ce;
+            float vre, vce;
+            r360_index_exact_inl(T, X, lv.res_inv, lv.half_rows, re, ce, vre, vce);
+            ++n_valid;
+            if (need & (1u << q)) ++n_fb;
+            else if (re != rf[q] || ce != cf[q]) ++n_bad;
+        }
+    }
+    atomicAdd(&out[0], n_valid);
+    atomicAdd(&out[1], n_fb);
+    atomicAdd(&out[2], n_bad);
 }
 
 // =========================================================================== K4: Gauss-Newton state machine
@@ -526,16 +672,26 @@ void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, l
     dim3 grid(r360_blocks((long long)rows * cols, 256, sm_count * 8), n_frames);
     k_texel<<<grid, 256, 0, st>>>(pyr, trg, off, rows, cols, n_sensors);
 }
+// The pass kernel's pipeline slots need more than the 48 KB default of dynamic shared memory.
+cudaError_t r360_pass_init() {
+    cudaError_t e = cudaFuncSetAttribute(k_pass<R360_PHOTO_CONSISTENCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_PASS_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass<R360_DEPTH_CONSISTENCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_PASS_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass<R360_PHOTO_DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_PASS_DYN_SMEM);
+    return e;
+}
 void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid) {
     switch (a.params.method) {
-        case R360_PHOTO_CONSISTENCY: k_pass<R360_PHOTO_CONSISTENCY><<<grid, R360_PASS_THREADS, 0, st>>>(a); break;
-        case R360_DEPTH_CONSISTENCY: k_pass<R360_DEPTH_CONSISTENCY><<<grid, R360_PASS_THREADS, 0, st>>>(a); break;
-        default: k_pass<R360_PHOTO_DEPTH><<<grid, R360_PASS_THREADS, 0, st>>>(a); break;
+        case R360_PHOTO_CONSISTENCY: k_pass<R360_PHOTO_CONSISTENCY><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
+        case R360_DEPTH_CONSISTENCY: k_pass<R360_DEPTH_CONSISTENCY><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
+        default: k_pass<R360_PHOTO_DEPTH><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
     }
 }
 void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
                            uint8_t* vp, uint8_t* vd, int sm_count) {
-    k_warp_dump<<<r360_blocks(a.lv.n, 256, sm_count * 8), 256, 0, st>>>(a, pair, a.params.method, r_idx, c_idx, vp, vd);
+    k_warp_dump<<<r360_blocks((a.lv.n + 1) / 2, 256, sm_count * 8), 256, 0, st>>>(a, pair, a.params.method, r_idx, c_idx, vp, vd);
+}
+void r360_launch_index_stats(cudaStream_t st, const R360PassArgs& a, int pair, unsigned long long* out, int sm_count) {
+    k_index_stats<<<r360_blocks((a.lv.n + 1) / 2, 256, sm_count * 8), 256, 0, st>>>(a, pair, out);
 }
 void r360_launch_pairs_init(cudaStream_t st, const R360GnArgs& g, const int32_t* src_idx, const int32_t* trg_idx,
                             const float* init_pose) {

@@ -3,12 +3,12 @@
 #include "r360_device.cuh"
 
 #define R360_PASS_THREADS 256
-#define R360_PASS_U 4        // pixels per thread per batch in k_pass
 
 struct R360PassArgs {
     R360Level lv;
     r360_params params;
     float inv_std_photo;                // (float)(1./stdDevPhoto), RPI.h:2774
+    float one;                          // 1.0f, opaque to the compiler (see f2add_sep)
     int items_per_pair, px_per_item;
     const int* n_active;                // device
     const int* active_list;             // device
@@ -36,9 +36,11 @@ void r360_launch_down(cudaStream_t st, float2* const* pyr, long long off_src, lo
                       int cols, float min_d, float max_d, int n_frames, int sm_count);
 void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, long long off, int rows, int cols,
                        int n_sensors, int n_frames, int sm_count);
+cudaError_t r360_pass_init();
 void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid);
 void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
                            uint8_t* vp, uint8_t* vd, int sm_count);
+void r360_launch_index_stats(cudaStream_t st, const R360PassArgs& a, int pair, unsigned long long* out, int sm_count);
 void r360_launch_pairs_init(cudaStream_t st, const R360GnArgs& g, const int32_t* src_idx, const int32_t* trg_idx,
                             const float* init_pose);
 void r360_launch_level_begin(cudaStream_t st, const R360GnArgs& g, int level);

@@ -5,7 +5,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "librgbd360_b200.so")
+# R360_LIB: development override (kernel variants built side by side); the product is the in-tree library
+_SO = os.environ.get("R360_LIB") or os.path.join(_HERE, "librgbd360_b200.so")
 
 R360_MAX_LEVELS = 8
 PHOTO_CONSISTENCY, DEPTH_CONSISTENCY, PHOTO_DEPTH = 0, 1, 2
@@ -17,7 +18,7 @@ EXPORTS = [
     "r360_eval_hessgrad", "r360_dump_level", "r360_dump_source_level", "r360_dump_warp",
     "r360_synth_frames_dev", "r360_synth_frames", "r360_synth_gt_pose", "r360_device_alloc",
     "r360_device_free", "r360_synchronize", "r360_last_device_ms", "r360_kernel_launches",
-    "r360_last_pass_stats", "r360_version",
+    "r360_last_pass_stats", "r360_version", "r360_index_stats",
 ]
 
 
@@ -105,6 +106,7 @@ def lib():
     L.r360_synth_frames.argtypes = [vp, i32, i32, i32, vp, vp]
     L.r360_synth_gt_pose.argtypes = [i32, i32, i32, vp]
     L.r360_synth_gt_pose.restype = None
+    L.r360_index_stats.argtypes = [vp, i32, i32, i32, vp, vp]
     L.r360_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.r360_device_free.argtypes = [vp, vp]
     L.r360_synchronize.argtypes = [vp]
@@ -252,6 +254,13 @@ class Context:
         T = pose_to_colmajor(pose)
         self._ck(self.L.r360_dump_warp(self.h, src, trg, level, _p(T), _p(ri), _p(ci), _p(vp), _p(vd)))
         return ri, ci, vp, vd
+
+    def index_stats(self, src, trg, level, pose):
+        """Packed vs scalar pinned index path (see include/r360.h): dict(valid, scalar, mismatch)."""
+        out = np.zeros(3, np.uint64)
+        T = pose_to_colmajor(pose)
+        self._ck(self.L.r360_index_stats(self.h, src, trg, level, _p(T), _p(out)))
+        return dict(valid=int(out[0]), scalar=int(out[1]), mismatch=int(out[2]))
 
     # ---- plumbing
     def synchronize(self):

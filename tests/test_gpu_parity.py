@@ -73,6 +73,20 @@ def test_warp_maps_bit_exact(pair_small, pi):
         assert np.array_equal(vdo, vdg)
 
 
+def test_packed_index_path(pair_small):
+    """The packed (2 pixels per thread) pinned index sequence never disagrees with the scalar one,
+    and sends only a small share of pixels (range guards, exact .5 ties) to the scalar code."""
+    ctx = pair_small["ctx"]
+    rng = np.random.default_rng(7)
+    poses = list(POSES) + [small_pose(*(rng.uniform(-1, 1, 3) * 0.5), *(rng.uniform(-1, 1, 3) * 1.5)) for _ in range(6)]
+    for T in poses:
+        for level in range(pair_small["L"]):
+            st = ctx.index_stats(0, 1, level, T)
+            assert st["valid"] > 0
+            assert st["mismatch"] == 0, st
+            assert st["scalar"] < 0.01 * st["valid"] + 8, st
+
+
 @pytest.mark.parametrize("pi", range(len(POSES)))
 def test_error_and_hessgrad(pair_small, pi):
     """a8/a9: counts bit-exact, sums within 1e-4 relative."""
@@ -307,6 +321,11 @@ def test_full_size_properties(orc, r360):
         single = ctx.register_pairs([src_idx[k]], [trg_idx[k]])[0]
         assert np.allclose(single["pose"], res[k]["pose"], atol=1e-6)
         assert list(single["iters"]) == list(res[k]["iters"])
+    # packed index path at full size: identical to the scalar pinned sequence on every pixel it keeps
+    for level in range(L):
+        for T in (POSES[0], POSES[1], POSES[2], np.array(res[0]["pose"], np.float32).reshape(4, 4).T):
+            st = ctx.index_stats(1, 0, level, T)
+            assert st["mismatch"] == 0 and st["scalar"] < 0.01 * st["valid"], (level, st)
     k = 1
     trg = orc.Frame(rgb[2 * k], dep[2 * k], P, True); src = orc.Frame(rgb[2 * k + 1], dep[2 * k + 1], P, False)
     T = np.array(res[k]["pose"], np.float32).reshape(4, 4).T
