@@ -346,6 +346,8 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
         R360Level& v = c->lv[l];
         v.rows = rows >> l; v.cols = cols >> l; v.n = v.rows * v.cols;
         v.div_magic = ((1ULL << 40) + v.cols - 1) / v.cols;
+        v.stride_r = (2 * R360_PASS_THREADS) / v.cols;
+        v.stride_c = (2 * R360_PASS_THREADS) % v.cols;
         v.px_off = off; off += v.n;
         v.res = (float)(2 * R360_PI_D / v.cols);
         v.res_inv = 1 / v.res;

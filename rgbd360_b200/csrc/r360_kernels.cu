@@ -158,8 +158,8 @@ struct R360SrcPair {
 __device__ __forceinline__ void r360_load_src_pair(const R360Level& lv, const r360_params& P, float4 s, int r, int c,
                                                    bool in0, bool in1, R360SrcPair& o) {
     // cols is even at every level (r360_create) and c is even: pixel 1 = (r, c + 1)
-    o.v0 = in0 && (P.min_depth < s.x && s.x < P.max_depth);
-    o.v1 = in1 && (P.min_depth < s.z && s.z < P.max_depth);
+    o.v0 = in0 & (P.min_depth < s.x) & (s.x < P.max_depth);
+    o.v1 = in1 & (P.min_depth < s.z) & (s.z < P.max_depth);
     // invalid pixels carry a finite dummy point (weight 0 later): keeps every packed lane finite
     const float2 d = make_float2(o.v0 ? s.x : 1.f, o.v1 ? s.z : 1.f);
     o.Is = make_float2(s.y, s.w);
@@ -220,7 +220,7 @@ k_pass(R360PassArgs a) {
     extern __shared__ float4 s_pipe[];                       // [stage][texel | geometry][thread][3]
     __shared__ float s_red[R360_PASS_THREADS / 32][R360_ACC_DOUBLES];
     __shared__ int s_cnt[R360_PASS_THREADS / 32][R360_ACC_INTS];
-    __shared__ float s_T[16];
+    __shared__ __align__(16) float s_T[16];
     const R360Level lv = a.lv;
     const r360_params P = a.params;
     const float inv_std_photo = a.inv_std_photo;
@@ -243,9 +243,6 @@ k_pass(R360PassArgs a) {
         const R360Pair* __restrict__ ps = a.pairs + pair;
         __syncthreads();                                             // s_T / s_red of the previous segment
         if (threadIdx.x < 16) s_T[threadIdx.x] = ps->pose_eval[threadIdx.x];
-        float T[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) T[k] = __ldg(&ps->pose_eval[k]);
         __syncthreads();
         const float4* __restrict__ src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
         const float2* __restrict__ trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
@@ -271,11 +268,22 @@ k_pass(R360PassArgs a) {
             r360_load_src_pair(lv, P, s_cur, r, c, i < p_end, i + 1 < p_end, sp);
             R360Geo2 g;
             int rr[2], cc[2];
+#ifdef R360_T_IN_REGS
             r360_index_pair(T, s_T, lv, sp, a.one, g, rr, cc, n_fb);
+#else
+            float T[16];                                             // pose: 3 x LDS.128 per iteration, no long-lived registers
+            {
+                const float4 c0 = reinterpret_cast<const float4*>(s_T)[0], c1 = reinterpret_cast<const float4*>(s_T)[1],
+                             c2 = reinterpret_cast<const float4*>(s_T)[2], c3 = reinterpret_cast<const float4*>(s_T)[3];
+                T[0] = c0.x; T[1] = c0.y; T[2] = c0.z; T[4] = c1.x; T[5] = c1.y; T[6] = c1.z;
+                T[8] = c2.x; T[9] = c2.y; T[10] = c2.z; T[12] = c3.x; T[13] = c3.y; T[14] = c3.z;
+            }
+            r360_index_pair(T, s_T, lv, sp, a.one, g, rr, cc, n_fb);
+#endif
             // RPI.h:2683 / 2989 (no c' >= 0 test upstream; c' is never negative, the unsigned compare
             // only guards memory)
-            const bool ok0 = sp.v0 && (unsigned)rr[0] < (unsigned)lv.rows && (unsigned)cc[0] < (unsigned)lv.cols;
-            const bool ok1 = sp.v1 && (unsigned)rr[1] < (unsigned)lv.rows && (unsigned)cc[1] < (unsigned)lv.cols;
+            const bool ok0 = sp.v0 & ((unsigned)rr[0] < (unsigned)lv.rows) & ((unsigned)cc[0] < (unsigned)lv.cols);
+            const bool ok1 = sp.v1 & ((unsigned)rr[1] < (unsigned)lv.rows) & ((unsigned)cc[1] < (unsigned)lv.cols);
             const float2* tx0 = trg + 3u * (ok0 ? (unsigned)(rr[0] * lv.cols + cc[0]) : 0u);
             const float2* tx1 = trg + 3u * (ok1 ? (unsigned)(rr[1] * lv.cols + cc[1]) : 0u);
             float2* dst = reinterpret_cast<float2*>(my_tex + st * (6 * R360_PASS_THREADS));
@@ -290,8 +298,9 @@ k_pass(R360PassArgs a) {
             n_vis += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
             // next pixel pair of this thread
             i += STRIDE;
-            c += STRIDE;
-            while (c >= lv.cols) { c -= lv.cols; ++r; }
+            r += lv.stride_r;
+            c += lv.stride_c;
+            if (c >= lv.cols) { c -= lv.cols; ++r; }
         };
 
         stage_a(0);
