@@ -177,18 +177,20 @@ __device__ __forceinline__ void r360_load_src_pair(const R360Level& lv, const r3
 __device__ __forceinline__ void r360_index_pair(const float* __restrict__ T, const float* Ts, const R360Level& lv,
                                                 const R360SrcPair& sp, float one, R360Geo2& g, int r[2], int c[2],
                                                 unsigned& n_fallback) {
-    unsigned need = r360_index_pair_packed(T, sp.X0, sp.X1, sp.X2, lv.res_inv, lv.half_rows, one, g, r, c);
-    need &= (sp.v0 ? 1u : 0u) | (sp.v1 ? 2u : 0u);
-    if (__any_sync(0xffffffffu, need != 0)) {
-        if (need & 1) {
+    bool bad[2];
+    r360_index_pair_packed(T, sp.X0, sp.X1, sp.X2, lv.res_inv, lv.half_rows, one, g, r, c, bad);
+    const bool need0 = bad[0] & sp.v0, need1 = bad[1] & sp.v1;
+    if (__any_sync(0xffffffffu, need0 | need1)) {
+        if (need0) {
             const int2 rc = r360_index_exact(Ts, sp.X0.x, sp.X1.x, sp.X2.x, lv.res_inv, lv.half_rows);
             r[0] = rc.x; c[0] = rc.y;
+            ++n_fallback;
         }
-        if (need & 2) {
+        if (need1) {
             const int2 rc = r360_index_exact(Ts, sp.X0.y, sp.X1.y, sp.X2.y, lv.res_inv, lv.half_rows);
             r[1] = rc.x; c[1] = rc.y;
+            ++n_fallback;
         }
-        n_fallback += __popc(need);
     }
 }
 
@@ -208,8 +210,23 @@ __device__ __forceinline__ void r360_index_pair(const float* __restrict__ T, con
 #define R360_SLOT_BYTES 48                                   // texels of 2 pixels = geometry of 2 pixels = 48 B
 #define R360_PASS_DYN_SMEM (2 * 2 * R360_PASS_THREADS * R360_SLOT_BYTES)
 
-__device__ __forceinline__ void r360_cp_async8(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+// Shared-memory accesses of the pipeline go through explicit 32-bit shared addresses held in a
+// register (the compiler otherwise re-derives them from %tid every iteration).
+__device__ __forceinline__ unsigned r360_smem_addr(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ void r360_cp_async8(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void r360_sts128(unsigned smem, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 r360_lds128(unsigned smem) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem) : "memory");
+    return v;
 }
 __device__ __forceinline__ void r360_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void r360_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -232,8 +249,9 @@ k_pass(R360PassArgs a) {
     const int item_end = item + per + (bid < rem ? 1 : 0);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int STRIDE = 2 * R360_PASS_THREADS;
-    float4* const my_tex = s_pipe + 3 * threadIdx.x;                               // + stage * 6 * THREADS
-    float4* const my_geo = s_pipe + 3 * R360_PASS_THREADS + 3 * threadIdx.x;
+    // this thread's slots: stage s at + s * STAGE_BYTES; texels at +0, geometry at + GEO_OFF
+    constexpr unsigned STAGE_BYTES = 2 * R360_PASS_THREADS * R360_SLOT_BYTES, GEO_OFF = R360_PASS_THREADS * R360_SLOT_BYTES;
+    const unsigned slot0 = r360_smem_addr(reinterpret_cast<char*>(s_pipe) + R360_SLOT_BYTES * threadIdx.x);
 
     int ap = item / ipp;
     int sub = item - ap * ipp;
@@ -263,7 +281,7 @@ k_pass(R360PassArgs a) {
         float4 s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
 
         // stage A: index of pixel pair (i, i+1), async gathers + geometry into slot `st`
-        auto stage_a = [&](int st) {
+        auto stage_a = [&](unsigned st) {                            // st: byte offset of the stage
             R360SrcPair sp;
             r360_load_src_pair(lv, P, s_cur, r, c, i < p_end, i + 1 < p_end, sp);
             R360Geo2 g;
@@ -286,15 +304,14 @@ k_pass(R360PassArgs a) {
             const bool ok1 = sp.v1 & ((unsigned)rr[1] < (unsigned)lv.rows) & ((unsigned)cc[1] < (unsigned)lv.cols);
             const float2* tx0 = trg + 3u * (ok0 ? (unsigned)(rr[0] * lv.cols + cc[0]) : 0u);
             const float2* tx1 = trg + 3u * (ok1 ? (unsigned)(rr[1] * lv.cols + cc[1]) : 0u);
-            float2* dst = reinterpret_cast<float2*>(my_tex + st * (6 * R360_PASS_THREADS));
-            r360_cp_async8(dst + 0, tx0); r360_cp_async8(dst + 1, tx0 + 1); r360_cp_async8(dst + 2, tx0 + 2);
-            r360_cp_async8(dst + 3, tx1); r360_cp_async8(dst + 4, tx1 + 1); r360_cp_async8(dst + 5, tx1 + 2);
+            const unsigned dst = slot0 + st;
+            r360_cp_async8(dst + 0, tx0); r360_cp_async8(dst + 8, tx0 + 1); r360_cp_async8(dst + 16, tx0 + 2);
+            r360_cp_async8(dst + 24, tx1); r360_cp_async8(dst + 32, tx1 + 1); r360_cp_async8(dst + 40, tx1 + 2);
             r360_cp_async_commit();
-            float4* geo = my_geo + st * (6 * R360_PASS_THREADS);
-            geo[0] = make_float4(g.px.x, g.px.y, g.py.x, g.py.y);
-            geo[1] = make_float4(g.pz.x, g.pz.y, g.dinv.x, g.dinv.y);
+            r360_sts128(dst + GEO_OFF, make_float4(g.px.x, g.px.y, g.py.x, g.py.y));
+            r360_sts128(dst + GEO_OFF + 16, make_float4(g.pz.x, g.pz.y, g.dinv.x, g.dinv.y));
             // |p| > 0: its sign carries the in-bounds flag of the pixel
-            geo[2] = make_float4(sp.Is.x, sp.Is.y, ok0 ? g.dist.x : -g.dist.x, ok1 ? g.dist.y : -g.dist.y);
+            r360_sts128(dst + GEO_OFF + 32, make_float4(sp.Is.x, sp.Is.y, ok0 ? g.dist.x : -g.dist.x, ok1 ? g.dist.y : -g.dist.y));
             n_vis += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
             // next pixel pair of this thread
             i += STRIDE;
@@ -303,22 +320,22 @@ k_pass(R360PassArgs a) {
             if (c >= lv.cols) { c -= lv.cols; ++r; }
         };
 
-        stage_a(0);
+        stage_a(0u);
+        unsigned st_b = 0u;                                          // stage of pixel pair k
         for (int k = 0; k < n_it; ++k) {
             if (k + 1 < n_it) {
                 s_cur = s_nxt;
                 s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
-                stage_a((k + 1) & 1);
+                stage_a(st_b ^ STAGE_BYTES);
             } else {
                 r360_cp_async_commit();                              // keeps "all but the newest group" == group k
             }
             r360_cp_async_wait1();
             // stage B: pixel pair k
-            const int st = k & 1;
-            const float4* tex = my_tex + st * (6 * R360_PASS_THREADS);
-            const float4* geo = my_geo + st * (6 * R360_PASS_THREADS);
-            const float4 q0 = tex[0], q1 = tex[1], q2 = tex[2];
-            const float4 g0 = geo[0], g1 = geo[1], g2 = geo[2];
+            const unsigned rd = slot0 + st_b;
+            st_b ^= STAGE_BYTES;
+            const float4 q0 = r360_lds128(rd), q1 = r360_lds128(rd + 16), q2 = r360_lds128(rd + 32);
+            const float4 g0 = r360_lds128(rd + GEO_OFF), g1 = r360_lds128(rd + GEO_OFF + 16), g2 = r360_lds128(rd + GEO_OFF + 32);
             const float2 ta[3] = { make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y) };
             const float2 tb[3] = { make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w) };
             R360Geo2 g;
@@ -443,7 +460,9 @@ k_index_stats(R360PassArgs a, int pair, unsigned long long* __restrict__ out) {
         r360_load_src_pair(lv, P, s, r, c, in0, in1, sp);
         R360Geo2 g;
         int rf[2], cf[2];
-        const unsigned need = r360_index_pair_packed(T, sp.X0, sp.X1, sp.X2, lv.res_inv, lv.half_rows, a.one, g, rf, cf);
+        bool bad[2];
+        r360_index_pair_packed(T, sp.X0, sp.X1, sp.X2, lv.res_inv, lv.half_rows, a.one, g, rf, cf, bad);
+        const unsigned need = (bad[0] ? 1u : 0u) | (bad[1] ? 2u : 0u);
         for (int q = 0; q < 2; ++q) {
             if (!(q ? sp.v1 : sp.v0)) continue;
             const float X[3] = { q ? sp.X0.y : sp.X0.x, q ? sp.X1.y : sp.X1.x, q ? sp.X2.y : sp.X2.x };

@@ -14,7 +14,7 @@ __global__ void k(unsigned long long* out, int iters, const float* Tg, float one
         float X[3] = { (rnd01(s) - 0.5f) * 8.f, (rnd01(s) - 0.5f) * 8.f, (rnd01(s) - 0.5f) * 8.f };
         float Y[3] = { (rnd01(s) - 0.5f) * 8.f, (rnd01(s) - 0.5f) * 8.f, (rnd01(s) - 0.5f) * 8.f };
         R360Geo2 g; int r[2], c[2];
-        unsigned need = r360_index_pair_packed(T, make_float2(X[0], Y[0]), make_float2(X[1], Y[1]), make_float2(X[2], Y[2]), res_inv, half_rows, one, g, r, c);
+        bool bad2[2]; r360_index_pair_packed(T, make_float2(X[0], Y[0]), make_float2(X[1], Y[1]), make_float2(X[2], Y[2]), res_inv, half_rows, one, g, r, c, bad2); unsigned need = (bad2[0] ? 1u : 0u) | (bad2[1] ? 2u : 0u);
         // scalar pinned, step by step (copy of r360_index_exact_inl)
         const float px = ((T[0] * X[0] + T[4] * X[1]) + T[8] * X[2]) + T[12];
         const float py = ((T[1] * X[0] + T[5] * X[1]) + T[9] * X[2]) + T[13];
