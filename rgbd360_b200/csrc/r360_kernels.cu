@@ -72,77 +72,129 @@ __device__ __forceinline__ int r360_reflect101(int i, int n) {
 
 // Level l-1 -> l: gray = cv::pyrDown (5x5 Gaussian, REFLECT_101, RPI.h:303), depth = mean of the
 // 2x2 parents inside (minDepth, maxDepth) else 0 (RPI.h:322-350).  Same op order as the oracle.
+// One thread = one output column x of a strip of R360_DOWN_R output rows: it walks down the source
+// rows with a rolling window of five horizontally filtered values in registers, so every source
+// row costs three 16-byte loads ({depth, gray} of columns 2x-2 .. 2x+3; lanes are consecutive x,
+// so a warp reads one contiguous 512-byte span per load) and every output needs two new rows.
+#define R360_DOWN_R 8
+struct R360HRow { float h, dl, dr; };    // filtered gray, depth of source columns 2x and 2x+1
+__device__ __forceinline__ R360HRow r360_down_hrow(const float2* __restrict__ s, int sr, int rows, int cols, int x) {
+    const float2* row = s + (size_t)r360_reflect101(sr, rows) * cols;
+    float c0, c1, c2, c3, c4;
+    R360HRow o;
+    if (x > 0 && 2 * x + 2 < cols) {
+        const float4 A = __ldg(reinterpret_cast<const float4*>(row + 2 * x - 2));
+        const float4 B = __ldg(reinterpret_cast<const float4*>(row + 2 * x));
+        const float4 C = __ldg(reinterpret_cast<const float4*>(row + 2 * x + 2));
+        c0 = A.y; c1 = A.w; c2 = B.y; c3 = B.w; c4 = C.y;
+        o.dl = B.x; o.dr = B.z;
+    } else {                                                         // image border columns: REFLECT_101
+        const float4 B = __ldg(reinterpret_cast<const float4*>(row + 2 * x));
+        c0 = __ldg(&row[r360_reflect101(2 * x - 2, cols)]).y;
+        c1 = __ldg(&row[r360_reflect101(2 * x - 1, cols)]).y;
+        c2 = B.y; c3 = B.w;
+        c4 = __ldg(&row[r360_reflect101(2 * x + 2, cols)]).y;
+        o.dl = B.x; o.dr = B.z;
+    }
+    o.h = c2 * 6 + (c1 + c3) * 4 + c0 + c4;
+    return o;
+}
 __global__ void __launch_bounds__(256)
 k_down(float2* const* __restrict__ pyr, long long off_src, long long off_dst, int rows, int cols,
        float min_d, float max_d) {
     const int f = blockIdx.y;
     const float2* __restrict__ s = pyr[f] + off_src;
     float2* __restrict__ o = pyr[f] + off_dst;
-    const int h = rows >> 1, w = cols >> 1, n = h * w;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int y = i / w, x = i - y * w;
-        const int c0 = r360_reflect101(2 * x - 2, cols), c1 = r360_reflect101(2 * x - 1, cols), c2 = 2 * x,
-                  c3 = r360_reflect101(2 * x + 1, cols), c4 = r360_reflect101(2 * x + 2, cols);
-        float hrow[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const float2* row = s + (size_t)r360_reflect101(2 * y - 2 + k, rows) * cols;
-            hrow[k] = __ldg(&row[c2]).y * 6 + (__ldg(&row[c1]).y + __ldg(&row[c3]).y) * 4 + __ldg(&row[c0]).y +
-                      __ldg(&row[c4]).y;
+    const int h = rows >> 1, w = cols >> 1;
+    const int n_strips = (h + R360_DOWN_R - 1) / R360_DOWN_R;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < w * n_strips; t += gridDim.x * blockDim.x) {
+        const int strip = t / w, x = t - strip * w;
+        const int y0 = strip * R360_DOWN_R, y1 = min(h, y0 + R360_DOWN_R);
+        float hm2 = r360_down_hrow(s, 2 * y0 - 2, rows, cols, x).h;
+        float hm1 = r360_down_hrow(s, 2 * y0 - 1, rows, cols, x).h;
+        R360HRow r0 = r360_down_hrow(s, 2 * y0, rows, cols, x);
+        for (int y = y0; y < y1; ++y) {
+            const R360HRow r1 = r360_down_hrow(s, 2 * y + 1, rows, cols, x);
+            const R360HRow r2 = r360_down_hrow(s, 2 * y + 2, rows, cols, x);
+            const float a = (hm2 + r2.h) + (r0.h + r0.h);
+            const float b = ((hm1 + r1.h) + r0.h) * 4.0f;
+            const float gray = (a + b) * (1.f / 256);
+            float av = 0.f;
+            unsigned cnt = 0;
+            if (r0.dl > min_d && r0.dl < max_d) { av += r0.dl; ++cnt; }
+            if (r0.dr > min_d && r0.dr < max_d) { av += r0.dr; ++cnt; }
+            if (r1.dl > min_d && r1.dl < max_d) { av += r1.dl; ++cnt; }
+            if (r1.dr > min_d && r1.dr < max_d) { av += r1.dr; ++cnt; }
+            const float depth = cnt > 0 ? av / cnt : 0.f;
+            o[(size_t)y * w + x] = make_float2(depth, gray);
+            hm2 = r0.h; hm1 = r1.h; r0 = r2;
         }
-        const float a = (hrow[0] + hrow[4]) + (hrow[2] + hrow[2]);
-        const float b = ((hrow[1] + hrow[3]) + hrow[2]) * 4.0f;
-        const float gray = (a + b) * (1.f / 256);
-        float av = 0.f;
-        unsigned cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float z = __ldg(&s[(size_t)(2 * y + (k >> 1)) * cols + 2 * x + (k & 1)]).x;
-            if (z > min_d && z < max_d) { av += z; ++cnt; }
-        }
-        const float depth = cnt > 0 ? av / cnt : 0.f;
-        o[i] = make_float2(depth, gray);
     }
 }
 
 // calcGradientXY (RPI.h:365-398): harmonic mean of the one-sided differences on strictly
-// monotone triples, 0 elsewhere and on the border.
+// monotone triples, 0 elsewhere and on the border:  g = 2 / (1/(nxt - v) + 1/(v - prv)).
+// Evaluated for two pixels at once with the packed IEEE reciprocal / division sequences (the
+// differences of a strictly monotone triple of finite floats are normal numbers of equal sign,
+// so the sequences are exact); a non-finite result (Inf / NaN neighbours, CV_32F depth only) is
+// recomputed with the scalar operators.
 __device__ __forceinline__ float r360_hgrad(float v, float nxt, float prv) {
     if ((v > nxt && v < prv) || (v < nxt && v > prv)) return 2.f / (1 / (nxt - v) + 1 / (v - prv));
     return 0.f;
 }
+__device__ __forceinline__ float2 r360_hgrad2(float2 v, float2 nxt, float2 prv) {
+    const float2 a = f2add(nxt, f2neg(v)), b = f2add(v, f2neg(prv));
+    const float2 g = f2div_rn(R360_F2(2.0f), f2add(f2rcp_rn(a), f2rcp_rn(b)));
+    // strictly monotone  <=>  both differences non-zero with equal sign (float subtraction keeps signs exactly)
+    const bool m0 = (a.x > 0.f & b.x > 0.f) | (a.x < 0.f & b.x < 0.f), m1 = (a.y > 0.f & b.y > 0.f) | (a.y < 0.f & b.y < 0.f);
+    float g0 = m0 ? g.x : 0.f, g1 = m1 ? g.y : 0.f;
+    if (!(fabsf(g0) < INFINITY)) g0 = r360_hgrad(v.x, nxt.x, prv.x);
+    if (!(fabsf(g1) < INFINITY)) g1 = r360_hgrad(v.y, nxt.y, prv.y);
+    return make_float2(g0, g1);
+}
 
 // Target texels of one level: {gray, depth, Ix, Iy, Dx, Dy} with the sensor-joint columns of the
-// four gradient planes zeroed (RPI.h:4537-4549).
+// four gradient planes zeroed (RPI.h:4537-4549).  Two horizontally adjacent pixels per thread
+// (cols is even): 5 loads and three 16-byte stores per pixel pair.
 __global__ void __launch_bounds__(256)
 k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long long off, int rows,
         int cols, int n_sensors) {
     const int f = blockIdx.y;
     const float2* __restrict__ s = pyr[f] + off;
-    float2* __restrict__ o = reinterpret_cast<float2*>(trg[f] + off * R360_TEXEL_FLOATS);
-    const int n = rows * cols;
+    float4* __restrict__ o = reinterpret_cast<float4*>(trg[f] + off * R360_TEXEL_FLOATS);
+    const int n2 = (rows * cols) >> 1, half = cols >> 1;
     const int ws = n_sensors > 1 ? cols / n_sensors : 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int r = i / cols, c = i - r * cols;
-        const float2 v = __ldg(&s[i]);
-        float ix = 0.f, iy = 0.f, dx = 0.f, dy = 0.f;
-        if (r > 0 && r < rows - 1 && c > 0 && c < cols - 1) {
-            const float2 e = __ldg(&s[i + 1]), wv = __ldg(&s[i - 1]), d = __ldg(&s[i + cols]), u = __ldg(&s[i - cols]);
-            ix = r360_hgrad(v.y, e.y, wv.y);
-            iy = r360_hgrad(v.y, d.y, u.y);
-            dx = r360_hgrad(v.x, e.x, wv.x);
-            dy = r360_hgrad(v.x, d.x, u.x);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += gridDim.x * blockDim.x) {
+        const int r = q / half, c = 2 * (q - r * half), i = r * cols + c;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s + i));              // {d0, g0, d1, g1}
+        float2 ix = make_float2(0.f, 0.f), iy = ix, dx = ix, dy = ix;
+        if (r > 0 && r < rows - 1) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(s + i - cols)), d = __ldg(reinterpret_cast<const float4*>(s + i + cols));
+            const float2 wv = c > 0 ? __ldg(&s[i - 1]) : make_float2(0.f, 0.f);
+            const float2 e = c + 2 < cols ? __ldg(&s[i + 2]) : make_float2(0.f, 0.f);
+            ix = r360_hgrad2(make_float2(v.y, v.w), make_float2(v.w, e.y), make_float2(wv.y, v.y));
+            dx = r360_hgrad2(make_float2(v.x, v.z), make_float2(v.z, e.x), make_float2(wv.x, v.x));
+            iy = r360_hgrad2(make_float2(v.y, v.w), make_float2(d.y, d.w), make_float2(u.y, u.w));
+            dy = r360_hgrad2(make_float2(v.x, v.z), make_float2(d.x, d.z), make_float2(u.x, u.z));
+            if (c == 0) { ix.x = 0.f; iy.x = 0.f; dx.x = 0.f; dy.x = 0.f; }                  // border columns
+            if (c + 2 == cols) { ix.y = 0.f; iy.y = 0.f; dx.y = 0.f; dy.y = 0.f; }
         }
         if (ws > 0) {
             // columns k*ws-1 and k*ws, k = 1..n_sensors-1
-            const int k0 = c / ws, rem = c - k0 * ws;
-            const bool masked = (rem == 0 && k0 >= 1 && k0 <= n_sensors - 1) ||
-                                (rem == ws - 1 && k0 + 1 <= n_sensors - 1);
-            if (masked) { ix = iy = dx = dy = 0.f; }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int cc = c + p, k0 = cc / ws, rem = cc - k0 * ws;
+                const bool masked = (rem == 0 && k0 >= 1 && k0 <= n_sensors - 1) ||
+                                    (rem == ws - 1 && k0 + 1 <= n_sensors - 1);
+                if (masked) {
+                    if (p == 0) { ix.x = 0.f; iy.x = 0.f; dx.x = 0.f; dy.x = 0.f; }
+                    else { ix.y = 0.f; iy.y = 0.f; dx.y = 0.f; dy.y = 0.f; }
+                }
+            }
         }
-        o[3 * (size_t)i + 0] = make_float2(v.y, v.x);
-        o[3 * (size_t)i + 1] = make_float2(ix, iy);
-        o[3 * (size_t)i + 2] = make_float2(dx, dy);
+        o[3 * (size_t)q + 0] = make_float4(v.y, v.x, ix.x, iy.x);
+        o[3 * (size_t)q + 1] = make_float4(dx.x, dy.x, v.w, v.z);
+        o[3 * (size_t)q + 2] = make_float4(ix.y, iy.y, dx.y, dy.y);
     }
 }
 
@@ -692,12 +744,13 @@ void r360_launch_level0(cudaStream_t st, const uint8_t* rgb, const uint16_t* dep
 }
 void r360_launch_down(cudaStream_t st, float2* const* pyr, long long off_src, long long off_dst, int rows,
                       int cols, float min_d, float max_d, int n_frames, int sm_count) {
-    dim3 grid(r360_blocks((long long)(rows / 2) * (cols / 2), 256, sm_count * 8), n_frames);
+    const long long n_thr = (long long)(cols / 2) * ((rows / 2 + R360_DOWN_R - 1) / R360_DOWN_R);
+    dim3 grid(r360_blocks(n_thr, 256, sm_count * 8), n_frames);
     k_down<<<grid, 256, 0, st>>>(pyr, off_src, off_dst, rows, cols, min_d, max_d);
 }
 void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, long long off, int rows, int cols,
                        int n_sensors, int n_frames, int sm_count) {
-    dim3 grid(r360_blocks((long long)rows * cols, 256, sm_count * 8), n_frames);
+    dim3 grid(r360_blocks((long long)rows * cols / 2, 256, sm_count * 8), n_frames);
     k_texel<<<grid, 256, 0, st>>>(pyr, trg, off, rows, cols, n_sensors);
 }
 // The pass kernel's pipeline slots need more than the 48 KB default of dynamic shared memory.
