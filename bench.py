@@ -232,8 +232,9 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def step_e2e():
-        ctx.set_frames_ptr(0, n_frames, rgb_host.data_ptr(), dep_host.data_ptr(), roles, device=False)
-        ctx.register_pairs(src_idx, trg_idx, None, out=res)
+        # one C-ABI call: host frames in, host results out (uploads, pyramid builds and batched
+        # registrations overlap inside; pair p = (target frame 2p, source frame 2p+1))
+        ctx.register_host_pairs(rgb_host.data_ptr(), dep_host.data_ptr(), n_pairs, None, out=res)
         gather_results()
 
     step_e2e()

@@ -121,6 +121,15 @@ int r360_set_frames_f32(r360_ctx* ctx, int first, int n, const uint8_t* rgb, con
 int r360_register_pairs(r360_ctx* ctx, int n_pairs, const int32_t* src_idx, const int32_t* trg_idx,
                         const float* init_pose, r360_result* out, r360_iter_record* trace);
 
+/* The per-pair sequence setTargetFrame + setSourceFrame + alignFrames360 (RPI.h:498-516, 480-495,
+ * 4519; call sites Registration/OdometryRGBD360.cpp:189-193, include/LoopClosure360.h:306-321)
+ * for n_pairs pairs whose frames are in HOST memory, as ONE pipelined call: frame 2p of
+ * rgb / depth_mm is the target and frame 2p+1 the source of pair p (they occupy frame slots
+ * 2p and 2p+1 afterwards; needs max_frames >= 2 n_pairs).  Uploads, pyramid builds and batched
+ * registrations overlap on the device; the host blocks once.  Pinned host buffers recommended. */
+int r360_register_host_pairs(r360_ctx* ctx, int n_pairs, const uint8_t* rgb, const uint16_t* depth_mm,
+                             const float* init_pose, r360_result* out);
+
 /* errorPhotoICP_sphere(level, pose, method) (RPI.h:2545-2739): returns the two sums the
  * RMS is formed from. */
 int r360_eval_error(r360_ctx* ctx, int src, int trg, int level, const float pose[16],

@@ -16,7 +16,9 @@ namespace {
 
 std::string g_create_error;
 
-constexpr int kChunkFrames = 16;     // frames per pyramid-build launch / H2D staging buffer
+constexpr int kChunkFrames = 16;     // max frames per pyramid-build launch / H2D staging buffer
+constexpr int kStages = 4;           // staging buffers: the copy stream runs up to kStages - 1 chunks ahead
+constexpr int kStreamPairs = 64;     // pairs per registration batch of r360_register_host_pairs
 
 struct Ctx {
     int device = 0, sm_count = 0, pass_grid = 0;
@@ -26,15 +28,17 @@ struct Ctx {
     long long px_total = 0;
     cudaStream_t st = nullptr, cs = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-    cudaEvent_t ev_copy[2]{}, ev_done[2]{};
+    cudaEvent_t ev_copy[kStages]{}, ev_done[kStages]{};
+    int chunk = kChunkFrames;                    // frames per chunk = min(kChunkFrames, max_frames)
+    long long n_chunks_done = 0;                 // staging-buffer rotation across calls
     std::vector<cudaEvent_t> ev_pass;            // pairs of events around each pixel pass
     float* d_tables = nullptr;
     // frame slots
     std::vector<float2*> src;                    // {depth, gray} pyramids
     std::vector<float*> trg;                     // texel pyramids
-    float2* scratch = nullptr;                   // kChunkFrames source-format pyramids (target-only frames)
-    uint8_t* stage_rgb[2]{};
-    uint16_t* stage_depth[2]{};                  // also holds float depth (sized for it)
+    float2* scratch = nullptr;                   // `chunk` source-format pyramids (target-only frames)
+    uint8_t* stage_rgb[kStages]{};
+    uint16_t* stage_depth[kStages]{};            // also holds float depth (sized for it)
     // pointer tables for the pyramid kernels (pinned host + device)
     float2** h_pyr = nullptr; float2** d_pyr = nullptr;
     float2** h_pyr_t = nullptr; float2** d_pyr_t = nullptr;
@@ -86,7 +90,7 @@ int ensure_trg(Ctx* c, int slot) {
     return R360_OK;
 }
 
-R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint) {
+R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint, int first = 0) {
     R360PassArgs a{};
     a.lv = c->lv[level];
     a.params = c->P;
@@ -100,26 +104,27 @@ R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint) {
     ppi = std::min<long long>(std::max<long long>(ppi, blk), 16 * blk);
     a.px_per_item = (int)ppi;
     a.items_per_pair = (int)((n + ppi - 1) / ppi);
+    // pair-indexed arrays are addressed relative to `first` (pair ids inside the kernels are batch-local)
     a.n_active = c->d_nactive;
-    a.active_list = c->d_active;
-    a.pairs = c->d_pairs;
-    a.src_base = c->d_srcb;
-    a.trg_base = c->d_trgb;
-    a.acc = c->d_acc;
-    a.cnt = c->d_cnt;
+    a.active_list = c->d_active + first;
+    a.pairs = c->d_pairs + first;
+    a.src_base = c->d_srcb + first;
+    a.trg_base = c->d_trgb + first;
+    a.acc = c->d_acc + (size_t)first * R360_ACC_DOUBLES;
+    a.cnt = c->d_cnt + (size_t)first * R360_ACC_INTS;
     return a;
 }
 
-R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace) {
+R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) {
     R360GnArgs g{};
     g.params = c->P;
     g.n_pairs = n_pairs;
-    g.pairs = c->d_pairs;
-    g.acc = c->d_acc;
-    g.cnt = c->d_cnt;
-    g.active_list = c->d_active;
+    g.pairs = c->d_pairs + first;
+    g.acc = c->d_acc + (size_t)first * R360_ACC_DOUBLES;
+    g.cnt = c->d_cnt + (size_t)first * R360_ACC_INTS;
+    g.active_list = c->d_active + first;
     g.n_active = c->d_nactive;
-    g.trace = trace;
+    g.trace = trace ? trace + (size_t)first * c->L * (c->P.max_iters + 2) : nullptr;
     return g;
 }
 
@@ -167,6 +172,26 @@ int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t
     return R360_OK;
 }
 
+// One chunk of host frames: H2D on the copy stream into the next staging buffer (the copy stream
+// runs up to kStages - 1 chunks ahead of the compute stream), pyramid build on the compute stream.
+int stage_and_build(Ctx* c, int first_slot, int m, const uint8_t* rgb, const uint8_t* depth, bool depth_is_f32,
+                    const uint8_t* roles, int table_off) {
+    const size_t npx = (size_t)c->rows * c->cols;
+    const size_t dsz = depth_is_f32 ? sizeof(float) : sizeof(uint16_t);
+    const int b = (int)(c->n_chunks_done % kStages);
+    if (c->n_chunks_done >= kStages) CK(c, cudaStreamWaitEvent(c->cs, c->ev_done[b], 0));
+    CK(c, cudaMemcpyAsync(c->stage_rgb[b], rgb, (size_t)m * npx * 3, cudaMemcpyHostToDevice, c->cs));
+    CK(c, cudaMemcpyAsync(c->stage_depth[b], depth, (size_t)m * npx * dsz, cudaMemcpyHostToDevice, c->cs));
+    CK(c, cudaEventRecord(c->ev_copy[b], c->cs));
+    CK(c, cudaStreamWaitEvent(c->st, c->ev_copy[b], 0));
+    int rc = build_chunk(c, first_slot, m, c->stage_rgb[b], depth_is_f32 ? nullptr : (const uint16_t*)c->stage_depth[b],
+                         depth_is_f32 ? (const float*)c->stage_depth[b] : nullptr, roles, table_off);
+    if (rc) return rc;
+    CK(c, cudaEventRecord(c->ev_done[b], c->st));
+    ++c->n_chunks_done;
+    return R360_OK;
+}
+
 int set_frames_impl(Ctx* c, int first, int n, const uint8_t* rgb, const void* depth, bool depth_is_f32,
                     bool on_device, const uint8_t* roles) {
     if (!c) return R360_E_ARG;
@@ -179,29 +204,16 @@ int set_frames_impl(Ctx* c, int first, int n, const uint8_t* rgb, const void* de
     const size_t npx = (size_t)c->rows * c->cols;
     const size_t dsz = depth_is_f32 ? sizeof(float) : sizeof(uint16_t);
     CK(c, cudaEventRecord(c->ev_t0, c->st));
-    int chunk_id = 0;
-    for (int off = 0; off < n; off += kChunkFrames, ++chunk_id) {
-        const int m = std::min(kChunkFrames, n - off);
-        const uint8_t* r_dev;
-        const void* d_dev;
-        const int b = chunk_id & 1;
-        if (on_device) {
-            r_dev = rgb + (size_t)off * npx * 3;
-            d_dev = (const uint8_t*)depth + (size_t)off * npx * dsz;
-        } else {
-            // double-buffered staging: copy stream runs ahead of the compute stream
-            if (chunk_id >= 2) CK(c, cudaStreamWaitEvent(c->cs, c->ev_done[b], 0));
-            CK(c, cudaMemcpyAsync(c->stage_rgb[b], rgb + (size_t)off * npx * 3, (size_t)m * npx * 3, cudaMemcpyHostToDevice, c->cs));
-            CK(c, cudaMemcpyAsync(c->stage_depth[b], (const uint8_t*)depth + (size_t)off * npx * dsz, (size_t)m * npx * dsz, cudaMemcpyHostToDevice, c->cs));
-            CK(c, cudaEventRecord(c->ev_copy[b], c->cs));
-            CK(c, cudaStreamWaitEvent(c->st, c->ev_copy[b], 0));
-            r_dev = c->stage_rgb[b];
-            d_dev = c->stage_depth[b];
-        }
-        int rc = build_chunk(c, first + off, m, r_dev, depth_is_f32 ? nullptr : (const uint16_t*)d_dev,
-                             depth_is_f32 ? (const float*)d_dev : nullptr, roles ? roles + off : nullptr, off);
+    for (int off = 0; off < n; off += c->chunk) {
+        const int m = std::min(c->chunk, n - off);
+        int rc = on_device
+                     ? build_chunk(c, first + off, m, rgb + (size_t)off * npx * 3,
+                                   depth_is_f32 ? nullptr : (const uint16_t*)((const uint8_t*)depth + (size_t)off * npx * dsz),
+                                   depth_is_f32 ? (const float*)((const uint8_t*)depth + (size_t)off * npx * dsz) : nullptr,
+                                   roles ? roles + off : nullptr, off)
+                     : stage_and_build(c, first + off, m, rgb + (size_t)off * npx * 3, (const uint8_t*)depth + (size_t)off * npx * dsz,
+                                       depth_is_f32, roles ? roles + off : nullptr, off);
         if (rc) return rc;
-        if (!on_device) CK(c, cudaEventRecord(c->ev_done[b], c->st));
     }
     CK(c, cudaEventRecord(c->ev_t1, c->st));
     CK(c, cudaStreamSynchronize(c->st));
@@ -297,7 +309,7 @@ void r360_destroy(r360_ctx* c) {
     for (auto p : c->src) if (p) cudaFree(p);
     for (auto p : c->trg) if (p) cudaFree(p);
     cudaFree(c->d_tables); cudaFree(c->scratch);
-    for (int b = 0; b < 2; ++b) { cudaFree(c->stage_rgb[b]); cudaFree(c->stage_depth[b]); }
+    for (int b = 0; b < kStages; ++b) { cudaFree(c->stage_rgb[b]); cudaFree(c->stage_depth[b]); }
     cudaFree(c->d_pyr); cudaFree(c->d_pyr_t); cudaFree(c->d_trg_t);
     cudaFreeHost(c->h_pyr); cudaFreeHost(c->h_pyr_t); cudaFreeHost(c->h_trg_t);
     cudaFree(c->d_pairs); cudaFree(c->d_acc); cudaFree(c->d_cnt); cudaFree(c->d_active); cudaFree(c->d_nactive);
@@ -306,7 +318,7 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_res); cudaFreeHost(c->h_res); cudaFree(c->d_trace);
     cudaFree(c->d_cams); cudaFreeHost(c->h_cams);
     for (auto e : c->ev_pass) cudaEventDestroy(e);
-    for (int b = 0; b < 2; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
+    for (int b = 0; b < kStages; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->st) cudaStreamDestroy(c->st);
@@ -331,7 +343,8 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
     CK(c, cudaEventCreate(&c->ev_t0));
     CK(c, cudaEventCreate(&c->ev_t1));
-    for (int b = 0; b < 2; ++b) {
+    c->chunk = std::min(kChunkFrames, max_frames);
+    for (int b = 0; b < kStages; ++b) {
         CK(c, cudaEventCreateWithFlags(&c->ev_copy[b], cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming));
     }
@@ -381,10 +394,10 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     c->src.assign(max_frames, nullptr);
     c->trg.assign(max_frames, nullptr);
     const size_t npx = (size_t)rows * cols;
-    CK(c, cudaMalloc(&c->scratch, sizeof(float2) * c->px_total * kChunkFrames));
-    for (int b = 0; b < 2; ++b) {
-        CK(c, cudaMalloc(&c->stage_rgb[b], npx * 3 * kChunkFrames));
-        CK(c, cudaMalloc(&c->stage_depth[b], npx * sizeof(float) * kChunkFrames));
+    CK(c, cudaMalloc(&c->scratch, sizeof(float2) * c->px_total * c->chunk));
+    for (int b = 0; b < kStages; ++b) {
+        CK(c, cudaMalloc(&c->stage_rgb[b], npx * 3 * c->chunk));
+        CK(c, cudaMalloc(&c->stage_depth[b], npx * sizeof(float) * c->chunk));
     }
     CK(c, cudaMallocHost(&c->h_pyr, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_pyr, sizeof(void*) * max_frames));
     CK(c, cudaMallocHost(&c->h_pyr_t, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_pyr_t, sizeof(void*) * max_frames));
@@ -440,6 +453,40 @@ int r360_set_frames_f32(r360_ctx* c, int first, int n, const uint8_t* rgb, const
     return set_frames_impl(c, first, n, rgb, depth_m, true, false, roles);
 }
 
+// Enqueues alignFrames360 for pairs [first, first + n) of the current call on the compute stream
+// (no host synchronisation): per-pair tables H2D, state init, then per level max_iters + 1 fused
+// passes with the on-device Gauss-Newton step in between, results into d_res[first ..].
+// The host tables (h_srcb, h_trgb, h_idx, h_pose) must already hold the whole call.
+static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has_pose, r360_iter_record* d_trace,
+                            bool time_passes, int* n_ev) {
+    CK(c, cudaMemcpyAsync(c->d_srcb + first, c->h_srcb + first, sizeof(void*) * n, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_trgb + first, c->h_trgb + first, sizeof(void*) * n, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_idx + first, c->h_idx + first, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_idx + c->max_pairs + 1 + first, c->h_idx + n_total + first, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->st));
+    if (has_pose)
+        CK(c, cudaMemcpyAsync(c->d_pose + 16 * (size_t)first, c->h_pose + 16 * (size_t)first, sizeof(float) * 16 * n, cudaMemcpyHostToDevice, c->st));
+    R360GnArgs g = gn_args(c, n, d_trace, first);
+    r360_launch_pairs_init(c->st, g, c->d_idx + first, c->d_idx + c->max_pairs + 1 + first,
+                           has_pose ? c->d_pose + 16 * (size_t)first : nullptr);
+    ++c->launches;
+    for (int level = c->L - 1; level >= 0; --level) {                 // RPI.h:4531
+        r360_launch_level_begin(c->st, g, level);
+        c->launches += 2;
+        R360PassArgs a = pass_args(c, level, n, first);
+        for (int k = 0; k <= c->P.max_iters; ++k) {                   // 1 initial + <= max_iters loop bodies
+            if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
+            r360_launch_pass(c->st, a, c->pass_grid);
+            if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
+            r360_launch_gn_step(c->st, g, level);
+            c->launches += 3;
+        }
+    }
+    r360_launch_finalize(c->st, g, c->d_res + first, c->rows, c->cols, first);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return R360_OK;
+}
+
 int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const int32_t* trg_idx, const float* init_pose,
                         r360_result* out, r360_iter_record* trace) {
     if (!c) return R360_E_ARG;
@@ -464,33 +511,11 @@ int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const 
         c->trace_cap = n_rec;
     }
     CK(c, cudaEventRecord(c->ev_t0, c->st));
-    CK(c, cudaMemcpyAsync(c->d_srcb, c->h_srcb, sizeof(void*) * n_pairs, cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemcpyAsync(c->d_trgb, c->h_trgb, sizeof(void*) * n_pairs, cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemcpyAsync(c->d_idx, c->h_idx, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyHostToDevice, c->st));
-    if (init_pose) {
-        memcpy(c->h_pose, init_pose, sizeof(float) * 16 * n_pairs);
-        CK(c, cudaMemcpyAsync(c->d_pose, c->h_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyHostToDevice, c->st));
-    }
+    if (init_pose) memcpy(c->h_pose, init_pose, sizeof(float) * 16 * n_pairs);
     if (trace) CK(c, cudaMemsetAsync(c->d_trace, 0, sizeof(r360_iter_record) * n_rec, c->st));
-    R360GnArgs g = gn_args(c, n_pairs, trace ? c->d_trace : nullptr);
-    r360_launch_pairs_init(c->st, g, c->d_idx, c->d_idx + n_pairs, init_pose ? c->d_pose : nullptr);
-    ++c->launches;
     int n_ev = 0;
-    for (int level = c->L - 1; level >= 0; --level) {                 // RPI.h:4531
-        r360_launch_level_begin(c->st, g, level);
-        c->launches += 2;
-        R360PassArgs a = pass_args(c, level, n_pairs);
-        for (int k = 0; k <= c->P.max_iters; ++k) {                   // 1 initial + <= max_iters loop bodies
-            CK(c, cudaEventRecord(c->ev_pass[n_ev++], c->st));
-            r360_launch_pass(c->st, a, c->pass_grid);
-            CK(c, cudaEventRecord(c->ev_pass[n_ev++], c->st));
-            r360_launch_gn_step(c->st, g, level);
-            c->launches += 3;
-        }
-    }
-    r360_launch_finalize(c->st, g, c->d_res, c->rows, c->cols);
-    ++c->launches;
-    CK(c, cudaGetLastError());
+    int rc = enqueue_register(c, 0, n_pairs, n_pairs, init_pose != nullptr, trace ? c->d_trace : nullptr, true, &n_ev);
+    if (rc) return rc;
     CK(c, cudaMemcpyAsync(c->h_res, c->d_res, sizeof(r360_result) * n_pairs, cudaMemcpyDeviceToHost, c->st));
     if (trace) CK(c, cudaMemcpyAsync(trace, c->d_trace, sizeof(r360_iter_record) * n_rec, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaEventRecord(c->ev_t1, c->st));
@@ -507,6 +532,52 @@ int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const 
     }
     for (int p = 0; p < n_pairs; ++p)
         for (int l = 0; l < c->L; ++l) c->pass_bytes += 32.0 * (double)c->lv[l].n * out[p].passes[l];
+    return R360_OK;
+}
+
+// setTargetFrame + setSourceFrame + alignFrames360 for n_pairs pairs whose frames are in HOST
+// memory, as one pipelined call: frame 2p is the target and frame 2p+1 the source of pair p.
+// Uploads (copy stream, kStages staging buffers), pyramid builds and batched registrations of
+// kStreamPairs pairs (compute stream) overlap; the host blocks once, at the end.
+int r360_register_host_pairs(r360_ctx* c, int n_pairs, const uint8_t* rgb, const uint16_t* depth_mm,
+                             const float* init_pose, r360_result* out) {
+    if (!c) return R360_E_ARG;
+    if (n_pairs < 0 || n_pairs > c->max_pairs || 2 * n_pairs > c->max_frames || !rgb || !depth_mm || !out)
+        return fail(c, R360_E_ARG, "register_host_pairs: n_pairs %d needs max_pairs >= n_pairs and max_frames >= 2 n_pairs, non-null buffers", n_pairs);
+    if (n_pairs == 0) return R360_OK;
+    CK(c, cudaSetDevice(c->device));
+    const size_t npx = (size_t)c->rows * c->cols;
+    for (int p = 0; p < n_pairs; ++p) {                               // allocate before the pipeline starts
+        int rc = ensure_trg(c, 2 * p);
+        if (!rc) rc = ensure_src(c, 2 * p + 1);
+        if (rc) return rc;
+        c->h_srcb[p] = c->src[2 * p + 1];
+        c->h_trgb[p] = c->trg[2 * p];
+        c->h_idx[p] = 2 * p + 1;
+        c->h_idx[n_pairs + p] = 2 * p;
+    }
+    if (init_pose) memcpy(c->h_pose, init_pose, sizeof(float) * 16 * n_pairs);
+    std::vector<uint8_t> roles(2 * (size_t)std::min(n_pairs, kStreamPairs));
+    for (size_t k = 0; k < roles.size(); ++k) roles[k] = (k & 1) ? R360_ROLE_SOURCE : R360_ROLE_TARGET;
+    CK(c, cudaEventRecord(c->ev_t0, c->st));
+    int n_ev = 0;
+    for (int first = 0; first < n_pairs; first += kStreamPairs) {
+        const int nb = std::min(kStreamPairs, n_pairs - first);
+        for (int off = 0; off < 2 * nb; off += c->chunk) {
+            const int m = std::min(c->chunk, 2 * nb - off);
+            const size_t f0 = 2 * (size_t)first + off;
+            int rc = stage_and_build(c, (int)f0, m, rgb + f0 * npx * 3, (const uint8_t*)(depth_mm + f0 * npx), false,
+                                     roles.data() + off, (int)f0);
+            if (rc) return rc;
+        }
+        int rc = enqueue_register(c, first, nb, n_pairs, init_pose != nullptr, nullptr, false, &n_ev);
+        if (rc) return rc;
+    }
+    CK(c, cudaMemcpyAsync(c->h_res, c->d_res, sizeof(r360_result) * n_pairs, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaEventRecord(c->ev_t1, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    memcpy(out, c->h_res, sizeof(r360_result) * n_pairs);
+    CK(c, cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1));
     return R360_OK;
 }
 
@@ -646,8 +717,8 @@ int r360_synth_frames(r360_ctx* c, int kind, int first_id, int n, uint8_t* rgb, 
     if (!c) return R360_E_ARG;
     if (n < 0 || !rgb || !depth_mm) return fail(c, R360_E_ARG, "synth_frames: bad arguments");
     const size_t npx = (size_t)c->rows * c->cols;
-    for (int off = 0; off < n; off += kChunkFrames) {
-        const int m = std::min(kChunkFrames, n - off);
+    for (int off = 0; off < n; off += c->chunk) {
+        const int m = std::min(c->chunk, n - off);
         int rc = r360_synth_frames_dev(c, kind, first_id + off, m, c->stage_rgb[0], c->stage_depth[0]);
         if (rc) return rc;
         CK(c, cudaMemcpy(rgb + (size_t)off * npx * 3, c->stage_rgb[0], (size_t)m * npx * 3, cudaMemcpyDeviceToHost));

@@ -685,7 +685,7 @@ __global__ void k_pairs_init(R360GnArgs g, const int32_t* __restrict__ src_idx,
     }
 }
 
-__global__ void k_finalize(R360GnArgs g, r360_result* __restrict__ out, int rows, int cols) {
+__global__ void k_finalize(R360GnArgs g, r360_result* __restrict__ out, int rows, int cols, int pair_id0) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
         const R360Pair* ps = g.pairs + p;
         r360_result* r = out + p;
@@ -701,7 +701,7 @@ __global__ void k_finalize(R360GnArgs g, r360_result* __restrict__ out, int rows
         r->final_n_valid = ps->n_valid;
         r->status = ps->status;
         for (int k = 0; k < R360_MAX_LEVELS; ++k) { r->iters[k] = ps->iters[k]; r->passes[k] = ps->passes[k]; }
-        r->pair_id = p;
+        r->pair_id = pair_id0 + p;
         r->reserved = 0;
     }
 }
@@ -786,8 +786,8 @@ void r360_launch_gn_step(cudaStream_t st, const R360GnArgs& g, int level) {
     k_gn_step<<<r360_blocks(g.n_pairs, 32, 1024), 32, 0, st>>>(g, level);
     k_compact<<<1, 32, 0, st>>>(g);
 }
-void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols) {
-    k_finalize<<<r360_blocks(g.n_pairs, 128, 1024), 128, 0, st>>>(g, out, rows, cols);
+void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols, int pair_id0) {
+    k_finalize<<<r360_blocks(g.n_pairs, 128, 1024), 128, 0, st>>>(g, out, rows, cols, pair_id0);
 }
 void r360_launch_synth(cudaStream_t st, int kind, int first_id, int rows, int cols, const float* cams, int n_frames,
                        uint8_t* rgb, uint16_t* depth_mm, int sm_count) {

@@ -45,6 +45,6 @@ void r360_launch_pairs_init(cudaStream_t st, const R360GnArgs& g, const int32_t*
                             const float* init_pose);
 void r360_launch_level_begin(cudaStream_t st, const R360GnArgs& g, int level);
 void r360_launch_gn_step(cudaStream_t st, const R360GnArgs& g, int level);
-void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols);
+void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols, int pair_id0);
 void r360_launch_synth(cudaStream_t st, int kind, int first_id, int rows, int cols, const float* cams, int n_frames,
                        uint8_t* rgb, uint16_t* depth_mm, int sm_count);

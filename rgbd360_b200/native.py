@@ -18,7 +18,7 @@ EXPORTS = [
     "r360_eval_hessgrad", "r360_dump_level", "r360_dump_source_level", "r360_dump_warp",
     "r360_synth_frames_dev", "r360_synth_frames", "r360_synth_gt_pose", "r360_device_alloc",
     "r360_device_free", "r360_synchronize", "r360_last_device_ms", "r360_kernel_launches",
-    "r360_last_pass_stats", "r360_version", "r360_index_stats",
+    "r360_last_pass_stats", "r360_version", "r360_index_stats", "r360_register_host_pairs",
 ]
 
 
@@ -97,6 +97,7 @@ def lib():
     L.r360_set_frames_dev.argtypes = [vp, i32, i32, vp, vp, vp]
     L.r360_set_frames_f32.argtypes = [vp, i32, i32, vp, vp, vp]
     L.r360_register_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.r360_register_host_pairs.argtypes = [vp, i32, vp, vp, vp, vp]
     L.r360_eval_error.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.r360_eval_hessgrad.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.POINTER(C.c_int32)]
     L.r360_dump_level.argtypes = [vp, i32, i32] + [vp] * 6
@@ -220,6 +221,19 @@ class Context:
         self._ck(self.L.r360_register_pairs(self.h, n, _p(s), _p(t), _p(ip), _p(res),
                                             C.cast(tr, C.c_void_p) if trace else None))
         return (res, tr) if trace else res
+
+    def register_host_pairs(self, rgb, depth_mm, n_pairs=None, init_pose=None, out=None):
+        """setTargetFrame + setSourceFrame + alignFrames360 of host frames in one pipelined call:
+        frame 2p = target, frame 2p+1 = source of pair p.  rgb / depth_mm: arrays or raw host pointers."""
+        if n_pairs is None:
+            n_pairs = rgb.shape[0] // 2
+        if not isinstance(rgb, int):
+            rgb = np.ascontiguousarray(rgb, np.uint8)
+            depth_mm = np.ascontiguousarray(depth_mm, np.uint16)
+        res = out if out is not None else np.zeros(n_pairs, RESULT_DTYPE)
+        ip = None if init_pose is None else np.ascontiguousarray(init_pose, np.float32).reshape(n_pairs, 16)
+        self._ck(self.L.r360_register_host_pairs(self.h, n_pairs, _p(rgb), _p(depth_mm), _p(ip), _p(res)))
+        return res
 
     def eval_error(self, src, trg, level, pose):
         e2, n = C.c_double(), C.c_int32()

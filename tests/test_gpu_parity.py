@@ -245,6 +245,31 @@ def test_non_power_of_two_width(orc, r360):
     ctx.close()
 
 
+def test_register_host_pairs_streaming(r360):
+    """The pipelined host entry point (upload + pyramids + batched registration overlapped) returns
+    the same records as set_frames + register_pairs; more pairs than one internal batch."""
+    rows, cols, L, n = 64, 128, 3, 70
+    ctx = r360.Context(rows, cols, 2 * n, n, r360.default_params(n_levels=L))
+    rgb, dep = ctx.synth_frames(0, 0, 2 * n)
+    roles = np.array([r360.ROLE_TARGET, r360.ROLE_SOURCE] * n, np.uint8)
+    ctx.set_frames(0, rgb, dep, roles)
+    trg_idx = np.arange(0, 2 * n, 2); src_idx = trg_idx + 1
+    rng = np.random.default_rng(5)
+    guesses = np.stack([r360.pose_to_colmajor(small_pose(*(rng.uniform(-1, 1, 6) * 0.01))) for _ in range(n)])
+    ref = ctx.register_pairs(src_idx, trg_idx, guesses)
+    ctx2 = r360.Context(rows, cols, 2 * n, n, r360.default_params(n_levels=L))
+    got = ctx2.register_host_pairs(rgb, dep, n, guesses)
+    for k in range(n):
+        assert got[k]["pair_id"] == k and got[k]["status"] == ref[k]["status"]
+        assert list(got[k]["iters"]) == list(ref[k]["iters"])
+        assert np.allclose(got[k]["pose"], ref[k]["pose"], atol=1e-6)
+        assert got[k]["final_n_valid"] == ref[k]["final_n_valid"]
+    # frames stay resident in slots 2p / 2p+1: a second registration through the slot API agrees
+    again = ctx2.register_pairs(src_idx[:3], trg_idx[:3], guesses[:3])
+    assert np.allclose(again["pose"], ref["pose"][:3], atol=1e-6)
+    ctx.close(); ctx2.close()
+
+
 def test_errors_are_loud(r360):
     ctx = r360.Context(64, 128, 2, 1, r360.default_params(n_levels=2))
     with pytest.raises(r360.R360Error):
