@@ -40,6 +40,16 @@ METRIC = "sphere-pair registrations/s @2048x1024"
 UNIT = "pairs/s"
 
 
+def measured_traffic_ratio():
+    """dram bytes / algorithmic bytes of one k_pass launch from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "k_pass_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes"]) / float(d["algorithmic_bytes"]), d.get("source", p)
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -105,20 +115,26 @@ def workload(args):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+CPU_SAMPLE = {"A": 96, "B": 384}        # pairs of the workload timed on the host cores (~10-30 s of CPU work)
+
+
 def cpu_reference_run(w, n_pairs, first_pair=0):
-    """Oracle (port of the reference CPU path, FAITHFUL accumulation, all host threads) on
-    n_pairs pairs of the workload: set{Target,Source}Frame + alignFrames360 per pair."""
+    """Oracle (port of the reference CPU path, FAITHFUL accumulation, glibc math, all host threads)
+    on n_pairs pairs of the workload: setTargetFrame + setSourceFrame + alignFrames360 per pair.
+    Frame synthesis is outside the timed region.  Returns (pairs/s, threads, seconds)."""
     from oracle import orc
     orc.build()
     orc.set_math(orc.MATH_LIBM)          # what a g++/glibc build of the reference calls
     P = orc.default_params(n_levels=w["levels"])
-    frames = [orc.synth_frame(0, 2 * (first_pair + k) + j, w["rows"], w["cols"]) for k in range(n_pairs) for j in (0, 1)]
-    t0 = time.perf_counter()
+    dt = 0.0
     for k in range(n_pairs):
-        trg = orc.Frame(frames[2 * k][0], frames[2 * k][1], P, True)        # setTargetFrame
-        src = orc.Frame(frames[2 * k + 1][0], frames[2 * k + 1][1], P, False)  # setSourceFrame
-        orc.align(src, trg, None, P, accum=orc.ACC_FAITHFUL)                 # alignFrames360
-    dt = time.perf_counter() - t0
+        ft = orc.synth_frame(0, 2 * (first_pair + k), w["rows"], w["cols"])
+        fs = orc.synth_frame(0, 2 * (first_pair + k) + 1, w["rows"], w["cols"])
+        t0 = time.perf_counter()
+        trg = orc.Frame(ft[0], ft[1], P, True)        # setTargetFrame
+        src = orc.Frame(fs[0], fs[1], P, False)       # setSourceFrame
+        orc.align(src, trg, None, P, accum=orc.ACC_FAITHFUL)   # alignFrames360
+        dt += time.perf_counter() - t0
     orc.set_math(orc.MATH_PINNED)
     return n_pairs / dt, orc.omp_threads(), dt
 
@@ -128,14 +144,13 @@ def run_reference(args):
     if rank != 0:
         return
     w = workload(args)
-    sample = 2 if args.workload == "A" else 4
+    sample = max(1, CPU_SAMPLE[args.workload] // 4)      # per step; the whole run stays within a few minutes
     for _ in range(args.warmup):
-        cpu_reference_run(w, 1)
-    t0 = time.perf_counter()
-    cores = 1
+        cpu_reference_run(w, 2)
+    cores, dt = 1, 0.0
     for s in range(args.steps):
-        _, cores, _ = cpu_reference_run(w, sample, first_pair=s * sample)
-    dt = time.perf_counter() - t0
+        _, cores, d = cpu_reference_run(w, sample, first_pair=s * sample)
+        dt += d
     v = args.steps * sample / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
@@ -144,7 +159,8 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": w["name"], "rows": w["rows"], "cols": w["cols"], "levels": w["levels"],
                    "pairs_per_step": sample, "note": "CPU oracle (port of the reference; the reference itself "
-                   "needs Eigen/OpenCV/PCL/MRPT and cannot be built here), FAITHFUL accumulation, glibc math"},
+                   "needs Eigen/OpenCV/PCL/MRPT and cannot be built here), FAITHFUL accumulation, glibc math, "
+                   "OpenMP over all host threads"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} pairs per step x {args.steps} steps, frame build + alignFrames360"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -260,6 +276,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = (pass_bytes / 1e9) / (pass_ms / 1e3) if pass_ms > 0 else 0.0     # rank 0's kernel
+        t_ratio, t_src = measured_traffic_ratio()
         iters = res["iters"][:, :L].astype(np.float64)
         passes = res["passes"][:, :L].astype(np.float64)
         line = {
@@ -285,16 +302,20 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_pass<PHOTO_DEPTH> (fused warp/residual/normal-equation pass)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         "traffic": (t_ratio * pass_bytes / max(pass_launches, 1)) if t_ratio else None,
+                         "traffic_source": t_src,
                          "alg_bytes_per_launch": pass_bytes / max(pass_launches, 1),
                          "avg_launch_ms": pass_ms / max(pass_launches, 1), "launches": pass_launches,
                          "kernel_share_of_step": pass_ms / dev_ms if dev_ms else None},
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, dt = cpu_reference_run(w, 2 if args.workload == "A" else 4)
+            n_cpu = CPU_SAMPLE[args.workload]
+            cpu_reference_run(w, 2)                                    # warm-up (library build, page-in)
+            v, cores, dt = cpu_reference_run(w, n_cpu)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d pairs of the same workload (frame build + alignFrames360, "
-                                              "FAITHFUL accumulation, glibc math), %.1f s" % (2 if args.workload == "A" else 4, dt)}
+                                              "FAITHFUL accumulation, glibc math, OpenMP), %.1f s" % (n_cpu, dt)}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -304,7 +325,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=list(WORKLOADS))
