@@ -124,6 +124,7 @@ def cpu_reference_run(w, n_pairs, first_pair=0):
     Frame synthesis is outside the timed region.  Returns (pairs/s, threads, seconds)."""
     from oracle import orc
     orc.build()
+    orc.use_all_cores()
     orc.set_math(orc.MATH_LIBM)          # what a g++/glibc build of the reference calls
     P = orc.default_params(n_levels=w["levels"])
     dt = 0.0
@@ -269,6 +270,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms, e2e_ms, pass_ms_max = [float(x) for x in t.tolist()]
+    launches = int(s[1].item())                     # all ranks
     total_pairs = n_pairs * world
     value = total_pairs * args.steps / (wall_ms / 1e3)
     e2e_value = total_pairs * e2e_steps / (e2e_ms / 1e3)

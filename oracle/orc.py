@@ -119,6 +119,14 @@ def omp_threads():
     return int(lib().orc_omp_threads())
 
 
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_threads(n)
+    return n
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

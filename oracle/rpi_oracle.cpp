@@ -802,3 +802,5 @@ int orc_omp_threads(void);
 
 #include <omp.h>
 extern "C" int orc_omp_threads(void) { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline wants all host cores.
+extern "C" void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
