@@ -1,0 +1,125 @@
+"""ctypes binding of oracle/_ref/librpi_ref.so -- the reference's own RegisterPhotoICP.h compiled
+against the from-scratch third-party stand-ins of oracle/refshim/ (see oracle/ref_harness.cpp).
+
+TEST INFRASTRUCTURE ONLY.  The library can only be (re)built where /root/reference exists; the
+prebuilt .so travels to the GPU box (oracle/_ref/ is git-ignored, not gpurun-ignored).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = {False: os.path.join(_HERE, "_ref", "librpi_ref.so"),          # glibc asinf/atan2f/sinf/cosf
+       True: os.path.join(_HERE, "_ref", "librpi_ref_pinned.so")}    # sphere_math.h sequences (what the GPU runs)
+REFERENCE_DIR = "/root/reference"
+
+
+def available():
+    return all(os.path.exists(p) for p in _SO.values()) or os.path.isdir(os.path.join(REFERENCE_DIR, "include"))
+
+
+def build():
+    if os.path.isdir(os.path.join(REFERENCE_DIR, "include")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return _SO
+
+
+_libs = {}
+
+
+def lib(pinned=False):
+    pinned = bool(pinned)
+    if pinned not in _libs:
+        if not os.path.exists(_SO[pinned]):
+            build()
+        L = C.CDLL(_SO[pinned])
+        assert L.ref_pinned_math() == int(pinned)
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_set_source.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ref_set_target.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ref_level.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        L.ref_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int]
+        L.ref_error.restype = C.c_double
+        L.ref_error.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ref_hessgrad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.ref_lut.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _libs[pinned] = L
+    return _libs[pinned]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _pose_arg(pose):
+    if pose is None:
+        pose = np.eye(4)
+    return np.ascontiguousarray(np.asarray(pose, dtype=np.float32).reshape(4, 4).T).reshape(16)
+
+
+class Reference:
+    """One RegisterPhotoICP instance of the reference (RPI.h:85)."""
+
+    def __init__(self, n_levels=4, min_depth=0.3, max_depth=6.0, std_photo=6.0 / 255, std_depth=0.2, pinned=False):
+        self.n_levels = n_levels
+        self.L = lib(pinned)
+        self.h = self.L.ref_create(n_levels, min_depth, max_depth, np.float32(std_photo), std_depth)
+        self.rows = self.cols = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ref_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_source(self, rgb, depth_mm):
+        rgb = np.ascontiguousarray(rgb, np.uint8); d = np.ascontiguousarray(depth_mm, np.uint16)
+        self.rows, self.cols = d.shape
+        self.L.ref_set_source(self.h, _ptr(rgb), _ptr(d), self.rows, self.cols)
+
+    def set_target(self, rgb, depth_mm):
+        rgb = np.ascontiguousarray(rgb, np.uint8); d = np.ascontiguousarray(depth_mm, np.uint16)
+        self.rows, self.cols = d.shape
+        self.L.ref_set_target(self.h, _ptr(rgb), _ptr(d), self.rows, self.cols)
+
+    def level(self, which, level):
+        r, c = self.rows >> level, self.cols >> level
+        names = ["gray", "depth"] + (["ggx", "ggy", "dgx", "dgy"] if which == 1 else [])
+        out = {n: np.zeros((r, c), np.float32) for n in names}
+        args = [_ptr(out[n]) if n in out else None for n in ["gray", "depth", "ggx", "ggy", "dgx", "dgy"]]
+        assert self.L.ref_level(self.h, which, level, *args) == 0
+        return out
+
+    def align(self, guess=None, method=2, occlusion=0):
+        T = _pose_arg(guess)
+        pose = np.zeros(16, np.float32); H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+        sso = np.zeros(1, np.float32); iters = np.zeros(self.n_levels, np.int32)
+        cap = self.n_levels * 24
+        e2 = np.zeros(cap, np.float64); nv = np.zeros(cap, np.int32)
+        n = self.L.ref_align(self.h, _ptr(T), method, occlusion, _ptr(pose), _ptr(H), _ptr(g), _ptr(sso), _ptr(iters),
+                            _ptr(e2), _ptr(nv), cap)
+        ill = n < 0
+        if ill:
+            n = -1 - n
+        return dict(pose=pose.reshape(4, 4).T.copy(), H=H.reshape(6, 6).T.copy(), g=g, sso=float(sso[0]),
+                    iters=iters, err2=e2[:n].copy(), n_valid=nv[:n].copy(), ill_posed=ill)
+
+    def error(self, level, pose, method=2):
+        e2, n = C.c_double(), C.c_int()
+        e = self.L.ref_error(self.h, level, _ptr(_pose_arg(pose)), method, C.byref(e2), C.byref(n))
+        return e, e2.value, n.value
+
+    def hessgrad(self, level, pose, method=2):
+        H = np.zeros(36, np.float32); g = np.zeros(6, np.float32); sso = C.c_float()
+        self.L.ref_hessgrad(self.h, level, _ptr(_pose_arg(pose)), method, _ptr(H), _ptr(g), C.byref(sso))
+        return H.reshape(6, 6).T.copy(), g, sso.value
+
+    def lut(self):
+        n = self.L.ref_lut(self.h, None, 0)
+        out = np.zeros((n, 3), np.float32)
+        self.L.ref_lut(self.h, _ptr(out), n)
+        return out

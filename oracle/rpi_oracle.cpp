@@ -4,13 +4,19 @@
 // cpu_baseline / --impl reference legs may load this library.  The product
 // (rgbd360_b200/, include/) never links, imports or calls it.
 //
-// PARITY UNPINNED: the reference (EduFdez/rgbd360) ships no tests, golden vectors or recorded
-// outputs for this path, and it cannot be compiled here (needs Eigen, OpenCV, PCL, MRPT,
-// Boost -- none present, no network).  This file follows the reference source line by line
-// (citations "RPI.h:N" = /root/reference/include/RegisterPhotoICP.h) and restates the
-// un-vendored third-party arithmetic it calls (OpenCV cvtColor/convertTo/pyrDown, Eigen
-// fixed-size products / inverse, MRPT CPose3D::exp and rank()); the OpenCV pieces are
-// cross-checked against python cv2 in tests/test_oracle.py.
+// PARITY PIN: the reference (EduFdez/rgbd360) ships no tests, golden vectors or recorded outputs for
+// this path, and its own build needs Eigen, OpenCV, PCL, MRPT and Boost (none present, no network).
+// Its header /root/reference/include/RegisterPhotoICP.h is nevertheless compiled here, unmodified
+// and from where it lies, against from-scratch stand-ins for the slice of those libraries it uses
+// (oracle/refshim/, oracle/ref_harness.cpp -> oracle/_ref/).  This restatement is BIT-IDENTICAL to
+// that build (planes, LUT, numValidPts of every evaluation, iteration counts, Hessian, gradient,
+// pose at one OpenMP thread; tests/test_reference.py, recorded in
+// tests/golden/reference_outputs.json) on synthetic pairs and on the reference's own sample pair.
+// What stays a restatement on BOTH sides is the third-party arithmetic itself: OpenCV
+// cvtColor/convertTo/pyrDown (pinned against python cv2 4.13 golden vectors, tests/test_oracle.py),
+// Eigen fixed-size products / norm / 6x6 inverse, MRPT rank() and CPose3D::exp (unpinned: no
+// version is named upstream and the libraries are absent).  Citations "RPI.h:N" =
+// /root/reference/include/RegisterPhotoICP.h.
 //
 // Two arithmetic modes (orc_set_math):
 //   0 PINNED : asin/atan2/sin/cos come from rgbd360_b200/csrc/sphere_math.h -- the exact

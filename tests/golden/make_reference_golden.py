@@ -1,0 +1,69 @@
+"""Runs the REFERENCE ITSELF (oracle/_ref/: /root/reference/include/RegisterPhotoICP.h compiled
+against oracle/refshim/, both arithmetic variants) on the cases of tests/refcases.py and records its
+outputs as tests/golden/reference_outputs.json.  Only runnable where /root/reference exists.
+
+    python tests/golden/make_reference_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import orc, refbind   # noqa: E402
+import refcases                   # noqa: E402
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def canonical_lut(lut):
+    """The reference only writes x = INVALID_POINT for an invalid pixel (RPI.h:4585) and leaves y, z
+    as whatever the vector held before; zero them before hashing."""
+    lut = lut.copy()
+    lut[lut[:, 0] == -10000.0, 1:] = 0
+    return lut
+
+
+def run_reference(case, pinned, threads=1):
+    refbind.lib(pinned).ref_set_threads(threads)
+    R = refbind.Reference(n_levels=case["levels"], std_photo=case["std_photo"], pinned=pinned)
+    R.set_source(case["rgb_s"], case["d_s"])
+    R.set_target(case["rgb_t"], case["d_t"])
+    a = R.align(case["guess"], case["method"])
+    out = dict(pose=a["pose"].astype(np.float64).ravel().tolist(), H=a["H"].astype(np.float64).ravel().tolist(),
+               g=a["g"].astype(np.float64).tolist(), sso=a["sso"], iters=a["iters"].tolist(),
+               trace_err2=a["err2"].tolist(), trace_n_valid=a["n_valid"].tolist(), ill_posed=bool(a["ill_posed"]))
+    planes = {}
+    for l in range(case["levels"]):
+        for which, tag in ((0, "src"), (1, "trg")):
+            for k, v in R.level(which, l).items():
+                planes[f"{tag}{l}_{k}"] = digest(v)
+    out["planes_sha"] = planes
+    out["lut0_sha"] = digest(canonical_lut(R.lut()))
+    probes = []
+    for T in refcases.probe_poses():
+        e, e2, n = R.error(0, T, case["method"])
+        H, g, sso = R.hessgrad(0, T, case["method"])
+        probes.append(dict(err2=e2, n_valid=n, H=H.astype(np.float64).ravel().tolist(), g=g.astype(np.float64).tolist(), sso=sso))
+    out["probes_level0"] = probes
+    R.close()
+    return out
+
+
+def main():
+    gold = {"_how": "oracle/_ref (reference header + refshim), OMP threads = 1; see this script", "cases": {}}
+    for name in refcases.CASES:
+        case = refcases.make_case(orc, name)
+        gold["cases"][name] = {"libm": run_reference(case, False), "pinned": run_reference(case, True)}
+        c = gold["cases"][name]
+        print(name, "iters", c["libm"]["iters"], c["pinned"]["iters"], "n_valid[0]", c["libm"]["trace_n_valid"][:1])
+    with open(os.path.join(HERE, "reference_outputs.json"), "w") as f:
+        json.dump(gold, f, indent=0)
+
+
+if __name__ == "__main__":
+    main()

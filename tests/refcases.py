@@ -1,0 +1,84 @@
+"""Input cases shared by tests/golden/make_reference_golden.py (which runs the compiled reference,
+oracle/_ref/) and tests/test_reference.py (which checks the oracle -- and, under -m gpu, the CUDA
+path -- against the recorded reference outputs)."""
+import os
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _synth(orc, kind, a, b, rows, cols):
+    rgb_t, d_t = orc.synth_frame(kind, a, rows, cols)
+    rgb_s, d_s = orc.synth_frame(kind, b, rows, cols)
+    return rgb_s, d_s, rgb_t, d_t
+
+
+def _holes(rgb_s, d_s, rgb_t, d_t, seed):
+    """Invalid depth (0), out-of-range depth (> maxDepth, < minDepth) and colour (non-gray RGB)
+    patches: exercises the validity masks, buildPyramidRange's valid-mean and the luma weights."""
+    rng = np.random.default_rng(seed)
+    d_s = d_s.copy(); d_t = d_t.copy(); rgb_s = rgb_s.copy(); rgb_t = rgb_t.copy()
+    H, W = d_s.shape
+    for d in (d_s, d_t):
+        for _ in range(6):
+            r, c = rng.integers(0, H - 9), rng.integers(0, W - 17)
+            d[r:r + rng.integers(2, 9), c:c + rng.integers(2, 17)] = rng.choice([0, 150, 6500, 65535])
+        d[rng.random(d.shape) < 0.01] = 0
+    for rgb in (rgb_s, rgb_t):
+        rgb[..., 0] = np.clip(rgb[..., 0].astype(np.int32) + rng.integers(-20, 21, rgb.shape[:2]), 0, 255)
+        rgb[..., 2] = np.clip(rgb[..., 2].astype(np.int32) + rng.integers(-20, 21, rgb.shape[:2]), 0, 255)
+    return rgb_s, d_s, rgb_t, d_t
+
+
+def small_guess(seed):
+    """A perturbed initial guess (float32 4x4)."""
+    rng = np.random.default_rng(seed)
+    w = rng.uniform(-0.02, 0.02, 3); t = rng.uniform(-0.05, 0.05, 3)
+    th = np.linalg.norm(w); k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    T = np.eye(4)
+    T[:3, :3] = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+    T[:3, 3] = t
+    return T.astype(np.float32)
+
+
+# name -> (builder kwargs).  method: 0 photo, 1 depth, 2 photo+depth (RPI.h:195)
+CASES = {
+    "synth_128x256_L3_pd": dict(rows=128, cols=256, levels=3, method=2, frames=(0, 1)),
+    "synth_128x256_L3_photo": dict(rows=128, cols=256, levels=3, method=0, frames=(2, 3)),
+    "synth_128x256_L3_depth": dict(rows=128, cols=256, levels=3, method=1, frames=(4, 5)),
+    "synth_256x512_L4_pd_guess": dict(rows=256, cols=512, levels=4, method=2, frames=(6, 7), guess=11),
+    "synth_256x512_L4_pd_far": dict(rows=256, cols=512, levels=4, method=2, frames=(0, 9)),
+    "synth_128x256_L3_holes": dict(rows=128, cols=256, levels=3, method=2, frames=(8, 9), holes=5),
+    "synth_256x512_L5_odo": dict(rows=256, cols=512, levels=5, method=2, frames=(20, 21), std_photo=3.0 / 255),
+    "loop_128x256_L3": dict(rows=128, cols=256, levels=3, method=2, kind=1, frames=(3, 17), guess_gt=True),
+    "sample_pair_1920x320_L4": dict(sample=True, levels=4, method=2),
+}
+
+
+def make_case(orc, name):
+    """-> dict(rgb_s, d_s, rgb_t, d_t, levels, method, guess (4x4 f32 or None), std_photo)."""
+    c = CASES[name]
+    if c.get("sample"):
+        z = np.load(os.path.join(GOLD, "sample_pair.npz"))
+        rgb_s, d_s, rgb_t, d_t = z["src_rgb"], z["src_depth"], z["trg_rgb"], z["trg_depth"]
+    else:
+        kind = c.get("kind", 0)
+        a, b = c["frames"]
+        rgb_s, d_s, rgb_t, d_t = _synth(orc, kind, a, b, c["rows"], c["cols"])   # target a, source b
+        if "holes" in c:
+            rgb_s, d_s, rgb_t, d_t = _holes(rgb_s, d_s, rgb_t, d_t, c["holes"])
+    guess = None
+    if "guess" in c:
+        guess = small_guess(c["guess"])
+    if c.get("guess_gt"):
+        a, b = c["frames"]
+        G = orc.synth_gt_pose(c.get("kind", 0), b, a)
+        guess = (small_guess(99).astype(np.float64) @ G).astype(np.float32)
+    return dict(rgb_s=rgb_s, d_s=d_s, rgb_t=rgb_t, d_t=d_t, levels=c["levels"], method=c["method"],
+                guess=guess, std_photo=c.get("std_photo", 6.0 / 255))
+
+
+def probe_poses(n=3):
+    """Level-0 probe poses for errorPhotoICP_sphere / calcHessGrad_sphere called directly."""
+    return [np.eye(4, dtype=np.float32)] + [small_guess(100 + i) for i in range(n - 1)]
