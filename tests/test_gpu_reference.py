@@ -65,11 +65,16 @@ def test_cuda_path_equals_reference(orc, r360, gold, name):
             assert abs(e2 - pr["err2"]) <= REL * pr["err2"]
             H, g, nvis = ctx.eval_hessgrad(0, 1, 0, T)
             assert np.float32(nvis) / np.float32(N0) == np.float32(pr["sso"])
+            # The reference sums H and g in 27 FLOAT accumulators (RPI.h:3117-3194); recorded at one
+            # thread that is a serial float sum of up to 2*N0 terms whose own rounding error grows
+            # like sqrt(N0)*2^-24 (1.1e-4 observed at N0 = 614400, the sample pair).  The GPU sums in
+            # double, so above 2^18 pixels the comparison allows for the reference's error.
+            rel_h = REL if N0 <= (1 << 18) else 5 * REL
             Hr = np.array(pr["H"]).reshape(6, 6)
             sc = np.sqrt(np.outer(np.diag(Hr), np.diag(Hr)))
-            assert np.all(np.abs(H - Hr) <= REL * sc), np.max(np.abs(H - Hr) / sc)
+            assert np.all(np.abs(H - Hr) <= rel_h * sc), np.max(np.abs(H - Hr) / sc)
             gs = np.sqrt(np.diag(Hr) * pr["err2"])
-            assert np.all(np.abs(g - np.array(pr["g"])) <= REL * gs)
+            assert np.all(np.abs(g - np.array(pr["g"])) <= rel_h * gs)
         # a10: the whole coarse-to-fine run
         guess = None if case["guess"] is None else r360.pose_to_colmajor(case["guess"])[None]
         res, tr = ctx.register_pairs([0], [1], guess, trace=True)
