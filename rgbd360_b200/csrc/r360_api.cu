@@ -337,7 +337,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     cudaDeviceProp prop;
     CK(c, cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    c->pass_grid = c->sm_count * 2;
+    c->pass_grid = c->sm_count * R360_PASS_CTAS;
     CK(c, r360_pass_init());
     CK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));

@@ -284,7 +284,11 @@ __device__ __forceinline__ void r360_cp_async_commit() { asm volatile("cp.async.
 __device__ __forceinline__ void r360_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 template <int METHOD>
-__global__ void __launch_bounds__(R360_PASS_THREADS, 2)
+#ifdef R360_PASS_MAXNREG
+__global__ void __maxnreg__(R360_PASS_MAXNREG)               // explicit register cap (variant builds)
+#else
+__global__ void __launch_bounds__(R360_PASS_THREADS, R360_PASS_CTAS)
+#endif
 k_pass(R360PassArgs a) {
     extern __shared__ float4 s_pipe[];                       // [stage][texel | geometry][thread][3]
     __shared__ float s_red[R360_PASS_THREADS / 32][R360_ACC_DOUBLES];

@@ -92,3 +92,32 @@ def allgather_results(local, pair_ids, n_total, device=None):
         out[gid] = recs
         out["pair_id"][gid] = gid
     return out
+
+
+# ---------------------------------------------------------------- config 5: perturbed initial guesses
+def _splitmix64(state):
+    state = (state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return state, z ^ (z >> 31)
+
+
+def loop_closure_guess(pair_id, gt_pose, max_t=0.05, max_w=0.02):
+    """Initial guess of loop-closure candidate `pair_id`: the ground-truth
+    relative pose composed with exp(delta), delta ~ U(+-max_t m, +-max_w rad) drawn from
+    splitmix64(0xC105E + pair_id).  Returns a float32 4x4."""
+    s = (0xC105E + int(pair_id)) & 0xFFFFFFFFFFFFFFFF
+    u = []
+    for _ in range(6):
+        s, z = _splitmix64(s)
+        u.append((z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0)
+    t = np.array(u[:3]) * max_t
+    w = np.array(u[3:]) * max_w
+    th = float(np.linalg.norm(w))
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) + (np.sin(th) / th if th > 0 else 1.0) * K + ((1 - np.cos(th)) / (th * th) if th > 0 else 0.5) * K @ K
+    D = np.eye(4)
+    D[:3, :3] = R
+    D[:3, 3] = t
+    return (D @ np.asarray(gt_pose, np.float64)).astype(np.float32)
