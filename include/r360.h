@@ -162,6 +162,34 @@ int r360_synth_frames(r360_ctx* ctx, int kind, int first_id, int n, uint8_t* rgb
 /* Ground-truth pose T_trg<-src (column-major 4x4 double) between two synthetic frames. */
 void r360_synth_gt_pose(int kind, int src_id, int trg_id, double T[16]);
 
+/* ---- Frame360 ingest: the step right before the path --------------------------
+ * Calib360 (include/Calib360.h:69-131): pinhole intrinsics shared by the 8 sensors and the INVERSE
+ * of each sensor's extrinsic matrix (Rt_inv[s] = Rt_[s].inverse(), column-major 4x4). */
+typedef struct r360_rig {
+    int32_t sensor_rows, sensor_cols;   /* 240, 320 (QVGA, Calib360.h:63-65)                      */
+    float   fx, fy, cx, cy;             /* 262.5, 262.5, 159.5, 119.5 (Calib360.h:75-77)           */
+    float   Rt_inv[8][16];
+} r360_rig;
+void r360_default_rig(r360_rig* rig);   /* QVGA intrinsics, identity extrinsics */
+
+/* Frame360::loadFrame (include/Frame360.h:231-266): parses a Frame360 .bin (boost binary_oarchive of
+ * 16 cv::Mat records, third_party/cvSerialization/cvmat_serialization.h:22-54, alternating RGB
+ * CV_8UC3 and depth CV_16UC1 for sensors 0..7).  rgb: 8 x rows x cols x 3, depth_mm: 8 x rows x
+ * cols; either may be NULL to query the size only.  Host-only, no ctx needed. */
+int r360_frame360_parse(const uint8_t* bytes, size_t n_bytes, int32_t* sensor_rows, int32_t* sensor_cols,
+                        uint8_t* rgb, size_t rgb_capacity, uint16_t* depth_mm, size_t depth_capacity);
+
+/* Frame360::stitchSphericalImage (include/Frame360.h:386-405, 1099-1148) on the device for n
+ * frames, followed by setSourceFrame / setTargetFrame of the stitched spheres into frame slots
+ * [first, first+n) (as r360_set_frames).  sensor_rgb: n x 8 x sensor_rows x sensor_cols x 3,
+ * sensor_depth_mm: n x 8 x sensor_rows x sensor_cols (z-depth, millimetres).  The ctx must have been
+ * created with cols = 8 * sensor_rows and rows = (int)(cols * 0.5 * 60 / 180).
+ * sphere_rgb / sphere_depth_mm: optional host outputs (n x rows x cols [x 3]) of what the reference
+ * keeps as Frame360::sphereRGB / sphereDepth. */
+int r360_stitch_frames(r360_ctx* ctx, const r360_rig* rig, int first, int n, const uint8_t* sensor_rgb,
+                       const uint16_t* sensor_depth_mm, const uint8_t* roles, uint8_t* sphere_rgb,
+                       uint16_t* sphere_depth_mm);
+
 /* Device memory / stream plumbing for callers that keep data on the GPU. */
 int r360_device_alloc(r360_ctx* ctx, size_t bytes, void** ptr_dev);
 int r360_device_free(r360_ctx* ctx, void* ptr_dev);

@@ -70,7 +70,8 @@ def build(force=False):
     if force or not os.path.exists(_SO) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
         for f in ("rpi_oracle.cpp", "../rgbd360_b200/csrc/sphere_math.h",
-                  "../rgbd360_b200/csrc/gn_math.h", "../rgbd360_b200/csrc/synth.h", "../include/r360.h")
+                  "../rgbd360_b200/csrc/gn_math.h", "../rgbd360_b200/csrc/synth.h",
+                  "../rgbd360_b200/csrc/stitch_math.h", "../include/r360.h")
     ):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -100,6 +101,7 @@ def lib():
                                 C.POINTER(Result), C.c_void_p, C.c_int]
         L.orc_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_synth_gt_pose.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_stitch.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float] + [C.c_void_p] * 5
         L.orc_pinned_vec.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_pinned_sincos.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_rank6.argtypes = [C.c_void_p]
@@ -231,3 +233,15 @@ def pinned_vec(fn, a, b=None):
     out = np.zeros_like(a)
     lib().orc_pinned_vec(fn, a.size, _ptr(a), _ptr(b), _ptr(out))
     return out
+
+
+def stitch(sensor_rgb, sensor_depth, Rt_inv, fx=262.5, fy=262.5, cx=159.5, cy=119.5):
+    """Frame360::stitchSphericalImage (Frame360.h:386-405, 1099-1148).  sensor_rgb 8 x h x w x 3 u8,
+    sensor_depth 8 x h x w u16 mm, Rt_inv 8 x 4 x 4 (row-major numpy matrices)."""
+    sensor_rgb = np.ascontiguousarray(sensor_rgb, np.uint8); sensor_depth = np.ascontiguousarray(sensor_depth, np.uint16)
+    h, w = sensor_depth.shape[1:]
+    cols = 8 * h; rows = int(cols * 0.5 * 60.0 / 180)
+    R = np.ascontiguousarray(np.asarray(Rt_inv, np.float32).transpose(0, 2, 1)).reshape(8, 16)    # column-major
+    rgb = np.zeros((rows, cols, 3), np.uint8); d = np.zeros((rows, cols), np.uint16)
+    lib().orc_stitch(h, w, fx, fy, cx, cy, _ptr(R), _ptr(sensor_rgb), _ptr(sensor_depth), _ptr(rgb), _ptr(d))
+    return rgb, d

@@ -40,6 +40,7 @@
 #include "../rgbd360_b200/csrc/sphere_math.h"
 #include "../rgbd360_b200/csrc/gn_math.h"
 #include "../rgbd360_b200/csrc/synth.h"
+#include "../rgbd360_b200/csrc/stitch_math.h"
 
 #define ORC_INVALID_POINT (-10000.0f)   // RPI.h:40
 
@@ -654,6 +655,32 @@ void warp_dump(const Frame* src, const Frame* trg, int level, const float* T,
     }
 }
 
+// Frame360::stitchSphericalImage (Frame360.h:386-405, 1099-1148): 8 sensor images -> one sphere
+// image.  sensor_rgb: 8 x size_h x size_w x 3, sensor_depth: 8 x size_h x size_w (mm, z-depth);
+// Rt_inv: 8 column-major 4x4.  Outputs rows x cols of r360_stitch_geom.
+template <class M>
+void stitch_sphere(const R360StitchGeom& g, const float* Rt_inv, const uint8_t* sensor_rgb,
+                          const uint16_t* sensor_depth, uint8_t* rgb, uint16_t* depth) {
+    memset(rgb, 0, (size_t)g.rows * g.cols * 3);
+    memset(depth, 0, (size_t)g.rows * g.cols * 2);
+    const size_t spx = (size_t)g.size_h * g.size_w;
+#pragma omp parallel for
+    for (int r = 0; r < g.rows; ++r) {
+        const float phi = (g.offset_phi - r) * g.angle_pixel;
+        const float sp = M::sin_(phi), cp = M::cos_(phi);
+        for (int c = 0; c < g.cols; ++c) {
+            const int s = 7 - c / g.size_h;
+            const float theta = (c + g.offset_theta) * g.angle_pixel;
+            int ui, vi;
+            double sc;
+            if (!r360_stitch_pixel(g, Rt_inv + 16 * s, sp, cp, M::sin_(theta), M::cos_(theta), &ui, &vi, &sc)) continue;
+            const size_t j = (size_t)s * spx + (size_t)vi * g.size_w + ui, i = (size_t)r * g.cols + c;
+            rgb[3 * i] = sensor_rgb[3 * j]; rgb[3 * i + 1] = sensor_rgb[3 * j + 1]; rgb[3 * i + 2] = sensor_rgb[3 * j + 2];
+            depth[i] = r360_stitch_range(sensor_depth[j], sc);
+        }
+    }
+}
+
 }  // namespace
 
 // ====================================================================== C interface (ctypes)
@@ -775,6 +802,13 @@ void orc_synth_frame(int kind, int id, int rows, int cols, uint8_t* rgb, uint16_
     }
 }
 void orc_synth_gt_pose(int kind, int src_id, int trg_id, double* T) { r360_synth_relpose(kind, src_id, trg_id, T); }
+
+void orc_stitch(int size_h, int size_w, float fx, float fy, float cx, float cy, const float* Rt_inv,
+                const uint8_t* sensor_rgb, const uint16_t* sensor_depth, uint8_t* rgb, uint16_t* depth) {
+    const R360StitchGeom g = r360_stitch_geom(size_h, size_w, fx, fy, cx, cy);
+    if (g_math_mode) stitch_sphere<MathLibm>(g, Rt_inv, sensor_rgb, sensor_depth, rgb, depth);
+    else stitch_sphere<MathPinned>(g, Rt_inv, sensor_rgb, sensor_depth, rgb, depth);
+}
 
 // math hooks for tests/test_sphere_math.py
 float orc_pinned_asinf(float x) { return r360_asinf(x); }

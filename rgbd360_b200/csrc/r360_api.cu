@@ -54,6 +54,7 @@ struct Ctx {
     r360_result* d_res = nullptr; r360_result* h_res = nullptr;
     r360_iter_record* d_trace = nullptr; size_t trace_cap = 0;
     float* d_cams = nullptr; float* h_cams = nullptr;
+    uint8_t* d_sens_rgb = nullptr; uint16_t* d_sens_depth = nullptr; size_t sens_cap = 0;   // ingest: sensor images of one chunk
     // stats
     float last_ms = 0.f, pass_ms = 0.f;
     int pass_launches = 0;
@@ -317,6 +318,7 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_idx); cudaFreeHost(c->h_idx); cudaFree(c->d_pose); cudaFreeHost(c->h_pose);
     cudaFree(c->d_res); cudaFreeHost(c->h_res); cudaFree(c->d_trace);
     cudaFree(c->d_cams); cudaFreeHost(c->h_cams);
+    cudaFree(c->d_sens_rgb); cudaFree(c->d_sens_depth);
     for (auto e : c->ev_pass) cudaEventDestroy(e);
     for (int b = 0; b < kStages; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -724,6 +726,102 @@ int r360_synth_frames(r360_ctx* c, int kind, int first_id, int n, uint8_t* rgb, 
         CK(c, cudaMemcpy(rgb + (size_t)off * npx * 3, c->stage_rgb[0], (size_t)m * npx * 3, cudaMemcpyDeviceToHost));
         CK(c, cudaMemcpy(depth_mm + (size_t)off * npx, c->stage_depth[0], (size_t)m * npx * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     }
+    return R360_OK;
+}
+
+// ---------------------------------------------------------------- Frame360 ingest
+void r360_default_rig(r360_rig* rig) {
+    if (!rig) return;
+    memset(rig, 0, sizeof(*rig));
+    rig->sensor_rows = 240; rig->sensor_cols = 320;
+    rig->fx = 262.5f; rig->fy = 262.5f; rig->cx = 159.5f; rig->cy = 119.5f;          // Calib360.h:75-77
+    for (int s = 0; s < 8; ++s)
+        for (int k = 0; k < 4; ++k) rig->Rt_inv[s][5 * k] = 1.0f;
+}
+
+// boost::archive::binary_oarchive layout as written by the reference's grabber (64-bit little endian
+// build): 4-byte length-prefixed signature "serialization::archive" with its version and flags (45
+// bytes in all up to the first object), then per cv::Mat {int32 cols, int32 rows, uint64 elemSize,
+// uint64 type, raw pixels} (cvmat_serialization.h:22-37).
+int r360_frame360_parse(const uint8_t* b, size_t n_bytes, int32_t* sensor_rows, int32_t* sensor_cols,
+                        uint8_t* rgb, size_t rgb_capacity, uint16_t* depth_mm, size_t depth_capacity) {
+    static const char sig[] = "serialization::archive";
+    if (!b || n_bytes < 45 + 24) return R360_E_ARG;
+    if (memcmp(b + 8, sig, sizeof(sig) - 1) != 0) return R360_E_ARG;
+    size_t off = 45;
+    int rows0 = 0, cols0 = 0;
+    for (int k = 0; k < 16; ++k) {
+        if (off + 24 > n_bytes) return R360_E_ARG;
+        int32_t cols, rows;
+        uint64_t es, ty;
+        memcpy(&cols, b + off, 4); memcpy(&rows, b + off + 4, 4);
+        memcpy(&es, b + off + 8, 8); memcpy(&ty, b + off + 16, 8);
+        off += 24;
+        const bool is_rgb = (k % 2) == 0;
+        if (cols <= 0 || rows <= 0 || cols > 4096 || rows > 4096) return R360_E_ARG;
+        if (is_rgb ? (es != 3 || ty != 16) : (es != 2 || ty != 2)) return R360_E_ARG;     // CV_8UC3 / CV_16UC1
+        if (k == 0) { rows0 = rows; cols0 = cols; }
+        else if (rows != rows0 || cols != cols0) return R360_E_ARG;
+        const size_t nb = (size_t)rows * cols * es;
+        if (off + nb > n_bytes) return R360_E_ARG;
+        const size_t s = (size_t)(k / 2);
+        if (is_rgb && rgb) {
+            if ((s + 1) * nb > rgb_capacity) return R360_E_ARG;
+            memcpy(rgb + s * nb, b + off, nb);
+        }
+        if (!is_rgb && depth_mm) {
+            if ((s + 1) * nb > depth_capacity * sizeof(uint16_t)) return R360_E_ARG;
+            memcpy((uint8_t*)depth_mm + s * nb, b + off, nb);
+        }
+        off += nb;
+    }
+    if (sensor_rows) *sensor_rows = rows0;
+    if (sensor_cols) *sensor_cols = cols0;
+    return R360_OK;
+}
+
+int r360_stitch_frames(r360_ctx* c, const r360_rig* rig, int first, int n, const uint8_t* sensor_rgb,
+                       const uint16_t* sensor_depth_mm, const uint8_t* roles, uint8_t* sphere_rgb,
+                       uint16_t* sphere_depth_mm) {
+    if (!c) return R360_E_ARG;
+    if (!rig || !sensor_rgb || !sensor_depth_mm || n < 0 || first < 0 || first + n > c->max_frames)
+        return fail(c, R360_E_ARG, "stitch_frames: bad range [%d,%d) of %d slots or null input", first, first + n, c->max_frames);
+    R360StitchArgs a;
+    a.g = r360_stitch_geom(rig->sensor_rows, rig->sensor_cols, rig->fx, rig->fy, rig->cx, rig->cy);
+    if (a.g.rows != c->rows || a.g.cols != c->cols)
+        return fail(c, R360_E_ARG, "stitch_frames: rig gives a %dx%d sphere, the context holds %dx%d", a.g.cols, a.g.rows, c->cols, c->rows);
+    if (roles)
+        for (int k = 0; k < n; ++k)
+            if (roles[k] < 1 || roles[k] > 3) return fail(c, R360_E_ARG, "stitch_frames: role %d of frame %d invalid", roles[k], k);
+    memcpy(a.Rt_inv, rig->Rt_inv, sizeof(a.Rt_inv));
+    CK(c, cudaSetDevice(c->device));
+    const size_t spx = (size_t)rig->sensor_rows * rig->sensor_cols * 8, npx = (size_t)c->rows * c->cols;
+    if (c->sens_cap < spx * c->chunk) {
+        cudaFree(c->d_sens_rgb); cudaFree(c->d_sens_depth);
+        c->d_sens_rgb = nullptr; c->d_sens_depth = nullptr; c->sens_cap = 0;
+        CK(c, cudaMalloc(&c->d_sens_rgb, spx * 3 * c->chunk));
+        CK(c, cudaMalloc(&c->d_sens_depth, spx * sizeof(uint16_t) * c->chunk));
+        c->sens_cap = spx * c->chunk;
+    }
+    CK(c, cudaEventRecord(c->ev_t0, c->st));
+    for (int off = 0; off < n; off += c->chunk) {
+        const int m = std::min(c->chunk, n - off);
+        const int b = (int)(c->n_chunks_done % kStages);
+        CK(c, cudaMemcpyAsync(c->d_sens_rgb, sensor_rgb + (size_t)off * spx * 3, (size_t)m * spx * 3, cudaMemcpyHostToDevice, c->st));
+        CK(c, cudaMemcpyAsync(c->d_sens_depth, sensor_depth_mm + (size_t)off * spx, (size_t)m * spx * sizeof(uint16_t), cudaMemcpyHostToDevice, c->st));
+        r360_launch_stitch(c->st, a, c->d_sens_rgb, c->d_sens_depth, c->stage_rgb[b], c->stage_depth[b], m, c->sm_count);
+        ++c->launches;
+        int rc = build_chunk(c, first + off, m, c->stage_rgb[b], c->stage_depth[b], nullptr, roles ? roles + off : nullptr, off);
+        if (rc) return rc;
+        if (sphere_rgb) CK(c, cudaMemcpyAsync(sphere_rgb + (size_t)off * npx * 3, c->stage_rgb[b], (size_t)m * npx * 3, cudaMemcpyDeviceToHost, c->st));
+        if (sphere_depth_mm) CK(c, cudaMemcpyAsync(sphere_depth_mm + (size_t)off * npx, c->stage_depth[b], (size_t)m * npx * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->st));
+        CK(c, cudaEventRecord(c->ev_done[b], c->st));
+        ++c->n_chunks_done;
+        CK(c, cudaStreamSynchronize(c->st));             // the sensor buffer is reused by the next chunk
+    }
+    CK(c, cudaEventRecord(c->ev_t1, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    CK(c, cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1));
     return R360_OK;
 }
 

@@ -12,6 +12,7 @@
 //                                      alignFrames360 (RPI.h:4519-4784), no host sync
 //       k_warp_dump                    parity hook: index maps + validity masks
 //       k_synth                        synthetic sphere frames
+//       k_stitch                       Frame360 ingest: 8 sensor images -> sphere RGB8 / depth u16 (Frame360.h:1099-1148)
 //
 // HBM-bound gather/reduction: no tensor cores.  Compiled with --fmad=false (sphere_math.h).
 #include "r360_device.cuh"
@@ -733,6 +734,41 @@ k_synth(int kind, int first_id, int rows, int cols, const float* __restrict__ ca
     }
 }
 
+// =========================================================================== K0: Frame360 ingest
+// Frame360::stitchSphericalImage (Frame360.h:386-405, 1099-1148): one thread per sphere pixel looks
+// its ray up in the sensor that owns its column band (stitch_math.h) and copies the nearest-below
+// sensor pixel; depth is rescaled from z to Euclidean range.  Writes exactly the RGB8 / depth-u16
+// sphere images the pyramid kernels (K1) read, so ingest + pyramids stay on the device.
+__global__ void __launch_bounds__(256)
+k_stitch(R360StitchArgs a, const uint8_t* __restrict__ sensor_rgb, const uint16_t* __restrict__ sensor_depth,
+         uint8_t* __restrict__ rgb, uint16_t* __restrict__ depth_mm) {
+    const R360StitchGeom g = a.g;
+    const int f = blockIdx.y;
+    const int n = g.rows * g.cols;
+    const size_t spx = (size_t)g.size_h * g.size_w;
+    const uint8_t* __restrict__ srgb = sensor_rgb + (size_t)f * 8 * spx * 3;
+    const uint16_t* __restrict__ sdep = sensor_depth + (size_t)f * 8 * spx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = i / g.cols, c = i - r * g.cols;
+        const int s = 7 - c / g.size_h;
+        float sp, cp, st, ct;
+        r360_sincosf((g.offset_phi - r) * g.angle_pixel, &sp, &cp);
+        r360_sincosf((c + g.offset_theta) * g.angle_pixel, &st, &ct);
+        int ui, vi;
+        double sc;
+        uint8_t p0 = 0, p1 = 0, p2 = 0;
+        uint16_t d = 0;
+        if (r360_stitch_pixel(g, a.Rt_inv[s], sp, cp, st, ct, &ui, &vi, &sc)) {
+            const size_t j = (size_t)s * spx + (size_t)vi * g.size_w + ui;
+            p0 = srgb[3 * j]; p1 = srgb[3 * j + 1]; p2 = srgb[3 * j + 2];
+            d = r360_stitch_range(sdep[j], sc);
+        }
+        const size_t o = (size_t)f * n + i;
+        rgb[3 * o] = p0; rgb[3 * o + 1] = p1; rgb[3 * o + 2] = p2;
+        depth_mm[o] = d;
+    }
+}
+
 // =========================================================================== launch wrappers
 static inline int r360_blocks(long long n, int threads, int cap) {
     long long b = (n + threads - 1) / threads;
@@ -792,6 +828,11 @@ void r360_launch_gn_step(cudaStream_t st, const R360GnArgs& g, int level) {
 }
 void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols, int pair_id0) {
     k_finalize<<<r360_blocks(g.n_pairs, 128, 1024), 128, 0, st>>>(g, out, rows, cols, pair_id0);
+}
+void r360_launch_stitch(cudaStream_t st, const R360StitchArgs& a, const uint8_t* sensor_rgb, const uint16_t* sensor_depth,
+                        uint8_t* rgb, uint16_t* depth_mm, int n_frames, int sm_count) {
+    dim3 grid(r360_blocks((long long)a.g.rows * a.g.cols, 256, sm_count * 8), n_frames);
+    k_stitch<<<grid, 256, 0, st>>>(a, sensor_rgb, sensor_depth, rgb, depth_mm);
 }
 void r360_launch_synth(cudaStream_t st, int kind, int first_id, int rows, int cols, const float* cams, int n_frames,
                        uint8_t* rgb, uint16_t* depth_mm, int sm_count) {

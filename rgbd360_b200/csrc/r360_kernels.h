@@ -1,8 +1,14 @@
 // r360_kernels.h -- launch interface between the host API (r360_api.cu) and the kernels.
 #pragma once
 #include "r360_device.cuh"
+#include "stitch_math.h"
 
-#define R360_PASS_THREADS 256
+#ifndef R360_PASS_THREADS
+#define R360_PASS_THREADS 256                 // threads per CTA of k_pass
+#endif
+#ifndef R360_PASS_CTAS
+#define R360_PASS_CTAS 2                      // resident CTAs per SM of k_pass (persistent grid = CTAS x SMs)
+#endif
 
 struct R360PassArgs {
     R360Level lv;
@@ -17,6 +23,11 @@ struct R360PassArgs {
     const float* const* trg_base;       // device: per pair, target texel pyramid
     double* acc;                        // device: per pair R360_ACC_DOUBLES
     int* cnt;                           // device: per pair R360_ACC_INTS
+};
+
+struct R360StitchArgs {
+    R360StitchGeom g;
+    float Rt_inv[8][16];                // inverse extrinsics of the 8 sensors, column-major (Calib360.h:122-131)
 };
 
 struct R360GnArgs {
@@ -41,6 +52,8 @@ void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid);
 void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
                            uint8_t* vp, uint8_t* vd, int sm_count);
 void r360_launch_index_stats(cudaStream_t st, const R360PassArgs& a, int pair, unsigned long long* out, int sm_count);
+void r360_launch_stitch(cudaStream_t st, const R360StitchArgs& a, const uint8_t* sensor_rgb, const uint16_t* sensor_depth,
+                        uint8_t* rgb, uint16_t* depth_mm, int n_frames, int sm_count);
 void r360_launch_pairs_init(cudaStream_t st, const R360GnArgs& g, const int32_t* src_idx, const int32_t* trg_idx,
                             const float* init_pose);
 void r360_launch_level_begin(cudaStream_t st, const R360GnArgs& g, int level);

@@ -19,6 +19,7 @@ EXPORTS = [
     "r360_synth_frames_dev", "r360_synth_frames", "r360_synth_gt_pose", "r360_device_alloc",
     "r360_device_free", "r360_synchronize", "r360_last_device_ms", "r360_kernel_launches",
     "r360_last_pass_stats", "r360_version", "r360_index_stats", "r360_register_host_pairs",
+    "r360_default_rig", "r360_frame360_parse", "r360_stitch_frames",
 ]
 
 
@@ -53,6 +54,12 @@ class IterRecord(C.Structure):
         ("pose", C.c_float * 16), ("hessian", C.c_float * 21), ("gradient", C.c_float * 6),
         ("pad", C.c_float),
     ]
+
+
+class Rig(C.Structure):
+    """Calib360 (Calib360.h:69-131): shared pinhole intrinsics + inverse extrinsics of the 8 sensors."""
+    _fields_ = [("sensor_rows", C.c_int32), ("sensor_cols", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("Rt_inv", (C.c_float * 16) * 8)]
 
 
 RESULT_DTYPE = np.dtype([
@@ -116,8 +123,48 @@ def lib():
     L.r360_kernel_launches.argtypes = [vp]
     L.r360_kernel_launches.restype = C.c_int64
     L.r360_last_pass_stats.argtypes = [vp, C.POINTER(f32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.r360_default_rig.argtypes = [C.POINTER(Rig)]
+    L.r360_default_rig.restype = None
+    L.r360_frame360_parse.argtypes = [vp, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, C.c_size_t, vp, C.c_size_t]
+    L.r360_stitch_frames.argtypes = [vp, C.POINTER(Rig), i32, i32, vp, vp, vp, vp, vp]
     _lib = L
     return L
+
+
+def make_rig(Rt_inv=None, sensor_rows=240, sensor_cols=320, fx=262.5, fy=262.5, cx=159.5, cy=119.5):
+    """r360_rig from 8 inverse extrinsic matrices (4x4, row-major numpy) -- Calib360::Rt_inv."""
+    rig = Rig()
+    lib().r360_default_rig(C.byref(rig))
+    rig.sensor_rows, rig.sensor_cols = sensor_rows, sensor_cols
+    rig.fx, rig.fy, rig.cx, rig.cy = fx, fy, cx, cy
+    if Rt_inv is not None:
+        M = np.asarray(Rt_inv, np.float32).reshape(8, 4, 4)
+        for s in range(8):
+            col = np.ascontiguousarray(M[s].T).reshape(16)
+            for k in range(16):
+                rig.Rt_inv[s][k] = float(col[k])
+    return rig
+
+
+def sphere_shape(sensor_rows):
+    """(rows, cols) of the stitched sphere image (Frame360.h:391-392)."""
+    cols = 8 * sensor_rows
+    return int(cols * 0.5 * 60.0 / 180), cols
+
+
+def frame360_parse(data):
+    """Frame360::loadFrame (Frame360.h:231-266) on the bytes of a .bin: -> (rgb 8xhxwx3 u8, depth 8xhxw u16)."""
+    buf = np.frombuffer(data, np.uint8)
+    r, c = C.c_int32(), C.c_int32()
+    rc = lib().r360_frame360_parse(buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(r), C.byref(c), None, 0, None, 0)
+    if rc:
+        raise R360Error(f"r360_frame360_parse: not a Frame360 archive (error {rc})")
+    rgb = np.zeros((8, r.value, c.value, 3), np.uint8); dep = np.zeros((8, r.value, c.value), np.uint16)
+    rc = lib().r360_frame360_parse(buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(r), C.byref(c),
+                                   rgb.ctypes.data_as(C.c_void_p), rgb.size, dep.ctypes.data_as(C.c_void_p), dep.size)
+    if rc:
+        raise R360Error(f"r360_frame360_parse failed (error {rc})")
+    return rgb, dep
 
 
 def default_params(**kw):
@@ -196,6 +243,18 @@ class Context:
         r = None if roles is None else np.ascontiguousarray(roles, np.uint8)
         fn = self.L.r360_set_frames_dev if device else self.L.r360_set_frames
         self._ck(fn(self.h, first, n, _p(rgb_ptr), _p(depth_ptr), _p(r)))
+
+    def stitch_frames(self, rig, first, sensor_rgb, sensor_depth, roles=None, want_sphere=True):
+        """Frame360::stitchSphericalImage on the device + set*Frame of the stitched spheres.
+        sensor_rgb: n x 8 x h x w x 3 u8, sensor_depth: n x 8 x h x w u16 (mm)."""
+        sensor_rgb = np.ascontiguousarray(sensor_rgb, np.uint8); sensor_depth = np.ascontiguousarray(sensor_depth, np.uint16)
+        n = sensor_rgb.shape[0]
+        r = None if roles is None else np.ascontiguousarray(roles, np.uint8)
+        srgb = np.zeros((n, self.rows, self.cols, 3), np.uint8) if want_sphere else None
+        sdep = np.zeros((n, self.rows, self.cols), np.uint16) if want_sphere else None
+        self._ck(self.L.r360_stitch_frames(self.h, C.byref(rig), first, n, _p(sensor_rgb), _p(sensor_depth), _p(r),
+                                           _p(srgb), _p(sdep)))
+        return srgb, sdep
 
     def synth_frames(self, kind, first_id, n):
         rgb = np.zeros((n, self.rows, self.cols, 3), np.uint8)

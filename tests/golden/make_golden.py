@@ -99,6 +99,17 @@ def main():
         print(name, srgb.shape, sd.shape, "valid depth %.3f" % np.mean((sd > 300) & (sd < 6000)))
     np.savez_compressed(os.path.join(HERE, "sample_pair.npz"), **out)
 
+    # ---- 1b. raw sensor images of sphere_images_1.bin (ingest fixture, tests/test_ingest.py)
+    import hashlib
+    path = f"{REF}/samples/sphere_images_1.bin"
+    b = open(path, "rb").read()
+    rgb, depth = load_frame360(path)
+    body = 16 * 24 + sum(a.nbytes for a in rgb) + sum(a.nbytes for a in depth)
+    Rt = np.stack([np.loadtxt(f"{REF}/Calibration/Extrinsics/Rt_0{s + 1}.txt") for s in range(8)])
+    np.savez_compressed(os.path.join(HERE, "frame360_raw_1.npz"), rgb=np.stack(rgb), depth=np.stack(depth),
+                        preamble=np.frombuffer(b[:45], np.uint8), tail=np.frombuffer(b[45 + body:], np.uint8), Rt=Rt,
+                        sha256=np.array(hashlib.sha256(b).hexdigest()))
+
     # ---- 2. cv2 vectors
     rng = np.random.default_rng(360)
     rgb = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
