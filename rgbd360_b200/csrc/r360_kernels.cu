@@ -379,6 +379,10 @@ k_pass(R360PassArgs a) {
 
         stage_a(0u);
         unsigned st_b = 0u;                                          // stage of pixel pair k
+#ifdef R360_PASS_UNROLL
+        constexpr int kUnroll = R360_PASS_UNROLL;
+#pragma unroll kUnroll
+#endif
         for (int k = 0; k < n_it; ++k) {
             if (k + 1 < n_it) {
                 s_cur = s_nxt;

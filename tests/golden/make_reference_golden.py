@@ -37,15 +37,28 @@ def run_reference(case, pinned, threads=1):
     out = dict(pose=a["pose"].astype(np.float64).ravel().tolist(), H=a["H"].astype(np.float64).ravel().tolist(),
                g=a["g"].astype(np.float64).tolist(), sso=a["sso"], iters=a["iters"].tolist(),
                trace_err2=a["err2"].tolist(), trace_n_valid=a["n_valid"].tolist(), ill_posed=bool(a["ill_posed"]))
+    if len(a["err2"]) <= case["levels"] and not a["ill_posed"]:
+        # no loop body ever ran: calcHessGrad_sphere was never called and the getters return the
+        # class's UNINITIALISED hessian / gradient / SSO members (RPI.h:112-115, no ctor init)
+        out["H"] = out["g"] = out["sso"] = None
     planes = {}
     for l in range(case["levels"]):
         for which, tag in ((0, "src"), (1, "trg")):
             for k, v in R.level(which, l).items():
+                if k in ("ggx", "ggy", "dgx", "dgy"):
+                    # The reference zeroes the sensor-joint columns inside alignFrames360, level by level
+                    # (RPI.h:4537-4549); levels it never reaches (ILL-POSED return) stay unmasked.  The
+                    # product applies the same (idempotent) mask when the target pyramid is built, so the
+                    # recording is taken with the mask applied at every level.
+                    ws = v.shape[1] // 8
+                    for q in range(1, 8):
+                        v[:, q * ws - 1:q * ws + 1] = 0
                 planes[f"{tag}{l}_{k}"] = digest(v)
     out["planes_sha"] = planes
-    out["lut0_sha"] = digest(canonical_lut(R.lut()))
+    # after an ILL-POSED return the LUT is the one of the level where the run stopped, not level 0
+    out["lut0_sha"] = None if a["ill_posed"] else digest(canonical_lut(R.lut()))
     probes = []
-    for T in refcases.probe_poses():
+    for T in ([] if a["ill_posed"] else refcases.probe_poses()):
         e, e2, n = R.error(0, T, case["method"])
         H, g, sso = R.hessgrad(0, T, case["method"])
         probes.append(dict(err2=e2, n_valid=n, H=H.astype(np.float64).ravel().tolist(), g=g.astype(np.float64).tolist(), sso=sso))

@@ -53,12 +53,28 @@ CASES = {
     "synth_256x512_L5_odo": dict(rows=256, cols=512, levels=5, method=2, frames=(20, 21), std_photo=3.0 / 255),
     "loop_128x256_L3": dict(rows=128, cols=256, levels=3, method=2, kind=1, frames=(3, 17), guess_gt=True),
     "sample_pair_1920x320_L4": dict(sample=True, levels=4, method=2),
+    # quirk 9: ILL-POSED (RPI.h:4682-4690) -- photo-only on a texture that varies along columns only over a
+    # constant-range sphere: the first twist column of J is identically 0, rank(H + lambda diag H) = 5
+    "illposed_cols_only_photo": dict(special="illposed", rows=64, cols=128, levels=2, method=0),
+    # no salient pixel at all: numValidPts = 0, error = sqrt(0/0) = NaN, the loop never runs
+    "no_valid_pixels_const": dict(special="const", rows=64, cols=128, levels=2, method=2),
 }
 
 
 def make_case(orc, name):
     """-> dict(rgb_s, d_s, rgb_t, d_t, levels, method, guess (4x4 f32 or None), std_photo)."""
     c = CASES[name]
+    if c.get("special"):
+        rows, cols = c["rows"], c["cols"]
+        d = np.full((rows, cols), 2000, np.uint16)
+        if c["special"] == "illposed":
+            x = (np.sin(np.arange(cols) * 2 * np.pi / 32) * 60 + 128).astype(np.uint8)
+            gt = np.ascontiguousarray(np.repeat(np.repeat(x[None, :, None], rows, 0), 3, 2))
+            gs = np.ascontiguousarray(np.roll(gt, 1, axis=1))
+        else:
+            gt = gs = np.full((rows, cols, 3), 128, np.uint8)
+        return dict(rgb_s=gs, d_s=d, rgb_t=gt, d_t=d, levels=c["levels"], method=c["method"], guess=None,
+                    std_photo=6.0 / 255)
     if c.get("sample"):
         z = np.load(os.path.join(GOLD, "sample_pair.npz"))
         rgb_s, d_s, rgb_t, d_t = z["src_rgb"], z["src_depth"], z["trg_rgb"], z["trg_depth"]

@@ -88,9 +88,9 @@ def test_cuda_path_equals_reference(orc, r360, gold, name):
             assert list(res["iters"][:L]) == ref["iters"]
             ang, dist = pose_err(Tg, np.array(ref["pose"]).reshape(4, 4))
             assert ang <= POSE_RAD and dist <= POSE_M, (ang, dist)
-            assert abs(res["sso"] - ref["sso"]) < 1e-3
-            # first evaluation of the coarsest level is at the initial guess in both runs
-            assert res["status"] == 0 and not ref["ill_posed"]
+            if ref["sso"] is not None:
+                assert abs(res["sso"] - ref["sso"]) < 1e-3
+            assert (res["status"] != 0) == ref["ill_posed"]
         # every level-0 pose the GPU evaluated, replayed through the live reference at the same bits
         R = _live_reference(case)
         if R is not None:

@@ -65,9 +65,10 @@ def test_oracle_equals_recorded_reference(orc, gold, name, pinned):
                 for k, v in f.level(l).items():
                     assert _digest(v) == ref["planes_sha"][f"{tag}{l}_{k}"], (tag, l, k)
         # a6: LUT at level 0
-        lut = orc.lut(src, 0, P)
-        lut[lut[:, 0] == -10000.0, 1:] = 0        # y, z of invalid points are unspecified (RPI.h:4585)
-        assert _digest(lut) == ref["lut0_sha"]
+        if ref["lut0_sha"] is not None:
+            lut = orc.lut(src, 0, P)
+            lut[lut[:, 0] == -10000.0, 1:] = 0    # y, z of invalid points are unspecified (RPI.h:4585)
+            assert _digest(lut) == ref["lut0_sha"]
         # a10: iteration counts, and a8 through every evaluation of the run
         assert list(res.iters)[:L] == ref["iters"]
         t = _trace_in_call_order(tr, L)
@@ -75,9 +76,10 @@ def test_oracle_equals_recorded_reference(orc, gold, name, pinned):
         np.testing.assert_allclose([e for _, e in t], ref["trace_err2"], rtol=1e-12)
         # a9 / a11: final pose, Hessian, gradient, SSO -- bit-identical at one thread
         assert np.array_equal(orc.pose_from(res.pose).astype(np.float64).ravel(), np.array(ref["pose"]))
-        assert np.array_equal(np.array(res.hessian, np.float64).reshape(6, 6).T.ravel(), np.array(ref["H"]))
-        assert np.array_equal(np.array(res.gradient, np.float64), np.array(ref["g"]))
-        assert np.float32(res.sso) == np.float32(ref["sso"])
+        if ref["H"] is not None:          # None: never computed upstream (uninitialised members)
+            assert np.array_equal(np.array(res.hessian, np.float64).reshape(6, 6).T.ravel(), np.array(ref["H"]))
+            assert np.array_equal(np.array(res.gradient, np.float64), np.array(ref["g"]))
+            assert np.float32(res.sso) == np.float32(ref["sso"])
         assert (res.status != 0) == ref["ill_posed"]
         # a8 / a9 called directly at level 0
         for T, pr in zip(refcases.probe_poses(), ref["probes_level0"]):
