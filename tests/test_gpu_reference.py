@@ -92,7 +92,7 @@ def test_cuda_path_equals_reference(orc, r360, gold, name):
                 assert abs(res["sso"] - ref["sso"]) < 1e-3
             assert (res["status"] != 0) == ref["ill_posed"]
         # every level-0 pose the GPU evaluated, replayed through the live reference at the same bits
-        R = _live_reference(case)
+        R = None if ref["ill_posed"] else _live_reference(case)      # ILL-POSED: level 0 is never reached
         if R is not None:
             R.align(case["guess"], case["method"])          # leaves LUT_xyz_sphere at level 0
             per = gp.max_iters + 2
