@@ -159,9 +159,9 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": w["name"], "rows": w["rows"], "cols": w["cols"], "levels": w["levels"],
-                   "pairs_per_step": sample, "note": "CPU oracle (port of the reference; the reference itself "
-                   "needs Eigen/OpenCV/PCL/MRPT and cannot be built here), FAITHFUL accumulation, glibc math, "
-                   "OpenMP over all host threads"},
+                   "pairs_per_step": sample, "note": "CPU oracle: port of the reference, bit-identical to the "
+                   "reference header compiled against third-party stand-ins (oracle/_ref, too slow to time fairly); "
+                   "FAITHFUL accumulation, glibc math, OpenMP over all host threads"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} pairs per step x {args.steps} steps, frame build + alignFrames360"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
