@@ -362,3 +362,67 @@ def test_full_size_properties(orc, r360):
     assert ang <= POSE_RAD and dist <= POSE_M, (ang, dist)
     assert list(res_o.iters)[:L] == list(res[k]["iters"][:L])
     ctx.close()
+
+
+def test_edge_cases_empty_ragged_and_limits(orc, r360):
+    """Empty batch, frames of one role only, geometry the pyramid cannot halve, out-of-range indices,
+    and the smallest legal image (every level still has an even width)."""
+    ctx = r360.Context(64, 128, 3, 2, r360.default_params(n_levels=3))
+    rgb, dep = ctx.synth_frames(0, 0, 3)
+    assert len(ctx.register_pairs([], [])) == 0                                   # empty batch: no work, no error
+    ctx.set_frames(0, rgb[:0], dep[:0])                                          # empty frame range
+    ctx.set_frames(0, rgb, dep, [r360.ROLE_SOURCE, r360.ROLE_TARGET, r360.ROLE_BOTH])
+    with pytest.raises(r360.R360Error):
+        ctx.register_pairs([1], [0])                                             # frame 1 has no source pyramid / 0 no target
+    with pytest.raises(r360.R360Error):
+        ctx.register_pairs([0], [3])                                             # slot out of range
+    with pytest.raises(r360.R360Error):
+        ctx.register_pairs([0, 2, 0], [1, 1, 2])                                 # more pairs than max_pairs
+    with pytest.raises(r360.R360Error):
+        ctx.eval_error(0, 1, 3, np.eye(4))                                       # level out of range
+    ok = ctx.register_pairs([0, 2], [1, 2])                                      # ragged roles; a frame against itself
+    assert ok[1]["status"] == 0 and np.allclose(np.array(ok[1]["pose"]).reshape(4, 4), np.eye(4), atol=1e-5)
+    ctx.close()
+    for rows, cols, L in ((64, 130, 3), (66, 128, 3), (64, 128, 9)):             # cols % 2^L, rows % 2^(L-1), too many levels
+        with pytest.raises(r360.R360Error):
+            r360.Context(rows, cols, 2, 1, r360.default_params(n_levels=L))
+    # smallest image with 4 levels: 8 x 16 -> coarsest level 1 x 2
+    P = orc.default_params(n_levels=4)
+    small = r360.Context(8, 16, 2, 1, r360.default_params(n_levels=4))
+    rgb, dep = small.synth_frames(0, 0, 2)
+    small.set_frames(0, rgb, dep)
+    trg = orc.Frame(rgb[0], dep[0], P, True); src = orc.Frame(rgb[1], dep[1], P, False)
+    for level in range(4):
+        g = small.dump_level(0, level); o = trg.level(level)
+        for k in o:
+            assert np.array_equal(g[k].view(np.int32), o[k].view(np.int32)), (level, k)
+        ro, co, vpo, vdo = orc.warp(src, trg, level, POSES[1], P)
+        rg, cg, vpg, vdg = small.dump_warp(1, 0, level, POSES[1])
+        assert np.array_equal(ro, rg) and np.array_equal(co, cg) and np.array_equal(vpo, vpg) and np.array_equal(vdo, vdg)
+    res_o = orc.align(src, trg, None, P)
+    res_g = small.register_pairs([1], [0])[0]
+    assert list(res_g["iters"][:4]) == list(res_o.iters)[:4] and res_g["status"] == res_o.status
+    small.close()
+
+
+def test_large_image_4096x2048(orc, r360):
+    """Above BASELINE's size: 4096 x 2048, 5 levels (8.4 Mpixel level 0).  Packed index path == scalar on
+    every pixel, final pose replayed through the oracle (counts exact, sum 1e-4), converges to the
+    analytic ground truth."""
+    rows, cols, L = 2048, 4096, 5
+    ctx = r360.Context(rows, cols, 2, 1, r360.default_params(n_levels=L))
+    rgb, dep = ctx.synth_frames(0, 10, 2)
+    ctx.set_frames(0, rgb, dep, [r360.ROLE_TARGET, r360.ROLE_SOURCE])
+    res = ctx.register_pairs([1], [0])[0]
+    assert res["status"] == 0
+    T = np.array(res["pose"], np.float32).reshape(4, 4).T
+    ang, dist = pose_err(T, orc.synth_gt_pose(0, 11, 10))
+    assert ang < 5e-4 and dist < 1.5e-3, (ang, dist)
+    st = ctx.index_stats(1, 0, 0, T)
+    assert st["mismatch"] == 0 and st["valid"] == rows * cols
+    P = orc.default_params(n_levels=L)
+    trg = orc.Frame(rgb[0], dep[0], P, True); src = orc.Frame(rgb[1], dep[1], P, False)
+    e2, nv = orc.error(src, trg, 0, T, P)
+    assert nv == res["final_n_valid"]
+    assert abs(e2 - res["final_err2"]) <= REL * e2
+    ctx.close()
