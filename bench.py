@@ -363,8 +363,8 @@ def bind_to_gpu_numa_node(local_rank):
         if cpus:
             os.sched_setaffinity(0, cpus)
             return node
-    except Exception:
-        pass
+    except Exception as e:                      # noqa: BLE001 -- best effort, but say why on stderr
+        print(f"bench.py: NUMA binding skipped for local rank {local_rank}: {e!r}", file=sys.stderr)
     return None
 
 
