@@ -261,7 +261,7 @@ __device__ __forceinline__ void r360_index_pair(const float* __restrict__ T, con
 //            normal-equation accumulation.
 // Every thread reads only what it wrote itself, so the pipeline needs no block barrier.
 #define R360_SLOT_BYTES 48                                   // texels of 2 pixels = geometry of 2 pixels = 48 B
-#define R360_PASS_DYN_SMEM (2 * 2 * R360_PASS_THREADS * R360_SLOT_BYTES)
+#define R360_PASS_DYN_SMEM (R360_PASS_STAGES * 2 * R360_PASS_THREADS * R360_SLOT_BYTES)
 
 // Shared-memory accesses of the pipeline go through explicit 32-bit shared addresses held in a
 // register (the compiler otherwise re-derives them from %tid every iteration).
@@ -283,6 +283,7 @@ __device__ __forceinline__ float4 r360_lds128(unsigned smem) {
 }
 __device__ __forceinline__ void r360_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void r360_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void r360_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int METHOD>
 #ifdef R360_PASS_MAXNREG
@@ -377,24 +378,41 @@ k_pass(R360PassArgs a) {
             if (c >= lv.cols) { c -= lv.cols; ++r; }
         };
 
+        // prologue: pixel pairs 0 .. STAGES-2 in flight before the first stage B
+        constexpr int S = R360_PASS_STAGES;
+        constexpr unsigned RING_END = S * STAGE_BYTES;
         stage_a(0u);
+#pragma unroll
+        for (int p = 1; p < S - 1; ++p) {
+            if (p < n_it) {
+                s_cur = s_nxt;
+                s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
+                stage_a(p * STAGE_BYTES);
+            } else {
+                r360_cp_async_commit();
+            }
+        }
         unsigned st_b = 0u;                                          // stage of pixel pair k
+        unsigned st_a = (S - 1) * STAGE_BYTES;                       // stage the next stage A fills
 #ifdef R360_PASS_UNROLL
         constexpr int kUnroll = R360_PASS_UNROLL;
 #pragma unroll kUnroll
 #endif
         for (int k = 0; k < n_it; ++k) {
-            if (k + 1 < n_it) {
+            if (k + S - 1 < n_it) {
                 s_cur = s_nxt;
                 s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
-                stage_a(st_b ^ STAGE_BYTES);
+                stage_a(st_a);
             } else {
-                r360_cp_async_commit();                              // keeps "all but the newest group" == group k
+                r360_cp_async_commit();                              // keeps "all but the S-1 newest groups" == group k
             }
-            r360_cp_async_wait1();
+            st_a += STAGE_BYTES;
+            if (st_a == RING_END) st_a = 0u;
+            r360_cp_async_wait<S - 1>();
             // stage B: pixel pair k
             const unsigned rd = slot0 + st_b;
-            st_b ^= STAGE_BYTES;
+            st_b += STAGE_BYTES;
+            if (st_b == RING_END) st_b = 0u;
             const float4 q0 = r360_lds128(rd), q1 = r360_lds128(rd + 16), q2 = r360_lds128(rd + 32);
             const float4 g0 = r360_lds128(rd + GEO_OFF), g1 = r360_lds128(rd + GEO_OFF + 16), g2 = r360_lds128(rd + GEO_OFF + 32);
             const float2 ta[3] = { make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y) };

@@ -9,6 +9,9 @@
 #ifndef R360_PASS_UNROLL
 #define R360_PASS_UNROLL 2                    // main loop of k_pass unrolled x2 (stage parity becomes static): +1.7 % on B200
 #endif
+#ifndef R360_PASS_STAGES
+#define R360_PASS_STAGES 2                    // depth of the shared-memory gather pipeline of k_pass
+#endif
 #ifndef R360_PASS_CTAS
 #define R360_PASS_CTAS 2                      // resident CTAs per SM of k_pass (persistent grid = CTAS x SMs)
 #endif
