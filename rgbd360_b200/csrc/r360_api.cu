@@ -16,7 +16,10 @@ namespace {
 
 std::string g_create_error;
 
-constexpr int kChunkFrames = 16;     // max frames per pyramid-build launch / H2D staging buffer
+#ifndef R360_CHUNK_FRAMES
+#define R360_CHUNK_FRAMES 64
+#endif
+constexpr int kChunkFrames = R360_CHUNK_FRAMES;     // max frames per pyramid-build launch / H2D staging buffer
 constexpr int kStages = 4;           // staging buffers: the copy stream runs up to kStages - 1 chunks ahead
 constexpr int kStreamPairs = 64;     // pairs per registration batch of r360_register_host_pairs
 
@@ -125,6 +128,7 @@ R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) 
     g.cnt = c->d_cnt + (size_t)first * R360_ACC_INTS;
     g.active_list = c->d_active + first;
     g.n_active = c->d_nactive;
+    g.ticket = c->d_nactive + 2;
     g.trace = trace ? trace + (size_t)first * c->L * (c->P.max_iters + 2) : nullptr;
     return g;
 }
@@ -410,8 +414,8 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaMalloc(&c->d_acc, sizeof(double) * R360_ACC_DOUBLES * np));
     CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * R360_ACC_INTS * np));
     CK(c, cudaMalloc(&c->d_active, sizeof(int) * np));
-    CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 2));
-    CK(c, cudaMemset(c->d_nactive, 0, sizeof(int) * 2));
+    CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 4));      // [0] batch, [1] eval hooks, [2] completion ticket
+    CK(c, cudaMemset(c->d_nactive, 0, sizeof(int) * 4));
     CK(c, cudaMallocHost(&c->h_srcb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_srcb, sizeof(void*) * np));
     CK(c, cudaMallocHost(&c->h_trgb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_trgb, sizeof(void*) * np));
     CK(c, cudaMallocHost(&c->h_idx, sizeof(int32_t) * 2 * np)); CK(c, cudaMalloc(&c->d_idx, sizeof(int32_t) * 2 * np));
@@ -473,14 +477,14 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
     ++c->launches;
     for (int level = c->L - 1; level >= 0; --level) {                 // RPI.h:4531
         r360_launch_level_begin(c->st, g, level);
-        c->launches += 2;
+        ++c->launches;
         R360PassArgs a = pass_args(c, level, n, first);
         for (int k = 0; k <= c->P.max_iters; ++k) {                   // 1 initial + <= max_iters loop bodies
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
             r360_launch_pass(c->st, a, c->pass_grid);
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
             r360_launch_gn_step(c->st, g, level);
-            c->launches += 3;
+            c->launches += 2;
         }
     }
     r360_launch_finalize(c->st, g, c->d_res + first, c->rows, c->cols, first);

@@ -570,12 +570,29 @@ __device__ void r360_compact_active(R360Pair* pairs, int n, int* active_list, in
     int base = 0;
     for (int p0 = 0; p0 < n; p0 += 32) {
         const int p = p0 + lane;
-        const bool on = p < n && pairs[p].active;
+        const bool on = p < n && *(volatile int*)&pairs[p].active;
         const unsigned m = __ballot_sync(0xffffffffu, on);
         if (on) active_list[base + __popc(m & ((1u << lane) - 1))] = p;
         base += __popc(m);
     }
     if (lane == 0) *n_active = base;
+}
+
+// The last block of a state-machine kernel to finish rebuilds the compact active list (what a
+// separate one-warp launch did before: 135 launches per 64-pair batch fewer).
+__device__ void r360_compact_when_last(const R360GnArgs& g) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(g.ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x < 32) r360_compact_active(g.pairs, g.n_pairs, g.active_list, g.n_active);
+        if (threadIdx.x == 0) *g.ticket = 0;
+    }
 }
 
 // Start of a pyramid level (RPI.h:4589-4605): evaluate the current estimate first.
@@ -592,10 +609,7 @@ __global__ void k_level_begin(R360GnArgs g, int level) {
         ps->ev = 0;
         ps->active = 1;
     }
-}
-
-__global__ void k_compact(R360GnArgs g) {
-    if (threadIdx.x < 32 && blockIdx.x == 0) r360_compact_active(g.pairs, g.n_pairs, g.active_list, g.n_active);
+    r360_compact_when_last(g);
 }
 
 // One step of the per-pair state machine after a pixel pass (RPI.h:4599-4722).
@@ -691,6 +705,7 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
         r360_mat4_mul(Tf, ps->pose_estim, Tn);
         for (int k = 0; k < 16; ++k) ps->pose_eval[k] = Tn[k];
     }
+    r360_compact_when_last(g);
 }
 
 __global__ void k_pairs_init(R360GnArgs g, const int32_t* __restrict__ src_idx,
@@ -842,11 +857,9 @@ void r360_launch_pairs_init(cudaStream_t st, const R360GnArgs& g, const int32_t*
 }
 void r360_launch_level_begin(cudaStream_t st, const R360GnArgs& g, int level) {
     k_level_begin<<<r360_blocks(g.n_pairs, 64, 1024), 64, 0, st>>>(g, level);
-    k_compact<<<1, 32, 0, st>>>(g);
 }
 void r360_launch_gn_step(cudaStream_t st, const R360GnArgs& g, int level) {
     k_gn_step<<<r360_blocks(g.n_pairs, 32, 1024), 32, 0, st>>>(g, level);
-    k_compact<<<1, 32, 0, st>>>(g);
 }
 void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols, int pair_id0) {
     k_finalize<<<r360_blocks(g.n_pairs, 128, 1024), 128, 0, st>>>(g, out, rows, cols, pair_id0);

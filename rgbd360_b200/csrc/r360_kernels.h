@@ -44,6 +44,7 @@ struct R360GnArgs {
     int* cnt;
     int* active_list;
     int* n_active;
+    int* ticket;                        // device: block-completion counter (the last block compacts the active list)
     r360_iter_record* trace;            // device or nullptr
 };
 
