@@ -97,9 +97,9 @@ class RegisterPhotoICP {
 
     // ---- alignFrames360, RPI.h:4519-4784
     void alignFrames360(const Pose& pose_guess = identity(), costFuncType method_ = PHOTO_CONSISTENCY, const int occlusion = 0) {
-        if (occlusion != 0) throw std::invalid_argument("RegisterPhotoICP: occlusion variants 1/2 (RPI.h:3232-4249) are not built");
+        if (occlusion < 0 || occlusion > 2) throw std::invalid_argument("RegisterPhotoICP: occlusion must be 0, 1 or 2 (RPI.h:4517)");
         if (!ctx_ || !have_[0] || !have_[1]) throw std::logic_error("RegisterPhotoICP: setSourceFrame and setTargetFrame first");
-        ensure_method(method_);
+        ensure_method(method_, occlusion);
         const int32_t s = 0, t = 1;
         check(r360_register_pairs(ctx_, 1, &s, &t, pose_guess.data(), &res_, nullptr));
         SSO = res_.sso;
@@ -108,14 +108,29 @@ class RegisterPhotoICP {
 
     /*! errorPhotoICP_sphere, RPI.h:2545-2739: sqrt(error2 / numValidPts). */
     double errorPhotoICP_sphere(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
-        ensure_method(method_);
+        ensure_method(method_, 0);
         double e2 = 0; int32_t n = 0;
         check(r360_eval_error(ctx_, 0, 1, pyramidLevel, poseGuess.data(), &e2, &n));
         return std::sqrt(e2 / n);
     }
+    /*! errorPhotoICP_sphereOcc1 / Occ2, RPI.h:3232-3369 / 3720-3858 (single-thread, source-order semantics):
+        sets avPhotoResidual / avDepthResidual and returns their sum. */
+    double errorPhotoICP_sphereOcc1(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
+        return error_occ(1, pyramidLevel, poseGuess, method_);
+    }
+    double errorPhotoICP_sphereOcc2(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
+        return error_occ(2, pyramidLevel, poseGuess, method_);
+    }
+    /*! calcHessGrad_sphereOcc1 / Occ2, RPI.h:3373-3716 / 3861-4249. */
+    void calcHessGrad_sphereOcc1(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
+        hessgrad_occ(1, pyramidLevel, poseGuess, method_);
+    }
+    void calcHessGrad_sphereOcc2(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
+        hessgrad_occ(2, pyramidLevel, poseGuess, method_);
+    }
     /*! calcHessGrad_sphere, RPI.h:2745-3228: fills hessian / gradient / SSO. */
     void calcHessGrad_sphere(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
-        ensure_method(method_);
+        ensure_method(method_, 0);
         int32_t nvis = 0;
         check(r360_eval_hessgrad(ctx_, 0, 1, pyramidLevel, poseGuess.data(), res_.hessian, res_.gradient, &nvis));
         SSO = (float)nvis / (float)((rows_ >> pyramidLevel) * (cols_ >> pyramidLevel));
@@ -153,6 +168,20 @@ class RegisterPhotoICP {
 #endif
 
   private:
+    double error_occ(int occ, int level, const Pose& pose, costFuncType m) {
+        ensure_method(m, occ);
+        double pr = 0, dr = 0, e = 0; int32_t np = 0, nd = 0;
+        check(r360_eval_error_occ(ctx_, 0, 1, level, pose.data(), &pr, &dr, &np, &nd, &e));
+        avPhotoResidual = std::sqrt(pr / (double)(occ == 1 ? np : nd));   // RPI.h:3360 / 3849
+        avDepthResidual = std::sqrt(dr / (double)nd);                      // RPI.h:3362 / 3851
+        return e;
+    }
+    void hessgrad_occ(int occ, int level, const Pose& pose, costFuncType m) {
+        ensure_method(m, occ);
+        int32_t nvis = 0;
+        check(r360_eval_hessgrad(ctx_, 0, 1, level, pose.data(), res_.hessian, res_.gradient, &nvis));
+        SSO = (float)nvis / (float)((rows_ >> level) * (cols_ >> level));
+    }
     r360_params p_;
     r360_ctx* ctx_ = nullptr;
     r360_result res_;
@@ -181,10 +210,11 @@ class RegisterPhotoICP {
             if (have_[s] && rgb_[s].size() == (size_t)rows * cols * 3) upload(s, s == 0 ? R360_ROLE_SOURCE : R360_ROLE_TARGET);
     }
     int method_or_default() const { return p_.method; }
-    void ensure_method(costFuncType m) {
+    void ensure_method(costFuncType m, int occlusion = 0) {
         method = m;
-        if (p_.method == (int)m && ctx_) return;
+        if (p_.method == (int)m && p_.occlusion == occlusion && ctx_) return;
         p_.method = (int)m;
+        p_.occlusion = occlusion;
         const int r = rows_, c = cols_;
         drop();
         ensure_ctx(r, c);

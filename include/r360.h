@@ -50,7 +50,9 @@ typedef struct r360_params {
     double  tol_residual;    /* 1e-3                 RPI.h:4594                         */
     double  tol_update;      /* 1e-4                 RPI.h:4595                         */
     int32_t method;          /* costFuncType; callers use R360_PHOTO_DEPTH              */
-    int32_t occlusion;       /* must be 0 (occlusion variants are out of scope)         */
+    int32_t occlusion;       /* alignFrames360's `occlusion` argument (RPI.h:4519): 0 regular,
+                                1 = *_sphereOcc1 (z-buffer), 2 = *_sphereOcc2 (0.3 m outlier gate +
+                                z-buffer), with the reference's single-thread (source-order) semantics */
     int32_t n_sensors_mask;  /* 8: zero the 2-px sensor-joint gradient columns
                                 (RPI.h:4537-4549) when the target pyramid is built; 0: no mask */
     int32_t reserved;
@@ -66,8 +68,10 @@ typedef struct r360_result {
     float   sso;             /* SSO = numVisiblePixels / imgSize   RPI.h:3226           */
     int32_t n_visible;       /* numVisiblePixels of that call                           */
     double  final_error;     /* `error` (RMS) at the accepted pose of the last level run */
-    double  final_err2;      /* its sum of squared weighted residuals                   */
-    int32_t final_n_valid;   /* its numValidPts                                         */
+    double  final_err2;      /* its sum of squared weighted residuals (occlusion 1/2:
+                                PhotoResidual + DepthResidual)                          */
+    int32_t final_n_valid;   /* its numValidPts (occlusion 1: nValidPhotoPts + nValidDepthPts,
+                                occlusion 2: nValidDepthPts)                            */
     int32_t status;          /* R360_PAIR_*                                             */
     int32_t iters[R360_MAX_LEVELS];   /* num_iterations[level] (accepted steps)         */
     int32_t passes[R360_MAX_LEVELS];  /* fused pixel passes executed per level          */
@@ -77,8 +81,9 @@ typedef struct r360_result {
 
 /* Optional per-iteration trace (parity hook): one record per evaluated pose. */
 typedef struct r360_iter_record {
-    double  err2;            /* sum of squared weighted residuals at `pose`            */
-    int32_t n_valid;
+    double  err2;            /* sum of squared weighted residuals at `pose`
+                                (occlusion 1/2: PhotoResidual)                          */
+    int32_t n_valid;         /* numValidPts (occlusion 1: nValidPhotoPts, 2: nValidDepthPts) */
     int32_t n_visible;
     int32_t level;
     int32_t it;              /* accepted steps so far when this pose was evaluated      */
@@ -88,6 +93,9 @@ typedef struct r360_iter_record {
     float   hessian[21];     /* upper triangle, row-major (h11,h12,..,h66)              */
     float   gradient[6];
     float   pad;
+    double  err2_depth;      /* occlusion 1/2: DepthResidual (RPI.h:3348, 3725), else 0 */
+    int32_t n_valid_depth;   /* occlusion 1/2: nValidDepthPts, else 0                   */
+    int32_t reserved;
 } r360_iter_record;
 
 typedef struct r360_ctx r360_ctx;
@@ -131,10 +139,19 @@ int r360_register_host_pairs(r360_ctx* ctx, int n_pairs, const uint8_t* rgb, con
                              const float* init_pose, r360_result* out);
 
 /* errorPhotoICP_sphere(level, pose, method) (RPI.h:2545-2739): returns the two sums the
- * RMS is formed from. */
+ * RMS is formed from.  Contexts created with occlusion 1/2 return PhotoResidual + DepthResidual
+ * and the sum of the counters; use r360_eval_error_occ for the separate terms. */
 int r360_eval_error(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
                     double* err2, int32_t* n_valid);
-/* calcHessGrad_sphere(level, pose, method) (RPI.h:2745-3228): H column-major 6x6. */
+/* errorPhotoICP_sphereOcc1 / errorPhotoICP_sphereOcc2(level, pose, method) (RPI.h:3232-3369,
+ * 3720-3858) of a context created with params.occlusion = 1 / 2: PhotoResidual, DepthResidual,
+ * nValidPhotoPts (0 for occlusion 2, which does not count it) and nValidDepthPts; `error` = the
+ * function's return value avPhotoResidual + avDepthResidual.  Any output pointer may be NULL. */
+int r360_eval_error_occ(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
+                        double* photo_residual, double* depth_residual, int32_t* n_valid_photo,
+                        int32_t* n_valid_depth, double* error);
+/* calcHessGrad_sphere(level, pose, method) (RPI.h:2745-3228): H column-major 6x6.  With
+ * params.occlusion = 1 / 2: calcHessGrad_sphereOcc1 / Occ2 (RPI.h:3373-3716, 3861-4249). */
 int r360_eval_hessgrad(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
                        float H[36], float g[6], int32_t* n_visible);
 

@@ -42,11 +42,11 @@ class IterRecord(C.Structure):
         ("err2", C.c_double), ("n_valid", C.c_int32), ("n_visible", C.c_int32),
         ("level", C.c_int32), ("it", C.c_int32), ("accepted", C.c_int32), ("used", C.c_int32),
         ("pose", C.c_float * 16), ("hessian", C.c_float * 21), ("gradient", C.c_float * 6),
-        ("pad", C.c_float),
+        ("pad", C.c_float), ("err2_depth", C.c_double), ("n_valid_depth", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
-def default_params(n_levels=4, method=PHOTO_DEPTH, std_photo=None, n_sensors_mask=8):
+def default_params(n_levels=4, method=PHOTO_DEPTH, std_photo=None, n_sensors_mask=8, occlusion=0):
     """Constructor defaults of RegisterPhotoICP (RPI.h:201-221) + alignFrames360 constants."""
     p = Params()
     p.n_levels = n_levels
@@ -60,7 +60,7 @@ def default_params(n_levels=4, method=PHOTO_DEPTH, std_photo=None, n_sensors_mas
     p.tol_residual = 1e-3
     p.tol_update = 1e-4
     p.method = method
-    p.occlusion = 0
+    p.occlusion = occlusion
     p.n_sensors_mask = n_sensors_mask
     return p
 
@@ -94,6 +94,8 @@ def lib():
         L.orc_lut.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), C.c_void_p]
         L.orc_error.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params),
                                 C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.orc_error_occ.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params),
+                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.orc_hessgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params),
                                    C.c_int] + [C.c_void_p] * 5
         L.orc_warp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params)] + [C.c_void_p] * 4
@@ -185,6 +187,14 @@ def error(src, trg, level, pose, params):
     T = pose_arg(pose)
     lib().orc_error(src.h, trg.h, level, _ptr(T), C.byref(params), C.byref(e2), C.byref(n))
     return e2.value, n.value
+
+
+def error_occ(src, trg, level, pose, params):
+    """errorPhotoICP_sphereOcc1 / Occ2 (params.occlusion) -> dict(photo, depth, n_photo, n_depth, error)."""
+    r2 = np.zeros(2, np.float64); cnt = np.zeros(2, np.int32); e = C.c_double()
+    T = pose_arg(pose)
+    lib().orc_error_occ(src.h, trg.h, level, _ptr(T), C.byref(params), _ptr(r2), _ptr(cnt), C.byref(e))
+    return dict(photo=float(r2[0]), depth=float(r2[1]), n_photo=int(cnt[0]), n_depth=int(cnt[1]), error=e.value)
 
 
 def hessgrad(src, trg, level, pose, params, accum=ACC_STABLE):

@@ -173,6 +173,30 @@ double ref_error(void* h, int level, const float* pose, int method, double* err2
     parse_trace(log, err2, nvalid, 1);
     return e;
 }
+// errorPhotoICP_sphereOcc1 / Occ2 (RPI.h:3232, 3720) at `level` (LUT caveat as ref_error): returns the
+// function's value avPhotoResidual + avDepthResidual; av[2] = the two public members it sets.
+// Order-dependent upstream (OpenMP over a shared z-buffer): call ref_set_threads(1) first.
+double ref_error_occ(void* h, int level, const float* pose, int method, int occlusion, double* av) {
+    RegisterPhotoICP* r = (RegisterPhotoICP*)h;
+    Capture c;
+    double e = occlusion == 1 ? r->errorPhotoICP_sphereOcc1(level, to_mat4(pose), (RegisterPhotoICP::costFuncType)method)
+                              : r->errorPhotoICP_sphereOcc2(level, to_mat4(pose), (RegisterPhotoICP::costFuncType)method);
+    if (av) { av[0] = r->avPhotoResidual; av[1] = r->avDepthResidual; }
+    return e;
+}
+// calcHessGrad_sphere / _sphereOcc1 / _sphereOcc2 by `occlusion` (RPI.h:2745, 3373, 3861)
+void ref_hessgrad_occ(void* h, int level, const float* pose, int method, int occlusion, float* H, float* g, float* sso) {
+    RegisterPhotoICP* r = (RegisterPhotoICP*)h;
+    Capture c;
+    if (occlusion == 1) r->calcHessGrad_sphereOcc1(level, to_mat4(pose), (RegisterPhotoICP::costFuncType)method);
+    else if (occlusion == 2) r->calcHessGrad_sphereOcc2(level, to_mat4(pose), (RegisterPhotoICP::costFuncType)method);
+    else r->calcHessGrad_sphere(level, to_mat4(pose), (RegisterPhotoICP::costFuncType)method);
+    Eigen::Matrix<float, 6, 6> Hm = r->getHessian();
+    Eigen::Matrix<float, 6, 1> gm = r->getGradient();
+    for (int i = 0; i < 36; ++i) H[i] = Hm.data()[i];
+    for (int i = 0; i < 6; ++i) g[i] = gm.data()[i];
+    *sso = r->SSO;
+}
 void ref_hessgrad(void* h, int level, const float* pose, int method, float* H, float* g, float* sso) {
     RegisterPhotoICP* r = (RegisterPhotoICP*)h;
     Capture c;

@@ -45,6 +45,9 @@ def lib(pinned=False):
         L.ref_error.restype = C.c_double
         L.ref_error.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ref_hessgrad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.ref_error_occ.restype = C.c_double
+        L.ref_error_occ.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_hessgrad_occ.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.ref_lut.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _libs[pinned] = L
     return _libs[pinned]
@@ -116,6 +119,17 @@ class Reference:
     def hessgrad(self, level, pose, method=2):
         H = np.zeros(36, np.float32); g = np.zeros(6, np.float32); sso = C.c_float()
         self.L.ref_hessgrad(self.h, level, _ptr(_pose_arg(pose)), method, _ptr(H), _ptr(g), C.byref(sso))
+        return H.reshape(6, 6).T.copy(), g, sso.value
+
+    def error_occ(self, level, pose, method=2, occlusion=1):
+        """errorPhotoICP_sphereOcc1/2 -> (return value, avPhotoResidual, avDepthResidual)."""
+        av = np.zeros(2, np.float64)
+        e = self.L.ref_error_occ(self.h, level, _ptr(_pose_arg(pose)), method, occlusion, _ptr(av))
+        return e, float(av[0]), float(av[1])
+
+    def hessgrad_occ(self, level, pose, method=2, occlusion=1):
+        H = np.zeros(36, np.float32); g = np.zeros(6, np.float32); sso = C.c_float()
+        self.L.ref_hessgrad_occ(self.h, level, _ptr(_pose_arg(pose)), method, occlusion, _ptr(H), _ptr(g), C.byref(sso))
         return H.reshape(6, 6).T.copy(), g, sso.value
 
     def lut(self):

@@ -318,7 +318,11 @@ void error_sphere(const Frame* src, const Frame* trg, int level, const float* T,
 // RPI.h:2991-3088.  Returns bit 0: photo row valid, bit 1: depth row valid.
 inline int jacobian_rows(const Warped& w, const LevelK& k, const r360_params* P, float Is,
                          float It, float Dt, float Ix, float Iy, float Dx, float Dy,
-                         float stdDevPhoto_inv, float* Jp, float* rp, float* Jd, float* rd) {
+                         float stdDevPhoto_inv, float* Jp, float* rp, float* Jd, float* rd,
+                         bool occ_store = false) {
+    // occ_store: calcHessGrad_sphereOcc1/Occ2 assign the rows in a block AFTER both terms
+    // (RPI.h:3573-3599, 4095-4121), so the depth saliency `continue` (RPI.h:3556-3557, 4078-4079)
+    // drops the photo row of that pixel as well.
     const int method = P->method;
     const float x = w.px, y = w.py, z = w.pz;
     // jacobianProj23
@@ -358,7 +362,7 @@ inline int jacobian_rows(const Warped& w, const LevelK& k, const r360_params* P,
     }
     if (method == R360_DEPTH_CONSISTENCY || method == R360_PHOTO_DEPTH) {
         if (std::isfinite(Dt)) {
-            if (fabsf(Dx) < P->thres_sal_depth && fabsf(Dy) < P->thres_sal_depth) return valid;
+            if (fabsf(Dx) < P->thres_sal_depth && fabsf(Dy) < P->thres_sal_depth) return occ_store ? 0 : valid;
             float depthDiff = Dt - w.dist;
             float sd = P->std_depth * Dt;
             float weight_depth = r360_huber(depthDiff, sd) / sd;
@@ -503,6 +507,170 @@ void hessgrad_sphere(const Frame* src, const Frame* trg, int level, const float*
     out->n_depth = nDepth;
 }
 
+
+// ------------------------------------------------------------------ f2: occlusion variants
+// errorPhotoICP_sphereOcc1 / Occ2 (RPI.h:3232-3369, 3720-3858) and calcHessGrad_sphereOcc1 / Occ2
+// (RPI.h:3373-3716, 3861-4249).  Upstream these loops carry `#pragma omp parallel for` over a
+// z-buffer that every iteration reads and writes, so their result depends on the thread schedule;
+// the semantics restated here (and implemented on the GPU) are those of ONE thread, i.e. source
+// pixels visited in index order -- what the compiled reference (oracle/_ref) computes with
+// omp_set_num_threads(1).  The loops below are therefore serial on purpose.
+//   Occ1 error : z-buffer per TARGET texel; a pixel passes iff its 1/|p| is >= every earlier
+//                candidate's of the same texel; squared residuals are stored per target texel (the
+//                last passer wins), the counters count every passer.
+//   Occ1 H/g   : the z-buffer is indexed with the SOURCE index (RPI.h:3473-3475), so it never
+//                rejects anything; rows are assigned after both terms (occ_store above).
+//   Occ2 error : |depth2 - dist| > thresDepthOutliers (0.3, RPI.h:4525) rejects first; then the
+//                Occ1 z-test; residuals per SOURCE pixel; both RMS use nValidDepthPts = #passers.
+//   Occ2 H/g   : outlier gate, no z-test; rows stored per TARGET texel (the last candidate in source
+//                order wins); numVisiblePixels counts distinct target texels.
+struct OccErr {
+    double photo, depth;      // PhotoResidual, DepthResidual
+    int n_photo, n_depth;     // nValidPhotoPts, nValidDepthPts
+};
+inline double occ_error_value(const OccErr& e, int occ) {
+    // RPI.h:3360-3367 (Occ1: each RMS over its own count) / 3849-3856 (Occ2: both over nValidDepthPts)
+    const double avP = sqrt(e.photo / (occ == 1 ? e.n_photo : e.n_depth));
+    const double avD = sqrt(e.depth / e.n_depth);
+    return avP + avD;
+}
+
+template <class M>
+void error_sphere_occ(const Frame* src, const Frame* trg, int level, const float* T, const r360_params* P,
+                      const std::vector<float>& lut, int occ, OccErr* out) {
+    const LevelK k = level_consts(src, level);
+    const int N = k.rows * k.cols;
+    const double stdDevPhoto_inv = 1. / P->std_photo;          // RPI.h:3256 (double)
+    const float* Is = src->gray[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Dt = trg->depth[level].data();
+    const float* Ix = trg->ggx[level].data();
+    const float* Iy = trg->ggy[level].data();
+    const float* Dx = trg->dgx[level].data();
+    const float* Dy = trg->dgy[level].data();
+    const int method = P->method;
+    const float thresDepthOutliers = (float)0.3;               // RPI.h:4525
+    std::vector<float> resP(N, 0.f), resD(N, 0.f), zbuf(N, 0.f);
+    int nP = 0, nD = 0;
+    for (int i = 0; i < N; ++i) {
+        if (lut[3 * (size_t)i] == ORC_INVALID_POINT) continue;
+        Warped w;
+        if (!warp_point<M>(T, &lut[3 * (size_t)i], k, w)) continue;
+        const size_t j = (size_t)w.r * k.cols + w.c;
+        float depth2 = Dt[j];
+        float depthDiff = depth2 - w.dist;
+        if (occ == 2 && fabsf(depthDiff) > thresDepthOutliers) continue;       // RPI.h:3788-3791
+        if (zbuf[j] > 0 && w.dinv < zbuf[j]) continue;                          // RPI.h:3299 / 3794
+        zbuf[j] = w.dinv;
+        if (occ == 2) ++nD;                                                     // RPI.h:3798
+        const size_t slot = occ == 1 ? j : (size_t)i;                           // RPI.h:3318 (ii) / 3814 (i)
+        if (method == R360_PHOTO_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            if (fabsf(Ix[j]) < P->thres_sal_int && fabsf(Iy[j]) < P->thres_sal_int) continue;
+            float photoDiff = It[j] - Is[i];
+            double weight_photo = r360_huber(photoDiff, P->std_photo) * stdDevPhoto_inv;
+            float werr = (float)(weight_photo * photoDiff);
+            resP[slot] = werr * werr;
+            if (occ == 1) ++nP;
+        }
+        if (method == R360_DEPTH_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            if (std::isfinite(depth2)) {
+                if (fabsf(Dx[j]) < P->thres_sal_depth && fabsf(Dy[j]) < P->thres_sal_depth) continue;
+                float sd = P->std_depth * depth2;
+                double weight_depth = r360_huber(depthDiff, sd) / sd;
+                float werr = (float)(weight_depth * depthDiff);
+                resD[slot] = werr * werr;
+                if (occ == 1) ++nD;
+            }
+        }
+    }
+    double PhotoResidual = 0.0, DepthResidual = 0.0;
+    for (int i = 0; i < N; ++i) { PhotoResidual += resP[i]; DepthResidual += resD[i]; }
+    out->photo = PhotoResidual; out->depth = DepthResidual; out->n_photo = nP; out->n_depth = nD;
+}
+
+template <class M>
+void hessgrad_sphere_occ(const Frame* src, const Frame* trg, int level, const float* T, const r360_params* P,
+                         const std::vector<float>& lut, int accum_mode, int occ, HessOut* out) {
+    const LevelK k = level_consts(src, level);
+    const int N = k.rows * k.cols;
+    const float stdDevPhoto_inv = (float)(1. / P->std_photo);      // RPI.h:3402 (float)
+    const float thresDepthOutliers = (float)0.3;
+    const float* Is = src->gray[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Dt = trg->depth[level].data();
+    const float* Ix = trg->ggx[level].data();
+    const float* Iy = trg->ggy[level].data();
+    const float* Dx = trg->dgx[level].data();
+    const float* Dy = trg->dgy[level].data();
+    std::vector<float> JP(6 * (size_t)N), JD(6 * (size_t)N), RP(N, 0.f), RD(N, 0.f), zbuf(N, 0.f);
+    std::vector<int> VP(N, 0), VD(N, 0);
+    int numVisible = 0;
+    for (int i = 0; i < N; ++i) {
+        if (lut[3 * (size_t)i] == ORC_INVALID_POINT) continue;
+        Warped w;
+        if (!warp_point<M>(T, &lut[3 * (size_t)i], k, w)) continue;
+        const size_t j = (size_t)w.r * k.cols + w.c;
+        size_t slot;
+        if (occ == 1) {
+            // invDepthBuffer(i): first and only visit of source index i, never occluded (RPI.h:3473-3475)
+            ++numVisible;
+            slot = (size_t)i;
+        } else {
+            if (fabsf(Dt[j] - w.dist) > thresDepthOutliers) continue;           // RPI.h:3968-3981
+            if (zbuf[j] == 0) ++numVisible;                                     // RPI.h:3984-3985
+            zbuf[j] = w.dinv;
+            slot = j;
+        }
+        float Jp[6], Jd[6], rp = 0.f, rd = 0.f;
+        const int v = jacobian_rows(w, k, P, Is[i], It[j], Dt[j], Ix[j], Iy[j], Dx[j], Dy[j], stdDevPhoto_inv,
+                                    Jp, &rp, Jd, &rd, true);
+        if (v & 1) { for (int q = 0; q < 6; ++q) JP[(size_t)q * N + slot] = Jp[q]; RP[slot] = rp; VP[slot] = 1; }
+        if (v & 2) { for (int q = 0; q < 6; ++q) JD[(size_t)q * N + slot] = Jd[q]; RD[slot] = rd; VD[slot] = 1; }
+    }
+    double acc[27];
+    int nPhoto = 0, nDepth = 0;
+    float hf[27];
+    double hd[27];
+    for (int q = 0; q < 27; ++q) { hf[q] = 0.f; hd[q] = 0.0; }
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<float>& J = pass == 0 ? JP : JD;
+        const std::vector<float>& R = pass == 0 ? RP : RD;
+        const std::vector<int>& V = pass == 0 ? VP : VD;
+        const bool on = pass == 0 ? (P->method != R360_DEPTH_CONSISTENCY) : (P->method != R360_PHOTO_CONSISTENCY);
+        if (!on) continue;
+        // an OpenMP `reduction(+: h11, ...)` sums into zero-initialised private copies and adds them to
+        // the shared variables at the end of the loop -- also with one thread (RPI.h:3611, 3649)
+        float pf[27];
+        for (int q = 0; q < 27; ++q) pf[q] = 0.f;
+        for (int i = 0; i < N; ++i)
+            if (V[i]) {
+                float jj[6];
+                for (int q = 0; q < 6; ++q) jj[q] = J[(size_t)q * N + i];
+                const float r = R[i];
+                int q = 0;
+                for (int a = 0; a < 6; ++a)
+                    for (int b = a; b < 6; ++b, ++q) {
+                        const float pr = jj[a] * jj[b];
+                        pf[q] += pr; hd[q] += pr;
+                    }
+                for (int a = 0; a < 6; ++a) { const float pr = jj[a] * r; pf[21 + a] += pr; hd[21 + a] += pr; }
+                if (pass == 0) ++nPhoto; else ++nDepth;
+            }
+        for (int q = 0; q < 27; ++q) hf[q] += pf[q];
+    }
+    for (int q = 0; q < 27; ++q) acc[q] = accum_mode == 0 ? (double)hf[q] : hd[q];
+    int q = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++q) {
+            out->Hd[q] = acc[q];
+            out->H[a + 6 * b] = out->H[b + 6 * a] = (float)acc[q];
+        }
+    for (int a = 0; a < 6; ++a) { out->gd[a] = acc[21 + a]; out->g[a] = (float)acc[21 + a]; }
+    out->n_visible = numVisible;
+    out->n_photo = nPhoto;
+    out->n_depth = nDepth;
+}
+
 // ------------------------------------------------------------------ a10 alignFrames360
 template <class M>
 int align360(const Frame* src, const Frame* trg, const float* guess, const r360_params* P,
@@ -531,14 +699,32 @@ int align360(const Frame* src, const Frame* trg, const float* guess, const r360_
         const double step = 5;
         int it = 0;
         float upd[6] = { 1, 1, 1, 1, 1, 1 };                               // RPI.h:4596
-        error_sphere<M>(src, trg, level, pose_estim, P, lut, &err2, &nvalid);   // RPI.h:4599
-        error = sqrt(err2 / nvalid);
+        const int occ = P->occlusion;
+        // errorPhotoICP_sphere / _sphereOcc1 / _sphereOcc2 (RPI.h:4598-4603, 4704-4709)
+        auto eval_error = [&](const float* pose, double* e2, int* nv, OccErr* oe) -> double {
+            if (occ == 0) {
+                error_sphere<M>(src, trg, level, pose, P, lut, e2, nv);
+                oe->photo = *e2; oe->depth = 0.0; oe->n_photo = *nv; oe->n_depth = 0;
+                return sqrt(*e2 / *nv);
+            }
+            error_sphere_occ<M>(src, trg, level, pose, P, lut, occ, oe);
+            *e2 = oe->photo + oe->depth;
+            *nv = occ == 1 ? oe->n_photo + oe->n_depth : oe->n_depth;
+            return occ_error_value(*oe, occ);
+        };
+        auto fill_err = [&](r360_iter_record* r, const OccErr& oe, double e2, int nv) {
+            if (occ == 0) { r->err2 = e2; r->n_valid = nv; return; }
+            r->err2 = oe.photo; r->err2_depth = oe.depth;
+            r->n_valid = occ == 1 ? oe.n_photo : oe.n_depth; r->n_valid_depth = oe.n_depth;
+        };
+        OccErr oe;
+        error = eval_error(pose_estim, &err2, &nvalid, &oe);               // RPI.h:4599
         out->passes[level] = 1;
         int ev = 0;
         r360_iter_record* cur = rec_at(level, ev++);
         if (cur) {
             memset(cur, 0, sizeof(*cur));
-            cur->err2 = err2; cur->n_valid = nvalid; cur->level = level; cur->it = 0;
+            fill_err(cur, oe, err2, nvalid); cur->level = level; cur->it = 0;
             cur->accepted = 1; cur->used = 1; memcpy(cur->pose, pose_estim, 64);
         }
         double diff_error = error;                                         // RPI.h:4605
@@ -549,7 +735,8 @@ int align360(const Frame* src, const Frame* trg, const float* guess, const r360_
             return sqrtf(a + b);
         };
         while (it < P->max_iters && norm6(upd) > P->tol_update && diff_error > P->tol_residual) {
-            hessgrad_sphere<M>(src, trg, level, pose_estim, P, lut, accum_mode, &ho);   // RPI.h:4623
+            if (occ == 0) hessgrad_sphere<M>(src, trg, level, pose_estim, P, lut, accum_mode, &ho);   // RPI.h:4623
+            else hessgrad_sphere_occ<M>(src, trg, level, pose_estim, P, lut, accum_mode, occ, &ho);    // RPI.h:4625-4627
             have_hess = true;
             ++out->passes[level];
             if (cur) {
@@ -588,14 +775,14 @@ int align360(const Frame* src, const Frame* trg, const float* guess, const r360_
                 r360_mat4_mul(Tf, pose_estim, pose_tmp);                    // RPI.h:4697
             }
             double new_err2; int new_nvalid;
-            error_sphere<M>(src, trg, level, pose_tmp, P, lut, &new_err2, &new_nvalid);   // RPI.h:4705
+            OccErr noe;
+            double new_error = eval_error(pose_tmp, &new_err2, &new_nvalid, &noe);   // RPI.h:4705
             ++out->passes[level];
-            double new_error = sqrt(new_err2 / new_nvalid);
             diff_error = error - new_error;                                // RPI.h:4711
             r360_iter_record* nr = rec_at(level, ev++);
             if (nr) {
                 memset(nr, 0, sizeof(*nr));
-                nr->err2 = new_err2; nr->n_valid = new_nvalid; nr->level = level; nr->it = it;
+                fill_err(nr, noe, new_err2, new_nvalid); nr->level = level; nr->it = it;
                 nr->used = 1; memcpy(nr->pose, pose_tmp, 64);
             }
             if (diff_error > P->tol_residual) {                            // RPI.h:4715-4722
@@ -732,18 +919,40 @@ int orc_error(void* srcv, void* trgv, int level, const float* pose, const r360_p
     return 0;
 }
 
+// errorPhotoICP_sphereOcc1 / Occ2 (P->occlusion = 1 / 2): out4 = {PhotoResidual, DepthResidual},
+// counts = {nValidPhotoPts, nValidDepthPts}; returns through *error the function's return value.
+int orc_error_occ(void* srcv, void* trgv, int level, const float* pose, const r360_params* P,
+                  double* res2, int* counts, double* error) {
+    std::vector<float> lut;
+    OccErr oe;
+    if (g_math_mode) {
+        build_lut<MathLibm>((Frame*)srcv, level, P, lut);
+        error_sphere_occ<MathLibm>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, P->occlusion, &oe);
+    } else {
+        build_lut<MathPinned>((Frame*)srcv, level, P, lut);
+        error_sphere_occ<MathPinned>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, P->occlusion, &oe);
+    }
+    if (res2) { res2[0] = oe.photo; res2[1] = oe.depth; }
+    if (counts) { counts[0] = oe.n_photo; counts[1] = oe.n_depth; }
+    if (error) *error = occ_error_value(oe, P->occlusion);
+    return 0;
+}
+
 // H: 36 floats column-major, g: 6 floats, Hd/gd: optional double sums (21 upper-tri + 6),
 // counts: optional {n_visible, n_photo_rows, n_depth_rows}.
 int orc_hessgrad(void* srcv, void* trgv, int level, const float* pose, const r360_params* P,
                  int accum_mode, float* H, float* g, double* Hd, double* gd, int* counts) {
     std::vector<float> lut;
     HessOut ho;
+    const int occ = P->occlusion;
     if (g_math_mode) {
         build_lut<MathLibm>((Frame*)srcv, level, P, lut);
-        hessgrad_sphere<MathLibm>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, &ho);
+        if (occ) hessgrad_sphere_occ<MathLibm>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, occ, &ho);
+        else hessgrad_sphere<MathLibm>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, &ho);
     } else {
         build_lut<MathPinned>((Frame*)srcv, level, P, lut);
-        hessgrad_sphere<MathPinned>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, &ho);
+        if (occ) hessgrad_sphere_occ<MathPinned>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, occ, &ho);
+        else hessgrad_sphere<MathPinned>((Frame*)srcv, (Frame*)trgv, level, pose, P, lut, accum_mode, &ho);
     }
     if (H) memcpy(H, ho.H, sizeof(ho.H));
     if (g) memcpy(g, ho.g, sizeof(ho.g));

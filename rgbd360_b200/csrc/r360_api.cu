@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdarg>
+#include <cmath>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -22,6 +23,7 @@ std::string g_create_error;
 constexpr int kChunkFrames = R360_CHUNK_FRAMES;     // max frames per pyramid-build launch / H2D staging buffer
 constexpr int kStages = 4;           // staging buffers: the copy stream runs up to kStages - 1 chunks ahead
 constexpr int kStreamPairs = 64;     // pairs per registration batch of r360_register_host_pairs
+constexpr int kOccPairs = 64;        // pairs per batch of the occlusion variants (bounds their scratch: 12 B per pixel and pair)
 
 struct Ctx {
     int device = 0, sm_count = 0, pass_grid = 0;
@@ -57,6 +59,8 @@ struct Ctx {
     r360_result* d_res = nullptr; r360_result* h_res = nullptr;
     r360_iter_record* d_trace = nullptr; size_t trace_cap = 0;
     float* d_cams = nullptr; float* h_cams = nullptr;
+    int* occ_head = nullptr; int* occ_next = nullptr; float* occ_dinv = nullptr;   // occlusion 1/2: per-texel candidate lists
+    int occ_cap = 0;                                                                // pairs the scratch holds
     uint8_t* d_sens_rgb = nullptr; uint16_t* d_sens_depth = nullptr; size_t sens_cap = 0;   // ingest: sensor images of one chunk
     // stats
     float last_ms = 0.f, pass_ms = 0.f;
@@ -114,7 +118,7 @@ R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint, int first = 0) {
     a.pairs = c->d_pairs + first;
     a.src_base = c->d_srcb + first;
     a.trg_base = c->d_trgb + first;
-    a.acc = c->d_acc + (size_t)first * R360_ACC_DOUBLES;
+    a.acc = c->d_acc + (size_t)first * R360_ACC_STRIDE;
     a.cnt = c->d_cnt + (size_t)first * R360_ACC_INTS;
     return a;
 }
@@ -124,7 +128,7 @@ R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) 
     g.params = c->P;
     g.n_pairs = n_pairs;
     g.pairs = c->d_pairs + first;
-    g.acc = c->d_acc + (size_t)first * R360_ACC_DOUBLES;
+    g.acc = c->d_acc + (size_t)first * R360_ACC_STRIDE;
     g.cnt = c->d_cnt + (size_t)first * R360_ACC_INTS;
     g.active_list = c->d_active + first;
     g.n_active = c->d_nactive;
@@ -254,7 +258,7 @@ int eval_setup(Ctx* c, int src, int trg, int level, const float pose[16], R360Pa
     const int one = 1;
     CK(c, cudaMemcpyAsync(c->d_active + slot, &slot, sizeof(int), cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(c->d_nactive + 1, &one, sizeof(int), cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemsetAsync(c->d_acc + (size_t)slot * R360_ACC_DOUBLES, 0, sizeof(double) * R360_ACC_DOUBLES, c->st));
+    CK(c, cudaMemsetAsync(c->d_acc + (size_t)slot * R360_ACC_STRIDE, 0, sizeof(double) * R360_ACC_STRIDE, c->st));
     CK(c, cudaMemsetAsync(c->d_cnt + (size_t)slot * R360_ACC_INTS, 0, sizeof(int) * R360_ACC_INTS, c->st));
     CK(c, cudaStreamSynchronize(c->st));    // hp / sb / tb are stack variables
     *a = pass_args(c, level, 1);
@@ -263,15 +267,26 @@ int eval_setup(Ctx* c, int src, int trg, int level, const float pose[16], R360Pa
     return R360_OK;
 }
 
-int eval_pass(Ctx* c, int src, int trg, int level, const float pose[16], double acc[R360_ACC_DOUBLES], int cnt[R360_ACC_INTS]) {
+// One evaluation of the active pairs of `a` at their pose_eval: the fused pass (occlusion 0) or the
+// scatter + evaluate pair of the occlusion variants.
+void launch_evaluation(Ctx* c, const R360PassArgs& a, int n_pairs) {
+    if (c->P.occlusion == 0) {
+        r360_launch_pass(c->st, a, c->pass_grid);
+        ++c->launches;
+    } else {
+        r360_launch_occ_pass(c->st, a, n_pairs, c->occ_head, c->occ_next, c->occ_dinv, c->sm_count);
+        c->launches += 2;
+    }
+}
+
+int eval_pass(Ctx* c, int src, int trg, int level, const float pose[16], double acc[R360_ACC_STRIDE], int cnt[R360_ACC_INTS]) {
     R360PassArgs a;
     int rc = eval_setup(c, src, trg, level, pose, &a);
     if (rc) return rc;
-    r360_launch_pass(c->st, a, c->pass_grid);
-    ++c->launches;
+    launch_evaluation(c, a, 1);
     CK(c, cudaGetLastError());
     const int slot = c->max_pairs;
-    CK(c, cudaMemcpyAsync(acc, c->d_acc + (size_t)slot * R360_ACC_DOUBLES, sizeof(double) * R360_ACC_DOUBLES, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(acc, c->d_acc + (size_t)slot * R360_ACC_STRIDE, sizeof(double) * R360_ACC_STRIDE, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaMemcpyAsync(cnt, c->d_cnt + (size_t)slot * R360_ACC_INTS, sizeof(int) * R360_ACC_INTS, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaStreamSynchronize(c->st));
     return R360_OK;
@@ -323,6 +338,7 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_res); cudaFreeHost(c->h_res); cudaFree(c->d_trace);
     cudaFree(c->d_cams); cudaFreeHost(c->h_cams);
     cudaFree(c->d_sens_rgb); cudaFree(c->d_sens_depth);
+    cudaFree(c->occ_head); cudaFree(c->occ_next); cudaFree(c->occ_dinv);
     for (auto e : c->ev_pass) cudaEventDestroy(e);
     for (int b = 0; b < kStages; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -411,7 +427,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
 
     const int np = max_pairs + 1;     // + 1 spare slot for the eval hooks
     CK(c, cudaMalloc(&c->d_pairs, sizeof(R360Pair) * np));
-    CK(c, cudaMalloc(&c->d_acc, sizeof(double) * R360_ACC_DOUBLES * np));
+    CK(c, cudaMalloc(&c->d_acc, sizeof(double) * R360_ACC_STRIDE * np));
     CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * R360_ACC_INTS * np));
     CK(c, cudaMalloc(&c->d_active, sizeof(int) * np));
     CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 4));      // [0] batch, [1] eval hooks, [2] completion ticket
@@ -421,6 +437,13 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaMallocHost(&c->h_idx, sizeof(int32_t) * 2 * np)); CK(c, cudaMalloc(&c->d_idx, sizeof(int32_t) * 2 * np));
     CK(c, cudaMallocHost(&c->h_pose, sizeof(float) * 16 * np)); CK(c, cudaMalloc(&c->d_pose, sizeof(float) * 16 * np));
     CK(c, cudaMalloc(&c->d_res, sizeof(r360_result) * np)); CK(c, cudaMallocHost(&c->h_res, sizeof(r360_result) * np));
+    if (params->occlusion != 0) {
+        c->occ_cap = std::min(max_pairs, kOccPairs);
+        const size_t n = (size_t)c->occ_cap * npx;
+        CK(c, cudaMalloc(&c->occ_head, sizeof(int) * n));
+        CK(c, cudaMalloc(&c->occ_next, sizeof(int) * n));
+        CK(c, cudaMalloc(&c->occ_dinv, sizeof(float) * n));
+    }
     CK(c, cudaMalloc(&c->d_cams, sizeof(float) * 12 * kChunkFrames)); CK(c, cudaMallocHost(&c->h_cams, sizeof(float) * 12 * kChunkFrames));
     return R360_OK;
 }
@@ -437,8 +460,8 @@ int r360_create(r360_ctx** out, int device, int rows, int cols, int max_frames, 
     if ((rows % (1 << (params->n_levels - 1))) || (cols % (1 << params->n_levels)))
         return fail(nullptr, R360_E_ARG, "r360_create: %dx%d: rows must be divisible by 2^(n_levels-1) and cols by 2^n_levels "
                                          "(every level keeps an even width)", cols, rows);
-    if (params->occlusion != 0)
-        return fail(nullptr, R360_E_ARG, "r360_create: occlusion variants 1/2 (RPI.h:3232-4249) are not built; use 0");
+    if (params->occlusion < 0 || params->occlusion > 2)
+        return fail(nullptr, R360_E_ARG, "r360_create: occlusion %d not in {0, 1, 2} (RPI.h:4517)", params->occlusion);
     if (params->method < 0 || params->method > 2) return fail(nullptr, R360_E_ARG, "r360_create: bad method %d", params->method);
     if (params->max_iters < 1 || params->max_iters > 64) return fail(nullptr, R360_E_ARG, "r360_create: max_iters %d not in [1,64]", params->max_iters);
     if ((long long)rows * cols >= (1LL << 27)) return fail(nullptr, R360_E_ARG, "r360_create: image too large");
@@ -481,10 +504,10 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
         R360PassArgs a = pass_args(c, level, n, first);
         for (int k = 0; k <= c->P.max_iters; ++k) {                   // 1 initial + <= max_iters loop bodies
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
-            r360_launch_pass(c->st, a, c->pass_grid);
+            launch_evaluation(c, a, n);
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
             r360_launch_gn_step(c->st, g, level);
-            c->launches += 2;
+            ++c->launches;
         }
     }
     r360_launch_finalize(c->st, g, c->d_res + first, c->rows, c->cols, first);
@@ -520,8 +543,17 @@ int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const 
     if (init_pose) memcpy(c->h_pose, init_pose, sizeof(float) * 16 * n_pairs);
     if (trace) CK(c, cudaMemsetAsync(c->d_trace, 0, sizeof(r360_iter_record) * n_rec, c->st));
     int n_ev = 0;
-    int rc = enqueue_register(c, 0, n_pairs, n_pairs, init_pose != nullptr, trace ? c->d_trace : nullptr, true, &n_ev);
-    if (rc) return rc;
+    if (c->P.occlusion == 0) {
+        int rc = enqueue_register(c, 0, n_pairs, n_pairs, init_pose != nullptr, trace ? c->d_trace : nullptr, true, &n_ev);
+        if (rc) return rc;
+    } else {
+        // the occlusion variants keep per-texel candidate lists for every pair of a batch: bounded batches
+        for (int first = 0; first < n_pairs; first += c->occ_cap) {
+            int rc = enqueue_register(c, first, std::min(c->occ_cap, n_pairs - first), n_pairs, init_pose != nullptr,
+                                      trace ? c->d_trace : nullptr, false, &n_ev);
+            if (rc) return rc;
+        }
+    }
     CK(c, cudaMemcpyAsync(c->h_res, c->d_res, sizeof(r360_result) * n_pairs, cudaMemcpyDeviceToHost, c->st));
     if (trace) CK(c, cudaMemcpyAsync(trace, c->d_trace, sizeof(r360_iter_record) * n_rec, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaEventRecord(c->ev_t1, c->st));
@@ -589,17 +621,41 @@ int r360_register_host_pairs(r360_ctx* c, int n_pairs, const uint8_t* rgb, const
 
 int r360_eval_error(r360_ctx* c, int src, int trg, int level, const float pose[16], double* err2, int32_t* n_valid) {
     if (!c) return R360_E_ARG;
-    double acc[R360_ACC_DOUBLES]; int cnt[R360_ACC_INTS];
+    double acc[R360_ACC_STRIDE]; int cnt[R360_ACC_INTS];
     int rc = eval_pass(c, src, trg, level, pose, acc, cnt);
     if (rc) return rc;
-    if (err2) *err2 = acc[27];
-    if (n_valid) *n_valid = cnt[1] + cnt[2];
+    if (c->P.occlusion == 0) {
+        if (err2) *err2 = acc[27];
+        if (n_valid) *n_valid = cnt[1] + cnt[2];
+    } else {
+        if (err2) *err2 = acc[27] + acc[28];
+        if (n_valid) *n_valid = c->P.occlusion == 1 ? cnt[1] + cnt[2] : cnt[2];
+    }
+    return R360_OK;
+}
+
+int r360_eval_error_occ(r360_ctx* c, int src, int trg, int level, const float pose[16], double* photo_residual,
+                        double* depth_residual, int32_t* n_valid_photo, int32_t* n_valid_depth, double* error) {
+    if (!c) return R360_E_ARG;
+    if (c->P.occlusion == 0) return fail(c, R360_E_STATE, "eval_error_occ: the context was created with occlusion = 0");
+    double acc[R360_ACC_STRIDE]; int cnt[R360_ACC_INTS];
+    int rc = eval_pass(c, src, trg, level, pose, acc, cnt);
+    if (rc) return rc;
+    if (photo_residual) *photo_residual = acc[27];
+    if (depth_residual) *depth_residual = acc[28];
+    if (n_valid_photo) *n_valid_photo = cnt[1];
+    if (n_valid_depth) *n_valid_depth = cnt[2];
+    if (error) {
+        // RPI.h:3360-3367 (Occ1: each RMS over its own counter) / 3849-3856 (Occ2: both over nValidDepthPts)
+        const double n_p = (double)(c->P.occlusion == 1 ? cnt[1] : cnt[2]), n_d = (double)cnt[2];
+        *error = std::sqrt(acc[27] / n_p) + std::sqrt(acc[28] / n_d);
+    }
     return R360_OK;
 }
 
 int r360_eval_hessgrad(r360_ctx* c, int src, int trg, int level, const float pose[16], float H[36], float g[6], int32_t* n_visible) {
     if (!c) return R360_E_ARG;
-    double acc[R360_ACC_DOUBLES]; int cnt[R360_ACC_INTS];
+    double acc[R360_ACC_STRIDE]; int cnt[R360_ACC_INTS];
     int rc = eval_pass(c, src, trg, level, pose, acc, cnt);
     if (rc) return rc;
     if (H) {

@@ -200,53 +200,6 @@ k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long lo
 }
 
 // =========================================================================== K3: fused pixel pass
-// Source pixel addressing shared by the pass, dump and statistics kernels: thread-local pixel
-// pair (i, i+1) of a level, its (row, col) and the back-projected points of both pixels.
-struct R360SrcPair {
-    float2 X0, X1, X2;       // back-projected points, packed {pixel 0, pixel 1}
-    float2 Is;               // source gray
-    bool v0, v1;             // LUT point valid (RPI.h:4575: minDepth < d < maxDepth) and inside the range
-};
-
-__device__ __forceinline__ void r360_load_src_pair(const R360Level& lv, const r360_params& P, float4 s, int r, int c,
-                                                   bool in0, bool in1, R360SrcPair& o) {
-    // cols is even at every level (r360_create) and c is even: pixel 1 = (r, c + 1)
-    o.v0 = in0 & (P.min_depth < s.x) & (s.x < P.max_depth);
-    o.v1 = in1 & (P.min_depth < s.z) & (s.z < P.max_depth);
-    // invalid pixels carry a finite dummy point (weight 0 later): keeps every packed lane finite
-    const float2 d = make_float2(o.v0 ? s.x : 1.f, o.v1 ? s.z : 1.f);
-    o.Is = make_float2(s.y, s.w);
-    const float2 tp = __ldg(&lv.tab_p[min((unsigned)r, (unsigned)(lv.rows - 1))]);   // tail lanes: r may be == rows
-    const float4 tt = __ldg(&lv.tab_t[(unsigned)c >> 1]);
-    o.X0 = f2mul(d, R360_F2(tp.x));                                     // d sin(phi)
-    const float2 m = f2mul(d, R360_F2(tp.y));                           // -d cos(phi)
-    o.X1 = f2mul(m, make_float2(tt.x, tt.y));
-    o.X2 = f2mul(m, make_float2(tt.z, tt.w));
-}
-
-// Bit-exact (r', c') of a pixel pair: packed pinned sequence + scalar recomputation of the rare
-// pixels it flags (out-of-range operands, exact .5 ties).  Must be called by all 32 lanes of the
-// warp (warp vote).  T: registers; Ts: same pose in shared or global memory for the out-of-line path.
-__device__ __forceinline__ void r360_index_pair(const float* __restrict__ T, const float* Ts, const R360Level& lv,
-                                                const R360SrcPair& sp, float one, R360Geo2& g, int r[2], int c[2],
-                                                unsigned& n_fallback) {
-    bool bad[2];
-    r360_index_pair_packed(T, sp.X0, sp.X1, sp.X2, lv.res_inv, lv.half_rows, one, g, r, c, bad);
-    const bool need0 = bad[0] & sp.v0, need1 = bad[1] & sp.v1;
-    if (__any_sync(0xffffffffu, need0 | need1)) {
-        if (need0) {
-            const int2 rc = r360_index_exact(Ts, sp.X0.x, sp.X1.x, sp.X2.x, lv.res_inv, lv.half_rows);
-            r[0] = rc.x; c[0] = rc.y;
-            ++n_fallback;
-        }
-        if (need1) {
-            const int2 rc = r360_index_exact(Ts, sp.X0.y, sp.X1.y, sp.X2.y, lv.res_inv, lv.half_rows);
-            r[1] = rc.x; c[1] = rc.y;
-            ++n_fallback;
-        }
-    }
-}
-
 // Work decomposition: the (active pair, pixel block) space is cut into `items` of px_per_item
 // pixels; every CTA of the persistent grid takes one CONTIGUOUS run of items, so it touches one
 // or two pairs, keeps its 28 packed partial sums in registers across the whole run and flushes
@@ -449,7 +402,7 @@ k_pass(R360PassArgs a) {
             double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < R360_PASS_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
-            atomicAdd(&a.acc[(size_t)pair * R360_ACC_DOUBLES + threadIdx.x], sum);
+            atomicAdd(&a.acc[(size_t)pair * R360_ACC_STRIDE + threadIdx.x], sum);
         } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
             int sum = 0;
 #pragma unroll
@@ -560,7 +513,7 @@ k_index_stats(R360PassArgs a, int pair, unsigned long long* __restrict__ out) {
 
 // =========================================================================== K4: Gauss-Newton state machine
 __device__ void r360_zero_acc(double* acc, int* cnt, int pair) {
-    for (int k = 0; k < R360_ACC_DOUBLES; ++k) acc[(size_t)pair * R360_ACC_DOUBLES + k] = 0.0;
+    for (int k = 0; k < R360_ACC_STRIDE; ++k) acc[(size_t)pair * R360_ACC_STRIDE + k] = 0.0;
     for (int k = 0; k < R360_ACC_INTS; ++k) cnt[(size_t)pair * R360_ACC_INTS + k] = 0;
 }
 
@@ -622,12 +575,24 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
         R360Pair* ps = g.pairs + p;
         if (!ps->active) continue;
-        const double* acc = g.acc + (size_t)p * R360_ACC_DOUBLES;
+        const double* acc = g.acc + (size_t)p * R360_ACC_STRIDE;
         const int* cnt = g.cnt + (size_t)p * R360_ACC_INTS;
-        const double e2 = acc[27];
-        const int n_valid = cnt[1] + cnt[2];
         const int n_vis = cnt[0];
-        const double err = sqrt(e2 / (double)n_valid);      // RPI.h:2738
+        double e2, err;
+        int n_valid;
+        if (P.occlusion == 0) {
+            e2 = acc[27];
+            n_valid = cnt[1] + cnt[2];
+            err = sqrt(e2 / (double)n_valid);               // RPI.h:2738
+        } else {
+            // errorPhotoICP_sphereOcc1: sqrt(Photo / nValidPhotoPts) + sqrt(Depth / nValidDepthPts)  RPI.h:3360-3367
+            // errorPhotoICP_sphereOcc2: both over nValidDepthPts                                      RPI.h:3849-3856
+            // (a missing term gives 0/0 = NaN upstream as well: the loop then never runs)
+            const double n_p = (double)(P.occlusion == 1 ? cnt[1] : cnt[2]), n_d = (double)cnt[2];
+            err = sqrt(acc[27] / n_p) + sqrt(acc[28] / n_d);
+            e2 = acc[27] + acc[28];
+            n_valid = P.occlusion == 1 ? cnt[1] + cnt[2] : cnt[2];
+        }
         ps->passes[level] += 1;
         double diff_error;
         int accepted;
@@ -655,6 +620,11 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
         }
         if (rec) {
             rec->err2 = e2; rec->n_valid = n_valid; rec->n_visible = n_vis; rec->level = level;
+            rec->err2_depth = 0.0; rec->n_valid_depth = 0; rec->reserved = 0;
+            if (P.occlusion != 0) {
+                rec->err2 = acc[27]; rec->err2_depth = acc[28];
+                rec->n_valid = P.occlusion == 1 ? cnt[1] : cnt[2]; rec->n_valid_depth = cnt[2];
+            }
             rec->it = ps->it; rec->accepted = accepted; rec->used = 3;
             for (int k = 0; k < 16; ++k) rec->pose[k] = ps->pose_eval[k];
             for (int k = 0; k < 21; ++k) rec->hessian[k] = (float)acc[k];

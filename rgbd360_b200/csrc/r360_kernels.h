@@ -27,7 +27,7 @@ struct R360PassArgs {
     const R360Pair* pairs;              // device
     const float2* const* src_base;      // device: per pair, source pyramid {depth, gray}
     const float* const* trg_base;       // device: per pair, target texel pyramid
-    double* acc;                        // device: per pair R360_ACC_DOUBLES
+    double* acc;                        // device: per pair R360_ACC_STRIDE doubles
     int* cnt;                           // device: per pair R360_ACC_INTS
 };
 
@@ -56,6 +56,9 @@ void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, l
                        int n_sensors, int n_frames, int sm_count);
 cudaError_t r360_pass_init();
 void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid);
+// occlusion variants (r360_occ.cu): head / next / dinv hold n_pairs * lv.n entries each
+void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, int* head, int* next, float* dinv,
+                          int sm_count);
 void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
                            uint8_t* vp, uint8_t* vd, int sm_count);
 void r360_launch_index_stats(cudaStream_t st, const R360PassArgs& a, int pair, unsigned long long* out, int sm_count);

@@ -1,0 +1,252 @@
+// r360_occ.cu -- the occlusion variants of the spherical registration:
+//   errorPhotoICP_sphereOcc1 / calcHessGrad_sphereOcc1   (RPI.h:3232-3369, 3373-3716)   occlusion = 1
+//   errorPhotoICP_sphereOcc2 / calcHessGrad_sphereOcc2   (RPI.h:3720-3858, 3861-4249)   occlusion = 2
+//
+// Upstream these loops run `#pragma omp parallel for` over a z-buffer that every iteration reads
+// and writes: the result depends on the thread schedule.  What is implemented here -- and pinned by
+// the compiled reference at one OpenMP thread, tests/test_occlusion.py -- is the semantics of ONE
+// thread (source pixels in index order), evaluated deterministically and in parallel:
+//
+//   * a z-test passer is a source pixel whose 1/|p| is >= that of every EARLIER candidate of the
+//     same target texel (the buffer always holds the running maximum);
+//   * "stored per target texel, last writer wins" = the candidate with the largest source index
+//     (Occ2 H/g), resp. the last passer = the latest occurrence of the maximal 1/|p| (Occ1 error).
+//
+// Two kernels per evaluated pose instead of the fused k_pass:
+//   k_occ_scatter  builds, per target texel, the linked list of its candidate source pixels
+//                  (head[texel] / next[pixel], atomicExch; list ORDER is arbitrary, list CONTENT is not)
+//                  and stores 1/|p| per candidate;
+//   k_occ_eval     every candidate walks its texel's list (1-3 entries) to decide passer / last /
+//                  winner, then accumulates the error sums (PhotoResidual, DepthResidual, counters)
+//                  and the J^T W J / J^T W r rows of ITS variant.  Same packed index path, Jacobian
+//                  rows and block reduction as k_pass; the reference evaluates the error and, when a
+//                  step is accepted, the Hessian at the same pose, so one evaluation yields both.
+#include <algorithm>
+#include "r360_device.cuh"
+#include "r360_kernels.h"
+
+#define R360_OCC_THREADS 256
+#define R360_OCC_GATE 0.3f                     // thresDepthOutliers, RPI.h:4525
+
+namespace {
+
+struct OccPixelPair {
+    R360SrcPair sp;
+    R360Geo2 g;
+    int ii[2];          // target texel index r' * cols + c' (valid when cand)
+    bool inb[2];        // LUT point valid and (r', c') inside the image (RPI.h:3292)
+    float2 ta[3], tb[3];
+};
+
+}  // namespace
+
+// Source pixel pair -> warped geometry, target texel, its six floats.  All 32 lanes must call.
+template <int OCC>
+__device__ __forceinline__ void r360_occ_pixel_pair(const R360PassArgs& a, const R360Level& lv, const r360_params& P,
+                                                    const float* T, const float* Tg, const float4* __restrict__ src4,
+                                                    const float2* __restrict__ trg, int i, OccPixelPair& o) {
+    const bool in0 = i < lv.n, in1 = i + 1 < lv.n;
+    const int r = in0 ? (int)(((unsigned long long)i * lv.div_magic) >> 40) : 0;
+    const int c = in0 ? i - r * lv.cols : 0;
+    const float4 s = in0 ? __ldg(&src4[i >> 1]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r360_load_src_pair(lv, P, s, r, c, in0, in1, o.sp);
+    int rr[2], cc[2];
+    unsigned n_fb = 0;
+    r360_index_pair(T, Tg, lv, o.sp, a.one, o.g, rr, cc, n_fb);
+    o.inb[0] = o.sp.v0 && (unsigned)rr[0] < (unsigned)lv.rows && (unsigned)cc[0] < (unsigned)lv.cols;
+    o.inb[1] = o.sp.v1 && (unsigned)rr[1] < (unsigned)lv.rows && (unsigned)cc[1] < (unsigned)lv.cols;
+    o.ii[0] = o.inb[0] ? rr[0] * lv.cols + cc[0] : 0;
+    o.ii[1] = o.inb[1] ? rr[1] * lv.cols + cc[1] : 0;
+    const float2* tx0 = trg + 3u * (unsigned)o.ii[0];
+    const float2* tx1 = trg + 3u * (unsigned)o.ii[1];
+    o.ta[0] = __ldg(tx0); o.ta[1] = __ldg(tx0 + 1); o.ta[2] = __ldg(tx0 + 2);
+    o.tb[0] = __ldg(tx1); o.tb[1] = __ldg(tx1 + 1); o.tb[2] = __ldg(tx1 + 2);
+}
+
+// Candidate test: Occ1 every in-bounds pixel; Occ2 those within the 0.3 m gate of the target depth
+// (RPI.h:3788-3791; a NaN difference is NOT an outlier upstream: fabs(NaN) > t is false).
+template <int OCC>
+__device__ __forceinline__ bool r360_occ_candidate(bool inb, float depth2, float dist) {
+    if (OCC == 2) return inb && !(fabsf(depth2 - dist) > R360_OCC_GATE);
+    return inb;
+}
+
+template <int OCC>
+__global__ void __launch_bounds__(R360_OCC_THREADS)
+k_occ_scatter(R360PassArgs a, int* __restrict__ head, int* __restrict__ next, float* __restrict__ dinv) {
+    const int ap = blockIdx.y;
+    if (ap >= *a.n_active) return;
+    const R360Level lv = a.lv;
+    const r360_params P = a.params;
+    const int pair = a.active_list[ap];
+    const R360Pair* ps = a.pairs + pair;
+    float T[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) T[k] = ps->pose_eval[k];
+    const float4* src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
+    const float2* trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
+    int* hd = head + (size_t)ap * lv.n;
+    int* nx = next + (size_t)ap * lv.n;
+    float* dv = dinv + (size_t)ap * lv.n;
+    const int stride = 2 * gridDim.x * blockDim.x;
+    for (int base = 0; base < lv.n; base += stride) {           // warp-uniform trip count (warp votes inside)
+        const int i = base + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+        OccPixelPair o;
+        r360_occ_pixel_pair<OCC>(a, lv, P, T, ps->pose_eval, src4, trg, i, o);
+        if (r360_occ_candidate<OCC>(o.inb[0], o.ta[0].y, o.g.dist.x)) {
+            dv[i] = o.g.dinv.x;
+            nx[i] = atomicExch(&hd[o.ii[0]], i);
+        }
+        if (r360_occ_candidate<OCC>(o.inb[1], o.tb[0].y, o.g.dist.y)) {
+            dv[i + 1] = o.g.dinv.y;
+            nx[i + 1] = atomicExch(&hd[o.ii[1]], i + 1);
+        }
+    }
+}
+
+// Walks the candidate list of target texel `ii` on behalf of candidate `i`:
+//   passer : no earlier candidate (smaller source index) has a larger 1/|p|        (RPI.h:3299-3301)
+//   last   : no later candidate exists                                              (last writer of a per-texel slot)
+//   winner : passer and no later candidate passes (none has 1/|p| >= ours)          (last passer)
+__device__ __forceinline__ void r360_occ_walk(const int* __restrict__ hd, const int* __restrict__ nx,
+                                              const float* __restrict__ dv, int ii, int i, bool& passer, bool& last,
+                                              bool& winner) {
+    const float di = dv[i];
+    passer = true; last = true; winner = true;
+    for (int j = hd[ii]; j >= 0; j = nx[j]) {
+        if (j == i) continue;
+        const float dj = dv[j];
+        if (j < i) { if (dj > di) passer = false; }
+        else { last = false; if (dj >= di) winner = false; }
+    }
+    winner = winner && passer;
+}
+
+template <int METHOD, int OCC>
+__global__ void __launch_bounds__(R360_OCC_THREADS)
+k_occ_eval(R360PassArgs a, const int* __restrict__ head, const int* __restrict__ next, const float* __restrict__ dinv) {
+    __shared__ float s_red[R360_OCC_THREADS / 32][R360_ACC_DOUBLES + 1];
+    __shared__ int s_cnt[R360_OCC_THREADS / 32][R360_ACC_INTS];
+    const int ap = blockIdx.y;
+    if (ap >= *a.n_active) return;
+    const R360Level lv = a.lv;
+    const r360_params P = a.params;
+    const int pair = a.active_list[ap];
+    const R360Pair* ps = a.pairs + pair;
+    float T[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) T[k] = ps->pose_eval[k];
+    const float4* src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
+    const float2* trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
+    const int* hd = head + (size_t)ap * lv.n;
+    const int* nx = next + (size_t)ap * lv.n;
+    const float* dv = dinv + (size_t)ap * lv.n;
+
+    R360Acc2 A;
+    r360_acc_zero(A);
+    float sumP = 0.f, sumD = 0.f;
+    int n_vis = 0, n_photo = 0, n_depth = 0;
+    const int stride = 2 * gridDim.x * blockDim.x;
+    for (int base = 0; base < lv.n; base += stride) {
+        const int i = base + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+        OccPixelPair o;
+        r360_occ_pixel_pair<OCC>(a, lv, P, T, ps->pose_eval, src4, trg, i, o);
+        bool okH[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float2* t = q ? o.tb : o.ta;
+            const float dist = q ? o.g.dist.y : o.g.dist.x;
+            const float Is = q ? o.sp.Is.y : o.sp.Is.x;
+            const bool cand = r360_occ_candidate<OCC>(o.inb[q], t[0].y, dist);
+            bool passer = false, last = false, winner = false;
+            if (cand) r360_occ_walk(hd, nx, dv, o.ii[q], i + q, passer, last, winner);
+            // ---- error function of the variant
+            const bool cnt_on = passer;                                   // counters count every passer
+            const bool sum_on = OCC == 1 ? winner : passer;               // Occ1 sums one value per texel (RPI.h:3318)
+            const bool photo_sal = !((fabsf(t[1].x) < P.thres_sal_int) & (fabsf(t[1].y) < P.thres_sal_int));
+            const bool depth_ok = (fabsf(t[0].y) < INFINITY) &&
+                                  !((fabsf(t[2].x) < P.thres_sal_depth) & (fabsf(t[2].y) < P.thres_sal_depth));
+            if (OCC == 2 && cnt_on) ++n_depth;                            // nValidDepthPts, RPI.h:3798
+            bool reach = true;                                            // the photo `continue` precedes the depth term
+            if (METHOD != R360_DEPTH_CONSISTENCY) {
+                reach = photo_sal;
+                if (photo_sal) {
+                    if (OCC == 1 && cnt_on) ++n_photo;                    // nValidPhotoPts, RPI.h:3319
+                    if (sum_on) { const float r = r360_wres_photo(t[0].x, Is, P, a.inv_std_photo); sumP += r * r; }
+                }
+            }
+            if (METHOD != R360_PHOTO_CONSISTENCY) {
+                if (reach && depth_ok) {
+                    if (OCC == 1 && cnt_on) ++n_depth;                    // RPI.h:3338
+                    if (sum_on) { const float r = r360_wres_depth(t[0].y, dist, P); sumD += r * r; }
+                }
+            }
+            // ---- rows of calcHessGrad_sphereOccN: Occ1 every in-bounds pixel (its z-buffer is indexed by
+            //      the SOURCE pixel, RPI.h:3473-3475, and never rejects); Occ2 the last candidate of a texel
+            okH[q] = OCC == 1 ? o.inb[q] : last;
+            n_vis += okH[q] ? 1 : 0;                                      // numVisiblePixels (Occ2: distinct texels)
+        }
+        r360_rows_pair<METHOD, 1>(o.g, lv.res_inv, o.sp.Is, o.ta, o.tb, okH[0], okH[1], P, a.inv_std_photo, A);
+    }
+
+    // ---- block reduction: 27 normal-equation sums + PhotoResidual + DepthResidual, 3 counters
+    float acc[R360_ACC_DOUBLES + 1];
+    r360_acc_unpack(A, acc);
+    acc[27] = sumP;
+    acc[28] = sumD;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < R360_ACC_DOUBLES + 1; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) s_red[wid][k] = v;
+    }
+    n_vis = __reduce_add_sync(0xffffffffu, n_vis);
+    n_photo = __reduce_add_sync(0xffffffffu, n_photo);
+    n_depth = __reduce_add_sync(0xffffffffu, n_depth);
+    if (lane == 0) { s_cnt[wid][0] = n_vis; s_cnt[wid][1] = n_photo; s_cnt[wid][2] = n_depth; s_cnt[wid][3] = 0; }
+    __syncthreads();
+    if (threadIdx.x < R360_ACC_DOUBLES + 1) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < R360_OCC_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
+        atomicAdd(&a.acc[(size_t)pair * R360_ACC_STRIDE + threadIdx.x], sum);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < R360_OCC_THREADS / 32; ++k) sum += s_cnt[k][threadIdx.x - 32];
+        atomicAdd(&a.cnt[(size_t)pair * R360_ACC_INTS + threadIdx.x - 32], sum);
+    }
+}
+
+// =========================================================================== launch wrappers
+static dim3 occ_grid(const R360PassArgs& a, int n_pairs, int sm_count) {
+    long long blocks = ((long long)(a.lv.n + 1) / 2 + R360_OCC_THREADS - 1) / R360_OCC_THREADS;
+    const long long cap = std::max(1LL, 8LL * sm_count / std::max(n_pairs, 1));     // ~8 CTAs per SM over all pairs
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return dim3((unsigned)blocks, (unsigned)n_pairs);
+}
+
+// One evaluation (error + Hessian / gradient of the occlusion variant) of the active pairs at their
+// pose_eval: list heads reset, scatter, evaluate.  scratch: head | next | dinv, each n_pairs * lv.n.
+void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, int* head, int* next, float* dinv,
+                          int sm_count) {
+    cudaMemsetAsync(head, 0xFF, sizeof(int) * (size_t)n_pairs * a.lv.n, st);
+    const dim3 grid = occ_grid(a, n_pairs, sm_count);
+    const int occ = a.params.occlusion;
+    if (occ == 1) k_occ_scatter<1><<<grid, R360_OCC_THREADS, 0, st>>>(a, head, next, dinv);
+    else k_occ_scatter<2><<<grid, R360_OCC_THREADS, 0, st>>>(a, head, next, dinv);
+#define R360_OCC_EVAL(M)                                                                                 \
+    do {                                                                                                 \
+        if (occ == 1) k_occ_eval<M, 1><<<grid, R360_OCC_THREADS, 0, st>>>(a, head, next, dinv);          \
+        else k_occ_eval<M, 2><<<grid, R360_OCC_THREADS, 0, st>>>(a, head, next, dinv);                   \
+    } while (0)
+    switch (a.params.method) {
+        case R360_PHOTO_CONSISTENCY: R360_OCC_EVAL(R360_PHOTO_CONSISTENCY); break;
+        case R360_DEPTH_CONSISTENCY: R360_OCC_EVAL(R360_DEPTH_CONSISTENCY); break;
+        default: R360_OCC_EVAL(R360_PHOTO_DEPTH); break;
+    }
+#undef R360_OCC_EVAL
+}

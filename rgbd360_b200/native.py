@@ -19,7 +19,7 @@ EXPORTS = [
     "r360_synth_frames_dev", "r360_synth_frames", "r360_synth_gt_pose", "r360_device_alloc",
     "r360_device_free", "r360_synchronize", "r360_last_device_ms", "r360_kernel_launches",
     "r360_last_pass_stats", "r360_version", "r360_index_stats", "r360_register_host_pairs",
-    "r360_default_rig", "r360_frame360_parse", "r360_stitch_frames",
+    "r360_default_rig", "r360_frame360_parse", "r360_stitch_frames", "r360_eval_error_occ",
 ]
 
 
@@ -52,7 +52,7 @@ class IterRecord(C.Structure):
         ("err2", C.c_double), ("n_valid", C.c_int32), ("n_visible", C.c_int32),
         ("level", C.c_int32), ("it", C.c_int32), ("accepted", C.c_int32), ("used", C.c_int32),
         ("pose", C.c_float * 16), ("hessian", C.c_float * 21), ("gradient", C.c_float * 6),
-        ("pad", C.c_float),
+        ("pad", C.c_float), ("err2_depth", C.c_double), ("n_valid_depth", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -106,6 +106,8 @@ def lib():
     L.r360_register_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.r360_register_host_pairs.argtypes = [vp, i32, vp, vp, vp, vp]
     L.r360_eval_error.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    L.r360_eval_error_occ.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.r360_eval_hessgrad.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.POINTER(C.c_int32)]
     L.r360_dump_level.argtypes = [vp, i32, i32] + [vp] * 6
     L.r360_dump_source_level.argtypes = [vp, i32, i32, vp, vp]
@@ -299,6 +301,15 @@ class Context:
         T = pose_to_colmajor(pose)
         self._ck(self.L.r360_eval_error(self.h, src, trg, level, _p(T), C.byref(e2), C.byref(n)))
         return e2.value, n.value
+
+    def eval_error_occ(self, src, trg, level, pose):
+        """errorPhotoICP_sphereOcc1 / Occ2 (ctx created with occlusion 1 / 2) -> dict(photo, depth, n_photo, n_depth, error)."""
+        pr, dr, e = C.c_double(), C.c_double(), C.c_double()
+        npv, ndv = C.c_int32(), C.c_int32()
+        T = pose_to_colmajor(pose)
+        self._ck(self.L.r360_eval_error_occ(self.h, src, trg, level, _p(T), C.byref(pr), C.byref(dr), C.byref(npv),
+                                            C.byref(ndv), C.byref(e)))
+        return dict(photo=pr.value, depth=dr.value, n_photo=npv.value, n_depth=ndv.value, error=e.value)
 
     def eval_hessgrad(self, src, trg, level, pose):
         H = np.zeros(36, np.float32); g = np.zeros(6, np.float32); nv = C.c_int32()

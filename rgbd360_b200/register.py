@@ -76,12 +76,13 @@ class RegisterPhotoICP:
         self._ctx.set_frames(1, rgb[None], depth[None], [ROLE_TARGET])
 
     def alignFrames360(self, pose_guess=None, method=PHOTO_CONSISTENCY, occlusion=0):
-        if occlusion != 0:
-            raise NotImplementedError("occlusion variants (RPI.h:3232-4249) are out of scope")
+        if occlusion not in (0, 1, 2):
+            raise ValueError("occlusion must be 0, 1 or 2 (RPI.h:4517)")
         if self._ctx is None:
             raise RuntimeError("setSourceFrame / setTargetFrame first")
-        if method != self._p.method:
+        if method != self._p.method or occlusion != self._p.occlusion:
             self._p.method = int(method)
+            self._p.occlusion = int(occlusion)
             self._ctx.close(); self._ctx = None
             self._ensure(self._pending[0][0])
         guess = None if pose_guess is None else pose_to_colmajor(pose_guess)[None]

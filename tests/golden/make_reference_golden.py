@@ -2,7 +2,8 @@
 against oracle/refshim/, both arithmetic variants) on the cases of tests/refcases.py and records its
 outputs as tests/golden/reference_outputs.json.  Only runnable where /root/reference exists.
 
-    python tests/golden/make_reference_golden.py
+    python tests/golden/make_reference_golden.py          # both recordings
+    python tests/golden/make_reference_golden.py occ      # reference_occlusion.json only
 """
 import hashlib
 import json
@@ -67,6 +68,57 @@ def run_reference(case, pinned, threads=1):
     return out
 
 
+# ---- alignFrames360(..., occlusion = 1 / 2) and the *_sphereOcc1 / Occ2 functions.
+# Upstream these are order-dependent under OpenMP; the recording is taken with ONE thread (source order).
+OCC_CASES = ["synth_128x256_L3_pd", "synth_256x512_L4_pd_far", "synth_128x256_L3_holes", "synth_128x256_L3_depth",
+             "synth_128x256_L3_photo", "loop_128x256_L3", "sample_pair_1920x320_L4"]
+
+
+def _f(x):
+    """JSON-safe float (NaN -> None)."""
+    x = float(x)
+    return None if x != x else x
+
+
+def run_reference_occ(case, pinned, occ):
+    refbind.lib(pinned).ref_set_threads(1)
+    R = refbind.Reference(n_levels=case["levels"], std_photo=case["std_photo"], pinned=pinned)
+    R.set_source(case["rgb_s"], case["d_s"])
+    R.set_target(case["rgb_t"], case["d_t"])
+    a = R.align(case["guess"], case["method"], occ)
+    out = dict(pose=a["pose"].astype(np.float64).ravel().tolist(), H=a["H"].astype(np.float64).ravel().tolist(),
+               g=a["g"].astype(np.float64).tolist(), sso=a["sso"], iters=a["iters"].tolist(), ill_posed=bool(a["ill_posed"]))
+    if not any(a["iters"]):
+        # the loop body may never have run (e.g. occlusion 1 with a single cost term: 0/0 = NaN error):
+        # the getters then return uninitialised members
+        out["H"] = out["g"] = out["sso"] = None
+    probes = []
+    for T in refcases.probe_poses() + [a["pose"]]:
+        e, avp, avd = R.error_occ(0, T, case["method"], occ)
+        H, g, sso = R.hessgrad_occ(0, T, case["method"], occ)
+        probes.append(dict(pose=np.asarray(T, np.float64).ravel().tolist(), error=_f(e), av_photo=_f(avp), av_depth=_f(avd),
+                           H=H.astype(np.float64).ravel().tolist(), g=g.astype(np.float64).tolist(), sso=sso))
+    out["probes_level0"] = probes
+    R.close()
+    return out
+
+
+def main_occ():
+    gold = {"_how": "oracle/_ref (reference header + refshim), OMP threads = 1, alignFrames360 occlusion = 1 / 2 and "
+                    "errorPhotoICP_sphereOcc{1,2} / calcHessGrad_sphereOcc{1,2} called directly; see this script",
+            "cases": {}}
+    for name in OCC_CASES:
+        case = refcases.make_case(orc, name)
+        gold["cases"][name] = {}
+        for occ in (1, 2):
+            gold["cases"][name][str(occ)] = {"libm": run_reference_occ(case, False, occ),
+                                             "pinned": run_reference_occ(case, True, occ)}
+            c = gold["cases"][name][str(occ)]
+            print(name, "occ", occ, "iters", c["libm"]["iters"], c["pinned"]["iters"])
+    with open(os.path.join(HERE, "reference_occlusion.json"), "w") as f:
+        json.dump(gold, f, indent=0)
+
+
 def main():
     gold = {"_how": "oracle/_ref (reference header + refshim), OMP threads = 1; see this script", "cases": {}}
     for name in refcases.CASES:
@@ -79,4 +131,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "occ":
+        main_occ()
+    else:
+        main()
+        main_occ()

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(native):
 def test_struct_layouts_match_header(native):
     assert C.sizeof(native.Params) == 64
     assert C.sizeof(native.Result) == 336
-    assert C.sizeof(native.IterRecord) == 208
+    assert C.sizeof(native.IterRecord) == 224
     assert native.native.RESULT_DTYPE.itemsize == 336
     p = native.default_params()
     assert (p.n_levels, p.max_iters, p.method, p.occlusion, p.n_sensors_mask) == (4, 10, 2, 0, 8)

@@ -275,7 +275,7 @@ def test_errors_are_loud(r360):
     with pytest.raises(r360.R360Error):
         ctx.register_pairs([0], [1])                  # frames never set
     with pytest.raises(r360.R360Error):
-        r360.Context(64, 128, 2, 1, r360.default_params(n_levels=2, occlusion=1))
+        r360.Context(64, 128, 2, 1, r360.default_params(n_levels=2, occlusion=3))
     with pytest.raises(r360.R360Error):
         r360.Context(65, 128, 2, 1, r360.default_params(n_levels=2))
     ctx.close()
