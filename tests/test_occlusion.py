@@ -229,7 +229,12 @@ def test_gpu_occlusion_align(orc, r360, gold_occ, name, occ):
         assert ang <= POSE_TOL and dist <= POSE_TOL, (ang, dist)
         if list(res_o.iters)[:L] == ref["iters"]:
             ang, dist = pose_err(Tg, np.array(ref["pose"]).reshape(4, 4))
-            assert ang <= POSE_TOL and dist <= POSE_TOL, (ang, dist)
+            # The recording was taken with the reference's 27 FLOAT accumulators (RPI.h:3605-3606); the GPU
+            # (and the oracle's STABLE mode it is held to 1e-4 against, above) sums in double.  On the real
+            # sample pair (30 accepted steps, 28 % invalid depth) that alone moves the reference's result by
+            # 1.5e-4 m -- its sensitivity to its own summation order, see test_sample_pair_summation_order_sensitivity.
+            tol = 5e-4 if name.startswith("sample_pair") else POSE_TOL
+            assert ang <= tol and dist <= tol, (ang, dist)
     finally:
         ctx.close()
 
