@@ -35,6 +35,7 @@ struct Ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_copy[kStages]{}, ev_done[kStages]{};
     int chunk = kChunkFrames;                    // frames per chunk = min(kChunkFrames, max_frames)
+    bool use_pyr_head = true;                    // R360_PYR_HEAD=0 in the environment: the separate level-0 kernels (A/B measurements)
     long long n_chunks_done = 0;                 // staging-buffer rotation across calls
     std::vector<cudaEvent_t> ev_pass;            // pairs of events around each pixel pass
     float* d_tables = nullptr;
@@ -48,6 +49,11 @@ struct Ctx {
     float2** h_pyr = nullptr; float2** d_pyr = nullptr;
     float2** h_pyr_t = nullptr; float2** d_pyr_t = nullptr;
     float** h_trg_t = nullptr; float** d_trg_t = nullptr;
+    // fused pyramid head: per frame of a chunk, where level 0 goes (null: target-only frame), where level 1
+    // goes, where the level-0 texels go (null: source-only frame)
+    float2** h_l0 = nullptr; float2** d_l0 = nullptr;
+    float2** h_l1 = nullptr; float2** d_l1 = nullptr;
+    float** h_tex = nullptr; float** d_tex = nullptr;
     // pair batch
     R360Pair* d_pairs = nullptr;
     double* d_acc = nullptr; int* d_cnt = nullptr;
@@ -164,15 +170,33 @@ int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t
         CK(c, cudaMemcpyAsync(c->d_pyr_t + table_off, c->h_pyr_t + table_off, sizeof(float2*) * n_t, cudaMemcpyHostToDevice, c->st));
         CK(c, cudaMemcpyAsync(c->d_trg_t + table_off, c->h_trg_t + table_off, sizeof(float*) * n_t, cudaMemcpyHostToDevice, c->st));
     }
-    r360_launch_level0(c->st, rgb_dev, depth_mm_dev, depth_m_dev, c->d_pyr + table_off, n, c->rows * c->cols, c->sm_count);
-    ++c->launches;
-    for (int l = 1; l < c->L; ++l) {
+    // Levels 0 and 1 and the level-0 texels come from ONE pass over the raw input (k_pyr_head) when the
+    // pyramid has a level 1; the remaining levels from k_down / k_texel.
+    const bool fused_head = c->L >= 2 && c->use_pyr_head;
+    if (fused_head) {
+        for (int k = 0; k < n; ++k) {
+            const int role = roles ? roles[k] : R360_ROLE_BOTH;
+            c->h_l0[table_off + k] = (role & R360_ROLE_SOURCE) ? c->h_pyr[table_off + k] : nullptr;
+            c->h_l1[table_off + k] = c->h_pyr[table_off + k] + c->lv[1].px_off;
+            c->h_tex[table_off + k] = (role & R360_ROLE_TARGET) ? c->trg[first + k] : nullptr;
+        }
+        CK(c, cudaMemcpyAsync(c->d_l0 + table_off, c->h_l0 + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
+        CK(c, cudaMemcpyAsync(c->d_l1 + table_off, c->h_l1 + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
+        CK(c, cudaMemcpyAsync(c->d_tex + table_off, c->h_tex + table_off, sizeof(float*) * n, cudaMemcpyHostToDevice, c->st));
+        r360_launch_pyr_head(c->st, rgb_dev, depth_mm_dev, depth_m_dev, c->d_l0 + table_off, c->d_l1 + table_off,
+                             c->d_tex + table_off, c->rows, c->cols, c->P.min_depth, c->P.max_depth, c->P.n_sensors_mask, n);
+        ++c->launches;
+    } else {
+        r360_launch_level0(c->st, rgb_dev, depth_mm_dev, depth_m_dev, c->d_pyr + table_off, n, c->rows * c->cols, c->sm_count);
+        ++c->launches;
+    }
+    for (int l = fused_head ? 2 : 1; l < c->L; ++l) {
         r360_launch_down(c->st, c->d_pyr + table_off, c->lv[l - 1].px_off, c->lv[l].px_off, c->lv[l - 1].rows,
                          c->lv[l - 1].cols, c->P.min_depth, c->P.max_depth, n, c->sm_count);
         ++c->launches;
     }
     if (n_t)
-        for (int l = 0; l < c->L; ++l) {
+        for (int l = fused_head ? 1 : 0; l < c->L; ++l) {
             r360_launch_texel(c->st, c->d_pyr_t + table_off, c->d_trg_t + table_off, c->lv[l].px_off, c->lv[l].rows,
                               c->lv[l].cols, c->P.n_sensors_mask, n_t, c->sm_count);
             ++c->launches;
@@ -332,6 +356,8 @@ void r360_destroy(r360_ctx* c) {
     for (int b = 0; b < kStages; ++b) { cudaFree(c->stage_rgb[b]); cudaFree(c->stage_depth[b]); }
     cudaFree(c->d_pyr); cudaFree(c->d_pyr_t); cudaFree(c->d_trg_t);
     cudaFreeHost(c->h_pyr); cudaFreeHost(c->h_pyr_t); cudaFreeHost(c->h_trg_t);
+    cudaFree(c->d_l0); cudaFree(c->d_l1); cudaFree(c->d_tex);
+    cudaFreeHost(c->h_l0); cudaFreeHost(c->h_l1); cudaFreeHost(c->h_tex);
     cudaFree(c->d_pairs); cudaFree(c->d_acc); cudaFree(c->d_cnt); cudaFree(c->d_active); cudaFree(c->d_nactive);
     cudaFree(c->d_srcb); cudaFree(c->d_trgb); cudaFreeHost(c->h_srcb); cudaFreeHost(c->h_trgb);
     cudaFree(c->d_idx); cudaFreeHost(c->h_idx); cudaFree(c->d_pose); cudaFreeHost(c->h_pose);
@@ -424,6 +450,10 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaMallocHost(&c->h_pyr, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_pyr, sizeof(void*) * max_frames));
     CK(c, cudaMallocHost(&c->h_pyr_t, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_pyr_t, sizeof(void*) * max_frames));
     CK(c, cudaMallocHost(&c->h_trg_t, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_trg_t, sizeof(void*) * max_frames));
+    CK(c, cudaMallocHost(&c->h_l0, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_l0, sizeof(void*) * max_frames));
+    CK(c, cudaMallocHost(&c->h_l1, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_l1, sizeof(void*) * max_frames));
+    CK(c, cudaMallocHost(&c->h_tex, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_tex, sizeof(void*) * max_frames));
+    if (const char* e = getenv("R360_PYR_HEAD")) c->use_pyr_head = atoi(e) != 0;
 
     const int np = max_pairs + 1;     // + 1 spare slot for the eval hooks
     CK(c, cudaMalloc(&c->d_pairs, sizeof(R360Pair) * np));

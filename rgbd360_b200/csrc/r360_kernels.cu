@@ -135,23 +135,78 @@ k_down(float2* const* __restrict__ pyr, long long off_src, long long off_dst, in
 
 // calcGradientXY (RPI.h:365-398): harmonic mean of the one-sided differences on strictly
 // monotone triples, 0 elsewhere and on the border:  g = 2 / (1/(nxt - v) + 1/(v - prv)).
-// Evaluated for two pixels at once with the packed IEEE reciprocal / division sequences (the
-// differences of a strictly monotone triple of finite floats are normal numbers of equal sign,
-// so the sequences are exact); a non-finite result (Inf / NaN neighbours, CV_32F depth only) is
-// recomputed with the scalar operators.
+// Evaluated for two pixels at once with the packed IEEE reciprocal sequences (the differences of a
+// strictly monotone triple of finite floats are normal numbers of equal sign, so the sequences are
+// exact; 2 / s == 2 * RN(1 / s) because scaling by 2 commutes with rounding).  The four gradients of
+// a pixel pair share ONE check for a non-finite result (Inf / NaN neighbours, CV_32F depth only, or
+// operands outside the normal range), which recomputes them with the scalar IEEE operators.
 __device__ __forceinline__ float r360_hgrad(float v, float nxt, float prv) {
     if ((v > nxt && v < prv) || (v < nxt && v > prv)) return 2.f / (1 / (nxt - v) + 1 / (v - prv));
     return 0.f;
 }
 __device__ __forceinline__ float2 r360_hgrad2(float2 v, float2 nxt, float2 prv) {
     const float2 a = f2add(nxt, f2neg(v)), b = f2add(v, f2neg(prv));
-    const float2 g = f2div_rn(R360_F2(2.0f), f2add(f2rcp_rn(a), f2rcp_rn(b)));
-    // strictly monotone  <=>  both differences non-zero with equal sign (float subtraction keeps signs exactly)
-    const bool m0 = (a.x > 0.f & b.x > 0.f) | (a.x < 0.f & b.x < 0.f), m1 = (a.y > 0.f & b.y > 0.f) | (a.y < 0.f & b.y < 0.f);
-    float g0 = m0 ? g.x : 0.f, g1 = m1 ? g.y : 0.f;
-    if (!(fabsf(g0) < INFINITY)) g0 = r360_hgrad(v.x, nxt.x, prv.x);
-    if (!(fabsf(g1) < INFINITY)) g1 = r360_hgrad(v.y, nxt.y, prv.y);
-    return make_float2(g0, g1);
+    const float2 r = f2rcp_rn(f2add(f2rcp_rn(a), f2rcp_rn(b)));
+    const float2 g = f2add(r, r);
+    // strictly monotone  <=>  both differences non-zero with equal sign (float subtraction keeps signs
+    // exactly)  <=>  (a 2^100)(b 2^100) > 0: the scaling is exact and keeps the product of two non-zero
+    // floats (denormals included) away from underflow; an overflow keeps the sign, 0 * Inf and NaN compare false.
+    const float K = 1.2676506002282294e30f;                                  // 2^100
+    const float2 p = f2mul(f2mul(a, R360_F2(K)), f2mul(b, R360_F2(K)));
+    return make_float2(p.x > 0.f ? g.x : 0.f, p.y > 0.f ? g.y : 0.f);
+}
+struct R360Grad4 { float2 ix, iy, dx, dy; };
+// Rare path, out of line (registers in, registers out): one gradient pair again, scalar IEEE operators.
+static __device__ __noinline__ float2 r360_hgrad2_scalar(float v0, float n0, float p0, float v1, float n1, float p1) {
+    return make_float2(r360_hgrad(v0, n0, p0), r360_hgrad(v1, n1, p1));
+}
+// Texels of the pixel pair (r, c), (r, c + 1), c even: v = {d0, g0, d1, g1} of the pair, u / d the pairs
+// above / below, wv / e the {depth, gray} west of pixel 0 / east of pixel 1 (any finite value on the image
+// border: border gradients are forced to 0).  Writes {gray, depth, Ix, Iy, Dx, Dy} x 2 as three float4.
+struct R360MaskGeom { int ws, n_sensors; unsigned magic; };     // ws = cols / n_sensors (0: no mask), magic = ceil(2^32 / ws) (0 when ws == 1)
+__device__ __forceinline__ void r360_texel_pair(float4 v, float4 u, float4 d, float2 wv, float2 e, int r, int c, int rows,
+                                                int cols, const R360MaskGeom& mg, float4 out[3]) {
+    R360Grad4 G;
+    G.ix = G.iy = G.dx = G.dy = make_float2(0.f, 0.f);
+    if (r > 0 && r < rows - 1) {
+        G.ix = r360_hgrad2(make_float2(v.y, v.w), make_float2(v.w, e.y), make_float2(wv.y, v.y));
+        G.dx = r360_hgrad2(make_float2(v.x, v.z), make_float2(v.z, e.x), make_float2(wv.x, v.x));
+        G.iy = r360_hgrad2(make_float2(v.y, v.w), make_float2(d.y, d.w), make_float2(u.y, u.w));
+        G.dy = r360_hgrad2(make_float2(v.x, v.z), make_float2(d.x, d.z), make_float2(u.x, u.z));
+        const float2 chk = f2add(f2add(G.ix, G.iy), f2add(G.dx, G.dy));                      // Inf / NaN if any term is
+        if (!(fabsf(chk.x) < INFINITY) | !(fabsf(chk.y) < INFINITY)) {
+            G.ix = r360_hgrad2_scalar(v.y, v.w, wv.y, v.w, e.y, v.y);
+            G.dx = r360_hgrad2_scalar(v.x, v.z, wv.x, v.z, e.x, v.x);
+            G.iy = r360_hgrad2_scalar(v.y, d.y, u.y, v.w, d.w, u.w);
+            G.dy = r360_hgrad2_scalar(v.x, d.x, u.x, v.z, d.z, u.z);
+        }
+        if (c == 0) { G.ix.x = 0.f; G.iy.x = 0.f; G.dx.x = 0.f; G.dy.x = 0.f; }              // border columns
+        if (c + 2 == cols) { G.ix.y = 0.f; G.iy.y = 0.f; G.dx.y = 0.f; G.dy.y = 0.f; }
+    }
+    if (mg.ws > 0) {
+        // sensor-joint columns k*ws-1 and k*ws, k = 1..n_sensors-1 (RPI.h:4537-4549); c / ws by multiplication
+        // (exact for c * ws < 2^32)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int cc = c + p, k0 = mg.magic ? (int)__umulhi((unsigned)cc, mg.magic) : cc, rem = cc - k0 * mg.ws;
+            const bool masked = (rem == 0 && k0 >= 1 && k0 <= mg.n_sensors - 1) ||
+                                (rem == mg.ws - 1 && k0 + 1 <= mg.n_sensors - 1);
+            if (masked) {
+                if (p == 0) { G.ix.x = 0.f; G.iy.x = 0.f; G.dx.x = 0.f; G.dy.x = 0.f; }
+                else { G.ix.y = 0.f; G.iy.y = 0.f; G.dx.y = 0.f; G.dy.y = 0.f; }
+            }
+        }
+    }
+    out[0] = make_float4(v.y, v.x, G.ix.x, G.iy.x);
+    out[1] = make_float4(G.dx.x, G.dy.x, v.w, v.z);
+    out[2] = make_float4(G.ix.y, G.iy.y, G.dx.y, G.dy.y);
+}
+static inline R360MaskGeom r360_mask_geom(int cols, int n_sensors) {
+    R360MaskGeom mg;
+    mg.n_sensors = n_sensors;
+    mg.ws = n_sensors > 1 ? cols / n_sensors : 0;
+    mg.magic = mg.ws > 1 ? (unsigned)(((1ULL << 32) + mg.ws - 1) / mg.ws) : 0u;     // 0: ws == 1, c / ws = c
+    return mg;
 }
 
 // Target texels of one level: {gray, depth, Ix, Iy, Dx, Dy} with the sensor-joint columns of the
@@ -159,43 +214,154 @@ __device__ __forceinline__ float2 r360_hgrad2(float2 v, float2 nxt, float2 prv) 
 // (cols is even): 5 loads and three 16-byte stores per pixel pair.
 __global__ void __launch_bounds__(256)
 k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long long off, int rows,
-        int cols, int n_sensors) {
+        int cols, R360MaskGeom mg) {
     const int f = blockIdx.y;
     const float2* __restrict__ s = pyr[f] + off;
     float4* __restrict__ o = reinterpret_cast<float4*>(trg[f] + off * R360_TEXEL_FLOATS);
     const int n2 = (rows * cols) >> 1, half = cols >> 1;
-    const int ws = n_sensors > 1 ? cols / n_sensors : 0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += gridDim.x * blockDim.x) {
         const int r = q / half, c = 2 * (q - r * half), i = r * cols + c;
         const float4 v = __ldg(reinterpret_cast<const float4*>(s + i));              // {d0, g0, d1, g1}
-        float2 ix = make_float2(0.f, 0.f), iy = ix, dx = ix, dy = ix;
+        float4 u = v, d = v;
+        float2 wv = make_float2(0.f, 0.f), e = wv;
         if (r > 0 && r < rows - 1) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(s + i - cols)), d = __ldg(reinterpret_cast<const float4*>(s + i + cols));
-            const float2 wv = c > 0 ? __ldg(&s[i - 1]) : make_float2(0.f, 0.f);
-            const float2 e = c + 2 < cols ? __ldg(&s[i + 2]) : make_float2(0.f, 0.f);
-            ix = r360_hgrad2(make_float2(v.y, v.w), make_float2(v.w, e.y), make_float2(wv.y, v.y));
-            dx = r360_hgrad2(make_float2(v.x, v.z), make_float2(v.z, e.x), make_float2(wv.x, v.x));
-            iy = r360_hgrad2(make_float2(v.y, v.w), make_float2(d.y, d.w), make_float2(u.y, u.w));
-            dy = r360_hgrad2(make_float2(v.x, v.z), make_float2(d.x, d.z), make_float2(u.x, u.z));
-            if (c == 0) { ix.x = 0.f; iy.x = 0.f; dx.x = 0.f; dy.x = 0.f; }                  // border columns
-            if (c + 2 == cols) { ix.y = 0.f; iy.y = 0.f; dx.y = 0.f; dy.y = 0.f; }
+            u = __ldg(reinterpret_cast<const float4*>(s + i - cols));
+            d = __ldg(reinterpret_cast<const float4*>(s + i + cols));
+            if (c > 0) wv = __ldg(&s[i - 1]);
+            if (c + 2 < cols) e = __ldg(&s[i + 2]);
         }
-        if (ws > 0) {
-            // columns k*ws-1 and k*ws, k = 1..n_sensors-1
+        float4 t[3];
+        r360_texel_pair(v, u, d, wv, e, r, c, rows, cols, mg, t);
+        o[3 * (size_t)q + 0] = t[0];
+        o[3 * (size_t)q + 1] = t[1];
+        o[3 * (size_t)q + 2] = t[2];
+    }
+}
+
+// Fused head of the pyramid build: level 0 (RGB8 -> gray, depth -> metres), the level-0 target
+// texels (gradients + joint mask) and level 1 (pyrDown + valid-mean) of a frame in ONE pass over the
+// raw input, tile by tile through shared memory.  The separate kernels move 5 + 8 (k_level0) + 8 + 2
+// (k_down) + 8 + 24 (k_texel) = 55 B per level-0 pixel of a target frame; this one moves 5 + 24 + 2
+// (+ 8 only when the frame is also a source) -- the level-0 {depth, gray} plane of a target-only frame
+// never exists in HBM.  Per-pixel arithmetic is that of k_level0 / k_down / k_texel, operation for
+// operation (the planes stay bit-identical to the oracle's).
+//   tile: R360_F0_TW x R360_F0_TH level-0 pixels + a 2-pixel REFLECT_101 halo (5-tap filter; the
+//   gradients need 1), staged as {depth, gray}; x is padded to groups of 4 pixels so that the raw
+//   loads are the 12-byte RGB / 8-byte depth vectors of k_level0.
+#define R360_F0_TW 64
+#define R360_F0_TH 32
+#define R360_F0_SW (R360_F0_TW + 8)            // smem columns: global x = tx0 - 4 + sx
+#define R360_F0_SH (R360_F0_TH + 4)            // smem rows:    global y = ty0 - 2 + sy
+__device__ __forceinline__ int r360_reflect101_clamped(int i, int n) {
+    i = r360_reflect101(i, n);
+    return min(max(i, 0), n - 1);               // partial tiles reach far outside; those values are never used
+}
+__device__ __forceinline__ float r360_gray_u8(unsigned r, unsigned g, unsigned b) {
+    const int v = (int)(r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15;
+    return (float)v * (float)(1. / 255);
+}
+__global__ void __launch_bounds__(256)
+k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_mm, const float* __restrict__ depth_m,
+           float2* const* __restrict__ l0_dst, float2* const* __restrict__ l1_dst, float* const* __restrict__ texel_dst,
+           int rows, int cols, int tiles_x, float min_d, float max_d, R360MaskGeom mg) {
+    __shared__ __align__(16) float2 s_dg[R360_F0_SH][R360_F0_SW];
+    __shared__ float s_h[R360_F0_SH][R360_F0_TW / 2];
+    const int f = blockIdx.y;
+    const int ty0 = (blockIdx.x / tiles_x) * R360_F0_TH, tx0 = (blockIdx.x % tiles_x) * R360_F0_TW;
+    const size_t n_px = (size_t)rows * cols;
+    const uint8_t* __restrict__ c8 = rgb + (size_t)f * n_px * 3;
+    const float ds = (float)0.001;
+
+    // ---- phase 1: raw input -> {depth, gray} of the tile + halo, 4 pixels per step
+    constexpr int GROUPS = R360_F0_SW / 4;
+    for (int q = threadIdx.x; q < GROUPS * R360_F0_SH; q += 256) {
+        const int sy = q / GROUPS, gq = q - sy * GROUPS;
+        const int gy = r360_reflect101_clamped(ty0 - 2 + sy, rows);
+        const int gx0 = tx0 - 4 + 4 * gq;
+        float d[4], g[4];
+        if (gx0 >= 0 && gx0 + 3 < cols) {
+            const size_t i0 = (size_t)gy * cols + gx0;                         // multiple of 4
+            const uint32_t* c4 = reinterpret_cast<const uint32_t*>(c8 + 3 * i0);
+            const uint32_t w0 = __ldg(c4), w1 = __ldg(c4 + 1), w2 = __ldg(c4 + 2);
+            g[0] = r360_gray_u8(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+            g[1] = r360_gray_u8(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
+            g[2] = r360_gray_u8((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
+            g[3] = r360_gray_u8((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+            if (depth_mm) {
+                const uint2 dd = __ldg(reinterpret_cast<const uint2*>(depth_mm + (size_t)f * n_px + i0));
+                d[0] = (float)(dd.x & 0xffffu) * ds; d[1] = (float)(dd.x >> 16) * ds;
+                d[2] = (float)(dd.y & 0xffffu) * ds; d[3] = (float)(dd.y >> 16) * ds;
+            } else {
+                const float4 dd = __ldg(reinterpret_cast<const float4*>(depth_m + (size_t)f * n_px + i0));
+                d[0] = dd.x; d[1] = dd.y; d[2] = dd.z; d[3] = dd.w;
+            }
+        } else {                                                               // image border columns: REFLECT_101
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const int cc = c + p, k0 = cc / ws, rem = cc - k0 * ws;
-                const bool masked = (rem == 0 && k0 >= 1 && k0 <= n_sensors - 1) ||
-                                    (rem == ws - 1 && k0 + 1 <= n_sensors - 1);
-                if (masked) {
-                    if (p == 0) { ix.x = 0.f; iy.x = 0.f; dx.x = 0.f; dy.x = 0.f; }
-                    else { ix.y = 0.f; iy.y = 0.f; dx.y = 0.f; dy.y = 0.f; }
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int gx = r360_reflect101_clamped(gx0 + k, cols);
+                const size_t i = (size_t)gy * cols + gx;
+                g[k] = r360_gray_u8(c8[3 * i], c8[3 * i + 1], c8[3 * i + 2]);
+                d[k] = depth_mm ? (float)depth_mm[(size_t)f * n_px + i] * ds : depth_m[(size_t)f * n_px + i];
             }
         }
-        o[3 * (size_t)q + 0] = make_float4(v.y, v.x, ix.x, iy.x);
-        o[3 * (size_t)q + 1] = make_float4(dx.x, dy.x, v.w, v.z);
-        o[3 * (size_t)q + 2] = make_float4(ix.y, iy.y, dx.y, dy.y);
+        float4* o = reinterpret_cast<float4*>(&s_dg[sy][4 * gq]);
+        o[0] = make_float4(d[0], g[0], d[1], g[1]);
+        o[1] = make_float4(d[2], g[2], d[3], g[3]);
+    }
+    __syncthreads();
+
+    // ---- phase 2: level-0 outputs, one pixel pair per step (pair p of row ly: columns tx0 + 2p, + 1)
+    float2* __restrict__ l0 = l0_dst[f];
+    float4* __restrict__ tex = reinterpret_cast<float4*>(texel_dst[f]);
+    for (int q = threadIdx.x; q < (R360_F0_TW / 2) * R360_F0_TH; q += 256) {
+        const int ly = q / (R360_F0_TW / 2), lp = q - ly * (R360_F0_TW / 2);
+        const int r = ty0 + ly, c = tx0 + 2 * lp;
+        if (r >= rows || c >= cols) continue;                                   // cols is even: the pair is inside or outside
+        const int sy = ly + 2, sx = 2 * lp + 4;
+        const float4 v = *reinterpret_cast<const float4*>(&s_dg[sy][sx]);       // {d0, g0, d1, g1}
+        const size_t pi = ((size_t)r * cols + c) >> 1;                          // pixel-pair index
+        if (l0) reinterpret_cast<float4*>(l0)[pi] = v;
+        if (tex) {
+            const float4 u = *reinterpret_cast<const float4*>(&s_dg[sy - 1][sx]);
+            const float4 d = *reinterpret_cast<const float4*>(&s_dg[sy + 1][sx]);
+            float4 t[3];
+            r360_texel_pair(v, u, d, s_dg[sy][sx - 1], s_dg[sy][sx + 2], r, c, rows, cols, mg, t);
+            tex[3 * pi + 0] = t[0];
+            tex[3 * pi + 1] = t[1];
+            tex[3 * pi + 2] = t[2];
+        }
+    }
+
+    // ---- phase 3: level 1.  Horizontal 5-tap of every staged row (k_down's r360_down_hrow), then the
+    //      vertical combination and the depth valid-mean.
+    for (int q = threadIdx.x; q < (R360_F0_TW / 2) * R360_F0_SH; q += 256) {
+        const int sy = q / (R360_F0_TW / 2), ox = q - sy * (R360_F0_TW / 2);
+        const float2* row = &s_dg[sy][2 * ox + 2];                              // global columns 2x-2 .. 2x+2
+        const float c0 = row[0].y, c1 = row[1].y, c2 = row[2].y, c3 = row[3].y, c4 = row[4].y;
+        s_h[sy][ox] = c2 * 6 + (c1 + c3) * 4 + c0 + c4;
+    }
+    __syncthreads();
+    float2* __restrict__ l1 = l1_dst[f] ;
+    const int h1 = rows >> 1, w1 = cols >> 1;
+    for (int q = threadIdx.x; q < (R360_F0_TW / 2) * (R360_F0_TH / 2); q += 256) {
+        const int oy = q / (R360_F0_TW / 2), ox = q - oy * (R360_F0_TW / 2);
+        const int y = (ty0 >> 1) + oy, x = (tx0 >> 1) + ox;
+        if (y >= h1 || x >= w1) continue;
+        const float hm2 = s_h[2 * oy][ox], hm1 = s_h[2 * oy + 1][ox], r0 = s_h[2 * oy + 2][ox],
+                    r1 = s_h[2 * oy + 3][ox], r2 = s_h[2 * oy + 4][ox];
+        const float a = (hm2 + r2) + (r0 + r0);
+        const float b = ((hm1 + r1) + r0) * 4.0f;
+        const float gray = (a + b) * (1.f / 256);
+        const float4 p0 = *reinterpret_cast<const float4*>(&s_dg[2 * oy + 2][2 * ox + 4]);   // row 2y:   {dl, g, dr, g}
+        const float4 p1 = *reinterpret_cast<const float4*>(&s_dg[2 * oy + 3][2 * ox + 4]);   // row 2y+1
+        float av = 0.f;
+        unsigned cnt = 0;
+        if (p0.x > min_d && p0.x < max_d) { av += p0.x; ++cnt; }
+        if (p0.z > min_d && p0.z < max_d) { av += p0.z; ++cnt; }
+        if (p1.x > min_d && p1.x < max_d) { av += p1.x; ++cnt; }
+        if (p1.z > min_d && p1.z < max_d) { av += p1.z; ++cnt; }
+        const float depth = cnt > 0 ? av / cnt : 0.f;
+        l1[(size_t)y * w1 + x] = make_float2(depth, gray);
     }
 }
 
@@ -798,7 +964,15 @@ void r360_launch_down(cudaStream_t st, float2* const* pyr, long long off_src, lo
 void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, long long off, int rows, int cols,
                        int n_sensors, int n_frames, int sm_count) {
     dim3 grid(r360_blocks((long long)rows * cols / 2, 256, sm_count * 8), n_frames);
-    k_texel<<<grid, 256, 0, st>>>(pyr, trg, off, rows, cols, n_sensors);
+    k_texel<<<grid, 256, 0, st>>>(pyr, trg, off, rows, cols, r360_mask_geom(cols, n_sensors));
+}
+void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* depth_mm, const float* depth_m,
+                          float2* const* l0_dst, float2* const* l1_dst, float* const* texel_dst, int rows, int cols,
+                          float min_d, float max_d, int n_sensors, int n_frames) {
+    const int tiles_x = (cols + R360_F0_TW - 1) / R360_F0_TW, tiles_y = (rows + R360_F0_TH - 1) / R360_F0_TH;
+    dim3 grid(tiles_x * tiles_y, n_frames);
+    k_pyr_head<<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, l0_dst, l1_dst, texel_dst, rows, cols, tiles_x, min_d, max_d,
+                                    r360_mask_geom(cols, n_sensors));
 }
 // The pass kernel's pipeline slots need more than the 48 KB default of dynamic shared memory.
 cudaError_t r360_pass_init() {

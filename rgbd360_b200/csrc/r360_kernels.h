@@ -54,6 +54,10 @@ void r360_launch_down(cudaStream_t st, float2* const* pyr, long long off_src, lo
                       int cols, float min_d, float max_d, int n_frames, int sm_count);
 void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, long long off, int rows, int cols,
                        int n_sensors, int n_frames, int sm_count);
+// fused level 0 + level-0 texels + level 1; l0_dst[f] / texel_dst[f] may be null (role), l1_dst[f] points at level 1
+void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* depth_mm, const float* depth_m,
+                          float2* const* l0_dst, float2* const* l1_dst, float* const* texel_dst, int rows, int cols,
+                          float min_d, float max_d, int n_sensors, int n_frames);
 cudaError_t r360_pass_init();
 void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid);
 // occlusion variants (r360_occ.cu): head / next / dinv hold n_pairs * lv.n entries each
