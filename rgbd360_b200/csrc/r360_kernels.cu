@@ -249,7 +249,12 @@ k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long lo
 //   gradients need 1), staged as {depth, gray}; x is padded to groups of 4 pixels so that the raw
 //   loads are the 12-byte RGB / 8-byte depth vectors of k_level0.
 #define R360_F0_TW 64
-#define R360_F0_TH 32
+#ifndef R360_F0_TH
+#define R360_F0_TH 64
+#endif
+#ifndef R360_F0_MINB
+#define R360_F0_MINB 4                         // resident CTAs per SM the register allocation aims at
+#endif
 #define R360_F0_SW (R360_F0_TW + 8)            // smem columns: global x = tx0 - 4 + sx
 #define R360_F0_SH (R360_F0_TH + 4)            // smem rows:    global y = ty0 - 2 + sy
 __device__ __forceinline__ int r360_reflect101_clamped(int i, int n) {
@@ -260,7 +265,8 @@ __device__ __forceinline__ float r360_gray_u8(unsigned r, unsigned g, unsigned b
     const int v = (int)(r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15;
     return (float)v * (float)(1. / 255);
 }
-__global__ void __launch_bounds__(256)
+template <bool F32DEPTH>
+__global__ void __launch_bounds__(256, R360_F0_MINB)
 k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_mm, const float* __restrict__ depth_m,
            float2* const* __restrict__ l0_dst, float2* const* __restrict__ l1_dst, float* const* __restrict__ texel_dst,
            int rows, int cols, int tiles_x, float min_d, float max_d, R360MaskGeom mg) {
@@ -272,36 +278,58 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
     const uint8_t* __restrict__ c8 = rgb + (size_t)f * n_px * 3;
     const float ds = (float)0.001;
 
-    // ---- phase 1: raw input -> {depth, gray} of the tile + halo, 4 pixels per step
-    constexpr int GROUPS = R360_F0_SW / 4;
-    for (int q = threadIdx.x; q < GROUPS * R360_F0_SH; q += 256) {
+    // ---- phase 1: raw input -> {depth, gray} of the tile + halo, 4 pixels per step.  All raw loads of the
+    //      thread are issued first (registers), then converted: the HBM latency is paid once per tile,
+    //      not once per group.
+    constexpr int GROUPS = R360_F0_SW / 4, N_GROUPS = GROUPS * R360_F0_SH, NIT = (N_GROUPS + 255) / 256;
+    uint32_t w0[NIT], w1[NIT], w2[NIT];
+    uint32_t dw[NIT][F32DEPTH ? 4 : 2];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+        const int q = threadIdx.x + 256 * k;
         const int sy = q / GROUPS, gq = q - sy * GROUPS;
         const int gy = r360_reflect101_clamped(ty0 - 2 + sy, rows);
         const int gx0 = tx0 - 4 + 4 * gq;
-        float d[4], g[4];
-        if (gx0 >= 0 && gx0 + 3 < cols) {
+        if (q < N_GROUPS && gx0 >= 0 && gx0 + 3 < cols) {
             const size_t i0 = (size_t)gy * cols + gx0;                         // multiple of 4
             const uint32_t* c4 = reinterpret_cast<const uint32_t*>(c8 + 3 * i0);
-            const uint32_t w0 = __ldg(c4), w1 = __ldg(c4 + 1), w2 = __ldg(c4 + 2);
-            g[0] = r360_gray_u8(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
-            g[1] = r360_gray_u8(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
-            g[2] = r360_gray_u8((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
-            g[3] = r360_gray_u8((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
-            if (depth_mm) {
-                const uint2 dd = __ldg(reinterpret_cast<const uint2*>(depth_mm + (size_t)f * n_px + i0));
-                d[0] = (float)(dd.x & 0xffffu) * ds; d[1] = (float)(dd.x >> 16) * ds;
-                d[2] = (float)(dd.y & 0xffffu) * ds; d[3] = (float)(dd.y >> 16) * ds;
+            w0[k] = __ldg(c4); w1[k] = __ldg(c4 + 1); w2[k] = __ldg(c4 + 2);
+            if (F32DEPTH) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(depth_m + (size_t)f * n_px + i0));
+                dw[k][0] = t.x; dw[k][1] = t.y; dw[k][F32DEPTH ? 2 : 0] = t.z; dw[k][F32DEPTH ? 3 : 1] = t.w;
             } else {
-                const float4 dd = __ldg(reinterpret_cast<const float4*>(depth_m + (size_t)f * n_px + i0));
-                d[0] = dd.x; d[1] = dd.y; d[2] = dd.z; d[3] = dd.w;
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(depth_mm + (size_t)f * n_px + i0));
+                dw[k][0] = t.x; dw[k][1] = t.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+        const int q = threadIdx.x + 256 * k;
+        if (q >= N_GROUPS) continue;
+        const int sy = q / GROUPS, gq = q - sy * GROUPS;
+        const int gx0 = tx0 - 4 + 4 * gq;
+        float d[4], g[4];
+        if (gx0 >= 0 && gx0 + 3 < cols) {
+            g[0] = r360_gray_u8(w0[k] & 0xffu, (w0[k] >> 8) & 0xffu, (w0[k] >> 16) & 0xffu);
+            g[1] = r360_gray_u8(w0[k] >> 24, w1[k] & 0xffu, (w1[k] >> 8) & 0xffu);
+            g[2] = r360_gray_u8((w1[k] >> 16) & 0xffu, w1[k] >> 24, w2[k] & 0xffu);
+            g[3] = r360_gray_u8((w2[k] >> 8) & 0xffu, (w2[k] >> 16) & 0xffu, w2[k] >> 24);
+            if (F32DEPTH) {
+                d[0] = __uint_as_float(dw[k][0]); d[1] = __uint_as_float(dw[k][1]);
+                d[2] = __uint_as_float(dw[k][F32DEPTH ? 2 : 0]); d[3] = __uint_as_float(dw[k][F32DEPTH ? 3 : 1]);
+            } else {
+                d[0] = (float)(dw[k][0] & 0xffffu) * ds; d[1] = (float)(dw[k][0] >> 16) * ds;
+                d[2] = (float)(dw[k][1] & 0xffffu) * ds; d[3] = (float)(dw[k][1] >> 16) * ds;
             }
         } else {                                                               // image border columns: REFLECT_101
+            const int gy = r360_reflect101_clamped(ty0 - 2 + sy, rows);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int gx = r360_reflect101_clamped(gx0 + k, cols);
+            for (int j = 0; j < 4; ++j) {
+                const int gx = r360_reflect101_clamped(gx0 + j, cols);
                 const size_t i = (size_t)gy * cols + gx;
-                g[k] = r360_gray_u8(c8[3 * i], c8[3 * i + 1], c8[3 * i + 2]);
-                d[k] = depth_mm ? (float)depth_mm[(size_t)f * n_px + i] * ds : depth_m[(size_t)f * n_px + i];
+                g[j] = r360_gray_u8(c8[3 * i], c8[3 * i + 1], c8[3 * i + 2]);
+                d[j] = F32DEPTH ? depth_m[(size_t)f * n_px + i] : (float)depth_mm[(size_t)f * n_px + i] * ds;
             }
         }
         float4* o = reinterpret_cast<float4*>(&s_dg[sy][4 * gq]);
@@ -342,11 +370,11 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
     }
     __syncthreads();
     float2* __restrict__ l1 = l1_dst[f] ;
-    const int h1 = rows >> 1, w1 = cols >> 1;
+    const int h1 = rows >> 1, wd1 = cols >> 1;
     for (int q = threadIdx.x; q < (R360_F0_TW / 2) * (R360_F0_TH / 2); q += 256) {
         const int oy = q / (R360_F0_TW / 2), ox = q - oy * (R360_F0_TW / 2);
         const int y = (ty0 >> 1) + oy, x = (tx0 >> 1) + ox;
-        if (y >= h1 || x >= w1) continue;
+        if (y >= h1 || x >= wd1) continue;
         const float hm2 = s_h[2 * oy][ox], hm1 = s_h[2 * oy + 1][ox], r0 = s_h[2 * oy + 2][ox],
                     r1 = s_h[2 * oy + 3][ox], r2 = s_h[2 * oy + 4][ox];
         const float a = (hm2 + r2) + (r0 + r0);
@@ -361,7 +389,7 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
         if (p1.x > min_d && p1.x < max_d) { av += p1.x; ++cnt; }
         if (p1.z > min_d && p1.z < max_d) { av += p1.z; ++cnt; }
         const float depth = cnt > 0 ? av / cnt : 0.f;
-        l1[(size_t)y * w1 + x] = make_float2(depth, gray);
+        l1[(size_t)y * wd1 + x] = make_float2(depth, gray);
     }
 }
 
@@ -971,8 +999,12 @@ void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* d
                           float min_d, float max_d, int n_sensors, int n_frames) {
     const int tiles_x = (cols + R360_F0_TW - 1) / R360_F0_TW, tiles_y = (rows + R360_F0_TH - 1) / R360_F0_TH;
     dim3 grid(tiles_x * tiles_y, n_frames);
-    k_pyr_head<<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, l0_dst, l1_dst, texel_dst, rows, cols, tiles_x, min_d, max_d,
-                                    r360_mask_geom(cols, n_sensors));
+    if (depth_mm)
+        k_pyr_head<false><<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, l0_dst, l1_dst, texel_dst, rows, cols, tiles_x, min_d,
+                                                max_d, r360_mask_geom(cols, n_sensors));
+    else
+        k_pyr_head<true><<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, l0_dst, l1_dst, texel_dst, rows, cols, tiles_x, min_d,
+                                               max_d, r360_mask_geom(cols, n_sensors));
 }
 // The pass kernel's pipeline slots need more than the 48 KB default of dynamic shared memory.
 cudaError_t r360_pass_init() {
