@@ -191,7 +191,7 @@ def run_ours(args):
     n_frames = 2 * n_pairs
     npx = rows * cols
 
-    params = r360.default_params(n_levels=L)
+    params = r360.default_params(n_levels=L, occlusion=args.occlusion)
     ctx = r360.Context(rows, cols, n_frames, n_pairs, params, device=local)
     # synthetic frames rendered on the device: pair j = (target frame 2j, source frame 2j+1),
     # frame ids offset per rank so every GPU registers different pairs (weak scaling)
@@ -296,6 +296,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": w["name"], "rows": rows, "cols": cols, "levels": L,
                        "pairs_per_gpu": n_pairs, "frames_per_gpu": n_frames, "method": "PHOTO_DEPTH",
+                       "occlusion": args.occlusion,
                        "sampling": "nearest-neighbour (reference semantics)",
                        "l2": "inputs larger than L2 (pyramids %.1f GB per GPU)" % (
                            (8 + 24) * ctx.rows * ctx.cols * sum(0.25 ** l for l in range(L)) * n_pairs / 1e9),
@@ -387,6 +388,9 @@ def main():
     ap.add_argument("--workload", default="A", choices=list(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--occlusion", type=int, default=0, choices=[0, 1, 2],
+                    help="alignFrames360's occlusion argument (side measurement; the headline metric is occlusion 0, "
+                         "whose fused pass the roofline object describes -- with 1 / 2 that object is empty)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
