@@ -140,6 +140,35 @@ def cpu_reference_run(w, n_pairs, first_pair=0):
     return n_pairs / dt, orc.omp_threads(), dt
 
 
+def compiled_reference_run(w, n_pairs=2):
+    """The reference's own RegisterPhotoICP.h as compiled here against the from-scratch Eigen / OpenCV / MRPT
+    stand-ins (oracle/_ref), all host threads, same call sequence.  Reported next to the port for
+    transparency: the stand-ins evaluate eagerly through heap temporaries and were written for fidelity, not
+    speed, so this figure understates what a real Eigen / OpenCV build of the reference would do."""
+    try:
+        from oracle import orc, refbind
+        if not refbind.available():
+            return None
+        n_thr = len(os.sched_getaffinity(0))
+        refbind.lib(False).ref_set_threads(n_thr)
+        dt = 0.0
+        for k in range(n_pairs):
+            ft = orc.synth_frame(0, 2 * k, w["rows"], w["cols"])
+            fs = orc.synth_frame(0, 2 * k + 1, w["rows"], w["cols"])
+            R = refbind.Reference(n_levels=w["levels"], pinned=False)
+            t0 = time.perf_counter()
+            R.set_target(*ft); R.set_source(*fs)
+            R.align(None, 2, 0)
+            dt += time.perf_counter() - t0
+            R.close()
+        refbind.lib(False).ref_set_threads(1)
+        return {"value": n_pairs / dt, "unit": UNIT, "cores": n_thr, "kind": "reference",
+                "sample": "%d pairs, oracle/_ref (reference header compiled against stand-in Eigen/OpenCV/MRPT: "
+                          "eager evaluation, heap temporaries -- a lower bound on the reference's CPU speed), %.1f s" % (n_pairs, dt)}
+    except Exception as e:                      # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -163,7 +192,8 @@ def run_reference(args):
                    "reference header compiled against third-party stand-ins (oracle/_ref, too slow to time fairly); "
                    "FAITHFUL accumulation, glibc math, OpenMP over all host threads"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} pairs per step x {args.steps} steps, frame build + alignFrames360"},
+                         "sample": f"{sample} pairs per step x {args.steps} steps, frame build + alignFrames360",
+                         "compiled_reference": compiled_reference_run(w)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -327,7 +357,8 @@ def run_ours(args):
             v, cores, dt = cpu_reference_run(w, n_cpu)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d pairs of the same workload (frame build + alignFrames360, "
-                                              "FAITHFUL accumulation, glibc math, OpenMP), %.1f s" % (n_cpu, dt)}
+                                              "FAITHFUL accumulation, glibc math, OpenMP), %.1f s" % (n_cpu, dt),
+                                    "compiled_reference": compiled_reference_run(w)}
         emit(line)
     ctx.close()
     if world > 1:

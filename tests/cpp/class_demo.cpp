@@ -37,7 +37,22 @@ int main() {
     double e = reg.errorPhotoICP_sphere(0, pose, RegisterPhotoICP::PHOTO_DEPTH);
     std::printf("rms at optimum = %g (final_error %g)\n", e, reg.result().final_error);
     r360_destroy(ctx);
-    const bool ok = dmax == 0.0 && terr < 2e-2 && std::fabs(e - reg.result().final_error) < 1e-6 * e;
+    // occlusion variants through the class surface (RPI.h:4519 third argument; RPI.h:3232, 3373, 3720, 3861)
+    bool occ_ok = true;
+    for (int occ = 1; occ <= 2; ++occ) {
+        reg.alignFrames360(RegisterPhotoICP::identity(), RegisterPhotoICP::PHOTO_DEPTH, occ);
+        auto po = reg.getOptimalPoseArray();
+        double to = 0; for (int k = 12; k < 15; ++k) to = std::fmax(to, std::fabs(T[k] - po[k]));
+        const double eo = occ == 1 ? reg.errorPhotoICP_sphereOcc1(0, po, RegisterPhotoICP::PHOTO_DEPTH)
+                                   : reg.errorPhotoICP_sphereOcc2(0, po, RegisterPhotoICP::PHOTO_DEPTH);
+        if (occ == 1) reg.calcHessGrad_sphereOcc1(0, po, RegisterPhotoICP::PHOTO_DEPTH);
+        else reg.calcHessGrad_sphereOcc2(0, po, RegisterPhotoICP::PHOTO_DEPTH);
+        std::printf("occlusion %d: |t - t_gt| = %g, error = %g (final_error %g), avPhoto %g avDepth %g, SSO %g\n", occ, to, eo,
+                    reg.result().final_error, reg.avPhotoResidual, reg.avDepthResidual, reg.SSO);
+        occ_ok = occ_ok && to < 2e-2 && std::fabs(eo - (reg.avPhotoResidual + reg.avDepthResidual)) < 1e-12 &&
+                 reg.SSO > 0.5f && reg.SSO <= 1.0f;
+    }
+    const bool ok = occ_ok && dmax == 0.0 && terr < 2e-2 && std::fabs(e - reg.result().final_error) < 1e-6 * e;
     std::printf(ok ? "OK\n" : "FAIL\n");
     return ok ? 0 : 1;
 }
