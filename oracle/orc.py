@@ -102,6 +102,13 @@ def lib():
         L.orc_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_int,
                                 C.POINTER(Result), C.c_void_p, C.c_int]
         L.orc_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_error_pinhole.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.orc_hessgrad_pinhole.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Params), C.c_void_p,
+                                           C.c_int] + [C.c_void_p] * 5
+        L.orc_align_pinhole.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int,
+                                        C.POINTER(Result), C.c_void_p, C.c_int]
+        L.orc_synth_pinhole_frame.argtypes = [C.c_int] * 4 + [C.c_float] * 4 + [C.c_void_p, C.c_void_p]
         L.orc_synth_gt_pose.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_stitch.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float] + [C.c_void_p] * 5
         L.orc_pinned_vec.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -228,6 +235,52 @@ def synth_frame(kind, fid, rows, cols):
     rgb = np.zeros((rows, cols, 3), np.uint8)
     d = np.zeros((rows, cols), np.uint16)
     lib().orc_synth_frame(kind, fid, rows, cols, _ptr(rgb), _ptr(d))
+    return rgb, d
+
+
+def pinhole_params(n_levels=4, method=PHOTO_DEPTH, std_photo=None):
+    """Defaults of the pinhole alignFrames (RPI.h:4304-4309): tol_residual 1e-4, no sensor-joint mask."""
+    p = default_params(n_levels=n_levels, method=method, std_photo=std_photo, n_sensors_mask=0)
+    p.tol_residual = 1e-4
+    p.reserved = 1
+    return p
+
+
+def _cam(cam):
+    return np.ascontiguousarray(cam, np.float32)
+
+
+def error_pinhole(src, trg, level, pose, params, cam):
+    r2 = np.zeros(2, np.float64); cnt = np.zeros(2, np.int32); e = C.c_double()
+    T = pose_arg(pose); K = _cam(cam)
+    lib().orc_error_pinhole(src.h, trg.h, level, _ptr(T), C.byref(params), _ptr(K), _ptr(r2), _ptr(cnt), C.byref(e))
+    return dict(photo=float(r2[0]), depth=float(r2[1]), n_photo=int(cnt[0]), n_depth=int(cnt[1]), error=e.value)
+
+
+def hessgrad_pinhole(src, trg, level, pose, params, cam, accum=ACC_STABLE):
+    H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+    Hd = np.zeros(21, np.float64); gd = np.zeros(6, np.float64); cnt = np.zeros(3, np.int32)
+    T = pose_arg(pose); K = _cam(cam)
+    lib().orc_hessgrad_pinhole(src.h, trg.h, level, _ptr(T), C.byref(params), _ptr(K), accum, _ptr(H), _ptr(g), _ptr(Hd),
+                               _ptr(gd), _ptr(cnt))
+    return dict(H=H.reshape(6, 6), g=g, Hd=Hd, gd=gd, n_visible=int(cnt[0]), n_photo=int(cnt[1]), n_depth=int(cnt[2]))
+
+
+def align_pinhole(src, trg, guess, params, cam, accum=ACC_STABLE, trace=False):
+    res = Result()
+    T = pose_arg(guess); K = _cam(cam)
+    cap = params.n_levels * (2 * params.max_iters + 2)
+    tr = (IterRecord * cap)() if trace else None
+    lib().orc_align_pinhole(src.h, trg.h, _ptr(T), C.byref(params), _ptr(K), accum, C.byref(res),
+                            C.cast(tr, C.c_void_p) if trace else None, cap if trace else 0)
+    return (res, tr) if trace else res
+
+
+def synth_pinhole_frame(kind, fid, rows, cols, fx, fy, ox, oy):
+    """Pinhole view of the synthetic room from the pose of frame `fid` (depth = z in mm)."""
+    rgb = np.zeros((rows, cols, 3), np.uint8)
+    d = np.zeros((rows, cols), np.uint16)
+    lib().orc_synth_pinhole_frame(kind, fid, rows, cols, fx, fy, ox, oy, _ptr(rgb), _ptr(d))
     return rgb, d
 
 

@@ -207,6 +207,48 @@ void ref_hessgrad(void* h, int level, const float* pose, int method, float* H, f
     for (int i = 0; i < 6; ++i) g[i] = gm.data()[i];
     *sso = r->SSO;
 }
+// ---- pinhole path: setCameraMatrix (RPI.h:254), alignFrames (RPI.h:4254),
+//      errorPhotoICP (RPI.h:560), calcHessGrad (RPI.h:776)
+void ref_set_camera(void* h, float fx, float fy, float ox, float oy) {
+    Eigen::Matrix3f K;
+    K << fx, 0, ox, 0, fy, oy, 0, 0, 1;
+    ((RegisterPhotoICP*)h)->setCameraMatrix(K);
+}
+// returns 1 when the reference reported "ILL-POSED"
+int ref_align_pinhole(void* h, const float* guess, int method, float* pose, float* H, float* g, int* iters) {
+    RegisterPhotoICP* r = (RegisterPhotoICP*)h;
+    std::string log;
+    {
+        Capture c;
+        r->alignFrames(to_mat4(guess), (RegisterPhotoICP::costFuncType)method, 0);
+        log = c.ss.str();
+    }
+    Eigen::Matrix4f P = r->getOptimalPose();
+    Eigen::Matrix<float, 6, 6> Hm = r->getHessian();
+    Eigen::Matrix<float, 6, 1> gm = r->getGradient();
+    for (int i = 0; i < 16; ++i) pose[i] = P.data()[i];
+    for (int i = 0; i < 36; ++i) H[i] = Hm.data()[i];
+    for (int i = 0; i < 6; ++i) g[i] = gm.data()[i];
+    for (int l = 0; l < r->nPyrLevels; ++l) iters[l] = r->num_iterations[l];
+    return log.find("ILL-POSED") != std::string::npos ? 1 : 0;
+}
+// errorPhotoICP at `level` (LUT caveat as ref_error): returns avResidual; av = {avPhotoResidual, avDepthResidual}
+double ref_error_pinhole(void* h, int level, const float* pose, int method, double* av) {
+    RegisterPhotoICP* r = (RegisterPhotoICP*)h;
+    Capture c;
+    double e = r->errorPhotoICP(level, to_mat4(pose), (RegisterPhotoICP::costFuncType)method);
+    if (av) { av[0] = r->avPhotoResidual; av[1] = r->avDepthResidual; }
+    return e;
+}
+void ref_hessgrad_pinhole(void* h, int level, const float* pose, int method, float* H, float* g) {
+    RegisterPhotoICP* r = (RegisterPhotoICP*)h;
+    Capture c;
+    r->calcHessGrad(level, to_mat4(pose), (RegisterPhotoICP::costFuncType)method);
+    Eigen::Matrix<float, 6, 6> Hm = r->getHessian();
+    Eigen::Matrix<float, 6, 1> gm = r->getGradient();
+    for (int i = 0; i < 36; ++i) H[i] = Hm.data()[i];
+    for (int i = 0; i < 6; ++i) g[i] = gm.data()[i];
+}
 // current LUT_xyz_sphere (private member, RPI.h:172): n points x 3 floats
 int ref_lut(void* h, float* xyz, int cap_points) {
     RegisterPhotoICP* r = (RegisterPhotoICP*)h;

@@ -48,6 +48,11 @@ def lib(pinned=False):
         L.ref_error_occ.restype = C.c_double
         L.ref_error_occ.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ref_hessgrad_occ.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.ref_set_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.ref_align_pinhole.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.ref_error_pinhole.restype = C.c_double
+        L.ref_error_pinhole.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_hessgrad_pinhole.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_lut.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _libs[pinned] = L
     return _libs[pinned]
@@ -131,6 +136,27 @@ class Reference:
         H = np.zeros(36, np.float32); g = np.zeros(6, np.float32); sso = C.c_float()
         self.L.ref_hessgrad_occ(self.h, level, _ptr(_pose_arg(pose)), method, occlusion, _ptr(H), _ptr(g), C.byref(sso))
         return H.reshape(6, 6).T.copy(), g, sso.value
+
+    # ---- pinhole path (RPI.h:254, 560, 776, 4254)
+    def set_camera(self, fx, fy, ox, oy):
+        self.L.ref_set_camera(self.h, fx, fy, ox, oy)
+
+    def align_pinhole(self, guess=None, method=2):
+        T = _pose_arg(guess)
+        pose = np.zeros(16, np.float32); H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+        iters = np.zeros(self.n_levels, np.int32)
+        ill = self.L.ref_align_pinhole(self.h, _ptr(T), method, _ptr(pose), _ptr(H), _ptr(g), _ptr(iters))
+        return dict(pose=pose.reshape(4, 4).T.copy(), H=H.reshape(6, 6).T.copy(), g=g, iters=iters, ill_posed=bool(ill))
+
+    def error_pinhole(self, level, pose, method=2):
+        av = np.zeros(2, np.float64)
+        e = self.L.ref_error_pinhole(self.h, level, _ptr(_pose_arg(pose)), method, _ptr(av))
+        return e, float(av[0]), float(av[1])
+
+    def hessgrad_pinhole(self, level, pose, method=2):
+        H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+        self.L.ref_hessgrad_pinhole(self.h, level, _ptr(_pose_arg(pose)), method, _ptr(H), _ptr(g))
+        return H.reshape(6, 6).T.copy(), g
 
     def lut(self):
         n = self.L.ref_lut(self.h, None, 0)

@@ -73,14 +73,7 @@ public:
             B = (1 - cos(th)) * (inv_th * inv_th);
         }
         r360_pseudo_exp_AB(vv, A, B, T);
-        if (!pseudo_exponential) {
-            // t = V u,  V = I + B [w]x + C [w]x^2,  C = (1 - A) / theta^2
-            const double C = th2 < 1e-8 ? 1.0 / 6.0 : (1 - A) / th2;
-            const double w[3] = { vv[3], vv[4], vv[5] }, u[3] = { vv[0], vv[1], vv[2] };
-            const double wu[3] = { w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0] };
-            const double wwu[3] = { w[1] * wu[2] - w[2] * wu[1], w[2] * wu[0] - w[0] * wu[2], w[0] * wu[1] - w[1] * wu[0] };
-            for (int i = 0; i < 3; ++i) T[12 + i] = u[i] + B * wu[i] + C * wwu[i];
-        }
+        if (!pseudo_exponential) r360_exp_translation(vv, A, B, th2, T);     // t = V u (gn_math.h)
         CPose3D p;
         for (int i = 0; i < 16; ++i) p.H.data()[i] = T[i];
         return p;

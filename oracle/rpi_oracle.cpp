@@ -671,6 +671,311 @@ void hessgrad_sphere_occ(const Frame* src, const Frame* trg, int level, const fl
     out->n_depth = nDepth;
 }
 
+// ------------------------------------------------------------------ f4: pinhole path
+// errorPhotoICP (RPI.h:560-775), calcHessGrad (RPI.h:776-1104) and alignFrames (RPI.h:4254-4512) with
+// occlusion = 0 and bUseSalientPixels = false (the default, RPI.h:205): the same pyramids as the spherical
+// path (no sensor-joint mask: that lives in alignFrames360), a pinhole projection with the camera matrix
+// of setCameraMatrix (RPI.h:254) scaled per level, and a Levenberg-Marquardt loop.  Differences from
+// the spherical functions that the restatement keeps: the ERROR applies no saliency test while the
+// HESSIAN does (and its depth-saliency `continue` drops the photo row too); both RMS terms divide by
+// nValidDepthPts (photo-only => 0/0 = NaN => the loop never runs); the sum is returned through the
+// FLOAT member avResidual; sigma_depth uses the transformed source z, not the target depth; H and g are
+// accumulated pixel by pixel in float under `omp critical` (order-dependent: pinned at one thread);
+// the full SE(3) exponential; lambda 0.01, step 10, tol_residual 1e-4, accept on diff_error > 0 and one
+// damped retry otherwise.
+struct PinK {
+    int rows, cols;
+    float fx, fy, ox, oy, inv_fx, inv_fy;
+};
+PinK pinhole_consts(const Frame* f, int level, const float* cam /* fx fy ox oy */) {
+    PinK k;
+    k.rows = f->rows >> level;
+    k.cols = f->cols >> level;
+    const float scaleFactor = 1.0 / pow(2, level);             // RPI.h:569
+    k.fx = cam[0] * scaleFactor; k.fy = cam[1] * scaleFactor;
+    k.ox = cam[2] * scaleFactor; k.oy = cam[3] * scaleFactor;
+    k.inv_fx = 1. / k.fx; k.inv_fy = 1. / k.fy;                // RPI.h:574-575 (double division, narrowed)
+    return k;
+}
+// LUT_xyz_sphere as alignFrames fills it (RPI.h:4275-4301)
+void build_lut_pinhole(const Frame* src, int level, const r360_params* P, const PinK& k, std::vector<float>& lut) {
+    lut.resize((size_t)3 * k.rows * k.cols);
+    const std::vector<float>& D = src->depth[level];
+    for (int r = 0; r < k.rows; ++r)
+        for (int c = 0; c < k.cols; ++c) {
+            const size_t i = (size_t)r * k.cols + c;
+            const float z = D[i];
+            lut[3 * i + 2] = z;
+            if (P->min_depth < z && z < P->max_depth) {
+                lut[3 * i + 0] = (c - k.ox) * z * k.inv_fx;
+                lut[3 * i + 1] = (r - k.oy) * z * k.inv_fy;
+            } else {
+                lut[3 * i + 0] = ORC_INVALID_POINT;
+            }
+        }
+}
+struct WarpedPin { float px, py, pz, inv_z; int r, c; };
+inline bool warp_point_pinhole(const float* T, const float* X, const PinK& k, WarpedPin& w) {
+    w.px = ((T[0] * X[0] + T[4] * X[1]) + T[8] * X[2]) + T[12];
+    w.py = ((T[1] * X[0] + T[5] * X[1]) + T[9] * X[2]) + T[13];
+    w.pz = ((T[2] * X[0] + T[6] * X[1]) + T[10] * X[2]) + T[14];
+    w.inv_z = 1.0 / w.pz;                                      // RPI.h:659: double division, narrowed to float
+    const float tc = (w.px * k.fx) * w.inv_z + k.ox;           // RPI.h:662
+    const float tr = (w.py * k.fy) * w.inv_z + k.oy;           // RPI.h:663
+    w.r = r360_round_to_int(tr);
+    w.c = r360_round_to_int(tc);
+    return (w.r >= 0 && w.r < k.rows) && (w.c >= 0 && w.c < k.cols);      // RPI.h:667-668
+}
+// errorPhotoICP: out = {PhotoResidual, DepthResidual, nValidPhotoPts, nValidDepthPts}; returns the value
+double error_pinhole(const Frame* src, const Frame* trg, int level, const float* T, const r360_params* P,
+                     const PinK& k, const std::vector<float>& lut, OccErr* out) {
+    const int N = k.rows * k.cols;
+    const float stdDevPhoto_inv = 1. / P->std_photo;            // RPI.h:578 (float)
+    const float* Is = src->gray[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Dt = trg->depth[level].data();
+    const int method = P->method;
+    double PhotoResidual = 0.0, DepthResidual = 0.0;
+    int nP = 0, nD = 0;
+    for (int i = 0; i < N; ++i) {
+        if (lut[3 * (size_t)i] == ORC_INVALID_POINT) continue;
+        WarpedPin w;
+        if (!warp_point_pinhole(T, &lut[3 * (size_t)i], k, w)) continue;
+        const size_t j = (size_t)w.r * k.cols + w.c;
+        if (method == R360_PHOTO_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            const float photoDiff = It[j] - Is[i];
+            const float weight_photo = r360_huber(photoDiff, P->std_photo) * stdDevPhoto_inv;
+            const float werr = weight_photo * photoDiff;
+            PhotoResidual += werr * werr;
+            ++nP;
+        }
+        if (method == R360_DEPTH_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            const float depth2 = Dt[j];
+            if (std::isfinite(depth2)) {
+                const float depth1 = w.pz;
+                const float depthDiff = depth2 - depth1;
+                const float sd = P->std_depth * depth1;          // RPI.h:694: the transformed SOURCE depth
+                const float weight_depth = r360_huber(depthDiff, sd) / sd;
+                const float werr = weight_depth * depthDiff;
+                DepthResidual += werr * werr;
+                ++nD;
+            }
+        }
+    }
+    out->photo = PhotoResidual; out->depth = DepthResidual; out->n_photo = nP; out->n_depth = nD;
+    const double avP = sqrt(PhotoResidual / nD), avD = sqrt(DepthResidual / nD);      // RPI.h:768-769
+    const float avResidual = avP + avD;                          // float member, RPI.h:183, 770
+    return avResidual;
+}
+void hessgrad_pinhole(const Frame* src, const Frame* trg, int level, const float* T, const r360_params* P,
+                      const PinK& k, const std::vector<float>& lut, int accum_mode, HessOut* out) {
+    const int N = k.rows * k.cols;
+    const float stdDevPhoto_inv = 1. / P->std_photo;
+    const float* Is = src->gray[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Dt = trg->depth[level].data();
+    const float* Ix = trg->ggx[level].data();
+    const float* Iy = trg->ggy[level].data();
+    const float* Dx = trg->dgx[level].data();
+    const float* Dy = trg->dgy[level].data();
+    const int method = P->method;
+    float Hf[36], gf[6];
+    double Hd[36], gd[6];
+    for (int q = 0; q < 36; ++q) { Hf[q] = 0.f; Hd[q] = 0.0; }
+    for (int q = 0; q < 6; ++q) { gf[q] = 0.f; gd[q] = 0.0; }
+    int nVisible = 0, nPhoto = 0, nDepth = 0;
+    for (int i = 0; i < N; ++i) {
+        if (lut[3 * (size_t)i] == ORC_INVALID_POINT) continue;
+        WarpedPin w;
+        if (!warp_point_pinhole(T, &lut[3 * (size_t)i], k, w)) continue;
+        ++nVisible;
+        const size_t j = (size_t)w.r * k.cols + w.c;
+        const float x = w.px, y = w.py, iz = w.inv_z;
+        float J0[6], J1[6];                                      // jacobianWarpRt rows, RPI.h:970-984
+        J0[0] = k.fx * iz; J1[0] = 0;
+        J0[1] = 0; J1[1] = k.fy * iz;
+        const float iz2 = iz * iz;
+        J0[2] = -k.fx * x * iz2;
+        J1[2] = -k.fy * y * iz2;
+        J0[3] = -k.fx * y * x * iz2;
+        J1[3] = -k.fy * (1 + y * y * iz2);
+        J0[4] = k.fx * (1 + x * x * iz2);
+        J1[4] = k.fy * x * y * iz2;
+        J0[5] = -k.fx * y * iz;
+        J1[5] = k.fy * x * iz;
+        float Jp[6], Jd[6], rp = 0.f, rd = 0.f;
+        bool have_depth = false;
+        if (method == R360_PHOTO_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            if (fabsf(Ix[j]) < P->thres_sal_int && fabsf(Iy[j]) < P->thres_sal_int) continue;
+            const float photoDiff = It[j] - Is[i];
+            const float weight_photo = r360_huber(photoDiff, P->std_photo) * stdDevPhoto_inv;
+            rp = weight_photo * photoDiff;
+            const float a = weight_photo * Ix[j], b = weight_photo * Iy[j];
+            for (int q = 0; q < 6; ++q) Jp[q] = a * J0[q] + b * J1[q];
+        }
+        if (method == R360_DEPTH_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+            if (fabsf(Dx[j]) < P->thres_sal_depth && fabsf(Dy[j]) < P->thres_sal_depth) continue;   // drops the photo row too
+            const float depth2 = Dt[j];
+            if (std::isfinite(depth2)) {
+                const float depthDiff = depth2 - w.pz;
+                const float sd = P->std_depth * w.pz;
+                const float weight_depth = r360_huber(depthDiff, sd) / sd;
+                rd = weight_depth * depthDiff;
+                const float Rz[6] = { 0, 0, 1, y, -x, 0 };      // jacobianRt_z, RPI.h:1053
+                for (int q = 0; q < 6; ++q) Jd[q] = weight_depth * ((Dx[j] * J0[q] + Dy[j] * J1[q]) - Rz[q]);
+                have_depth = true;
+            }
+        }
+        // hessian += J^T J; gradient += J^T r  (Eigen, float, every pixel in turn: RPI.h:1065-1083)
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool on = pass == 0 ? (method != R360_DEPTH_CONSISTENCY) : (method != R360_PHOTO_CONSISTENCY && have_depth);
+            if (!on) continue;
+            const float* J = pass == 0 ? Jp : Jd;
+            const float r = pass == 0 ? rp : rd;
+            if (pass == 0) ++nPhoto; else ++nDepth;
+            for (int a = 0; a < 6; ++a) {
+                for (int b = 0; b < 6; ++b) { const float pr = J[a] * J[b]; Hf[a + 6 * b] += pr; Hd[a + 6 * b] += pr; }
+                const float pr = J[a] * r; gf[a] += pr; gd[a] += pr;
+            }
+        }
+    }
+    int q = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++q) out->Hd[q] = accum_mode == 0 ? (double)Hf[a + 6 * b] : Hd[a + 6 * b];
+    for (int a = 0; a < 36; ++a) out->H[a] = accum_mode == 0 ? Hf[a] : (float)Hd[a];
+    for (int a = 0; a < 6; ++a) { out->gd[a] = accum_mode == 0 ? (double)gf[a] : gd[a]; out->g[a] = accum_mode == 0 ? gf[a] : (float)gd[a]; }
+    out->n_visible = nVisible; out->n_photo = nPhoto; out->n_depth = nDepth;
+}
+
+template <class M>
+int align_pinhole(const Frame* src, const Frame* trg, const float* guess, const r360_params* P, const float* cam,
+                  int accum_mode, r360_result* out, r360_iter_record* trace, int trace_cap) {
+    memset(out, 0, sizeof(*out));
+    const int L = P->n_levels;
+    const int per_level = 2 * P->max_iters + 2;
+    float pose_estim[16], pose_tmp[16];
+    memcpy(pose_estim, guess, sizeof(pose_estim));
+    HessOut ho;
+    memset(&ho, 0, sizeof(ho));
+    bool have_hess = false, ill_posed = false;
+    std::vector<float> lut;
+    double error = 0.0;
+    OccErr oe_acc; memset(&oe_acc, 0, sizeof(oe_acc));
+    auto norm6 = [](const float* u) {
+        float a = u[0] * u[0] + (u[1] * u[1] + u[2] * u[2]);
+        float b = u[3] * u[3] + (u[4] * u[4] + u[5] * u[5]);
+        return sqrtf(a + b);
+    };
+    auto exp_mul = [&](const float* upd, float* dst) {           // CPose3D::exp(update) * pose_estim, RPI.h:4375
+        double ud[6], Td[16], A, B;
+        for (int a = 0; a < 6; ++a) ud[a] = (double)upd[a];
+        const double th2 = ud[3] * ud[3] + ud[4] * ud[4] + ud[5] * ud[5];
+        if (r360_rodrigues_small(th2, &A, &B)) {
+            const double th = sqrt(th2);
+            double sn, cs;
+            M::sincos_d(th, &sn, &cs);
+            const double inv_th = 1.0 / th;
+            A = sn * inv_th;
+            B = (1 - cs) * (inv_th * inv_th);
+        }
+        r360_pseudo_exp_AB(ud, A, B, Td);
+        r360_exp_translation(ud, A, B, th2, Td);
+        float Tf[16];
+        for (int a = 0; a < 16; ++a) Tf[a] = (float)Td[a];
+        r360_mat4_mul(Tf, pose_estim, dst);
+    };
+    for (int level = L - 1; level >= 0 && !ill_posed; --level) {
+        const PinK k = pinhole_consts(src, level, cam);
+        build_lut_pinhole(src, level, P, k, lut);
+        double lambda = 0.01;                                      // RPI.h:4304
+        const double step = 10;
+        int it = 0, ev = 0;
+        float upd[6] = { 1, 1, 1, 1, 1, 1 };
+        auto record = [&](const float* pose, const OccErr& oe, int accepted, int itv) {
+            if (!trace) return;
+            const int idx = level * per_level + ev;
+            if (ev < per_level && idx < trace_cap) {
+                r360_iter_record* r = &trace[idx];
+                memset(r, 0, sizeof(*r));
+                r->err2 = oe.photo; r->err2_depth = oe.depth; r->n_valid = oe.n_photo; r->n_valid_depth = oe.n_depth;
+                r->level = level; r->it = itv; r->accepted = accepted; r->used = 1; memcpy(r->pose, pose, 64);
+            }
+            ++ev;
+        };
+        OccErr oe;
+        error = error_pinhole(src, trg, level, pose_estim, P, k, lut, &oe);       // RPI.h:4312
+        oe_acc = oe;
+        out->passes[level] = 1;
+        record(pose_estim, oe, 1, 0);
+        double diff_error = error;
+        while (it < P->max_iters && norm6(upd) > P->tol_update && diff_error > P->tol_residual) {
+            hessgrad_pinhole(src, trg, level, pose_estim, P, k, lut, accum_mode, &ho);   // RPI.h:4340
+            have_hess = true;
+            ++out->passes[level];
+            float Hl[36];
+            const float lam = (float)lambda;
+            for (int q = 0; q < 36; ++q) Hl[q] = ho.H[q];
+            for (int a = 0; a < 6; ++a) Hl[a + 6 * a] = ho.H[a + 6 * a] + lam * ho.H[a + 6 * a];
+            if (r360_rank6(Hl) != 6) {                             // RPI.h:4360-4368
+                out->status = R360_PAIR_ILL_POSED;
+                ill_posed = true;
+                break;
+            }
+            float inv[36];
+            r360_inverse6(ho.H, inv);
+            r360_solve_update(inv, ho.g, upd);                      // RPI.h:4371
+            exp_mul(upd, pose_tmp);
+            OccErr noe;
+            double new_error = error_pinhole(src, trg, level, pose_tmp, P, k, lut, &noe);   // RPI.h:4378
+            ++out->passes[level];
+            diff_error = error - new_error;
+            if (diff_error > 0) {                                   // RPI.h:4390-4396
+                lambda /= step;
+                memcpy(pose_estim, pose_tmp, sizeof(pose_estim));
+                error = new_error; oe_acc = noe;
+                it = it + 1;
+                record(pose_tmp, noe, 1, it);
+            } else {
+                record(pose_tmp, noe, 0, it);
+                unsigned LM_it = 0;
+                while (LM_it < 1 && diff_error < 0) {               // RPI.h:4399-4424, LM_maxIters = 1
+                    lambda = lambda * step;
+                    const float lm = (float)lambda;
+                    float Hd2[36];
+                    for (int q = 0; q < 36; ++q) Hd2[q] = ho.H[q];
+                    for (int a = 0; a < 6; ++a) Hd2[a + 6 * a] = ho.H[a + 6 * a] + lm * ho.H[a + 6 * a];
+                    r360_inverse6(Hd2, inv);
+                    r360_solve_update(inv, ho.g, upd);
+                    exp_mul(upd, pose_tmp);
+                    new_error = error_pinhole(src, trg, level, pose_tmp, P, k, lut, &noe);
+                    ++out->passes[level];
+                    diff_error = error - new_error;
+                    if (diff_error > 0) {
+                        memcpy(pose_estim, pose_tmp, sizeof(pose_estim));
+                        error = new_error; oe_acc = noe;
+                        it = it + 1;
+                        record(pose_tmp, noe, 1, it);
+                    } else {
+                        LM_it = LM_it + 1;
+                        record(pose_tmp, noe, 0, it);
+                    }
+                }
+            }
+        }
+        if (!ill_posed) out->iters[level] = it;
+    }
+    memcpy(out->pose, pose_estim, sizeof(pose_estim));
+    if (have_hess) {
+        memcpy(out->hessian, ho.H, sizeof(ho.H));
+        memcpy(out->gradient, ho.g, sizeof(ho.g));
+        out->n_visible = ho.n_visible;
+    }
+    out->final_error = error;
+    out->final_err2 = oe_acc.photo + oe_acc.depth;
+    out->final_n_valid = oe_acc.n_depth;
+    return 0;
+}
+
 // ------------------------------------------------------------------ a10 alignFrames360
 template <class M>
 int align360(const Frame* src, const Frame* trg, const float* guess, const r360_params* P,
@@ -986,6 +1291,41 @@ int orc_align(void* srcv, void* trgv, const float* guess, const r360_params* P, 
     return rc;
 }
 
+// ---- pinhole path: cam = {fx, fy, ox, oy} of setCameraMatrix (level 0)
+int orc_error_pinhole(void* srcv, void* trgv, int level, const float* pose, const r360_params* P, const float* cam,
+                      double* res2, int* counts, double* error) {
+    const PinK k = pinhole_consts((Frame*)srcv, level, cam);
+    std::vector<float> lut;
+    build_lut_pinhole((Frame*)srcv, level, P, k, lut);
+    OccErr oe;
+    const double e = error_pinhole((Frame*)srcv, (Frame*)trgv, level, pose, P, k, lut, &oe);
+    if (res2) { res2[0] = oe.photo; res2[1] = oe.depth; }
+    if (counts) { counts[0] = oe.n_photo; counts[1] = oe.n_depth; }
+    if (error) *error = e;
+    return 0;
+}
+int orc_hessgrad_pinhole(void* srcv, void* trgv, int level, const float* pose, const r360_params* P, const float* cam,
+                         int accum_mode, float* H, float* g, double* Hd, double* gd, int* counts) {
+    const PinK k = pinhole_consts((Frame*)srcv, level, cam);
+    std::vector<float> lut;
+    build_lut_pinhole((Frame*)srcv, level, P, k, lut);
+    HessOut ho;
+    hessgrad_pinhole((Frame*)srcv, (Frame*)trgv, level, pose, P, k, lut, accum_mode, &ho);
+    if (H) memcpy(H, ho.H, sizeof(ho.H));
+    if (g) memcpy(g, ho.g, sizeof(ho.g));
+    if (Hd) memcpy(Hd, ho.Hd, sizeof(ho.Hd));
+    if (gd) memcpy(gd, ho.gd, sizeof(ho.gd));
+    if (counts) { counts[0] = ho.n_visible; counts[1] = ho.n_photo; counts[2] = ho.n_depth; }
+    return 0;
+}
+int orc_align_pinhole(void* srcv, void* trgv, const float* guess, const r360_params* P, const float* cam, int accum_mode,
+                      r360_result* out, r360_iter_record* trace, int trace_cap) {
+    float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    const float* g0 = guess ? guess : ident;
+    if (g_math_mode) return align_pinhole<MathLibm>((Frame*)srcv, (Frame*)trgv, g0, P, cam, accum_mode, out, trace, trace_cap);
+    return align_pinhole<MathPinned>((Frame*)srcv, (Frame*)trgv, g0, P, cam, accum_mode, out, trace, trace_cap);
+}
+
 // Synthetic frame (host render of rgbd360_b200/csrc/synth.h).
 void orc_synth_frame(int kind, int id, int rows, int cols, uint8_t* rgb, uint16_t* depth_mm) {
     double Rd[9], td[3];
@@ -1011,6 +1351,31 @@ void orc_synth_frame(int kind, int id, int rows, int cols, uint8_t* rgb, uint16_
     }
 }
 void orc_synth_gt_pose(int kind, int src_id, int trg_id, double* T) { r360_synth_relpose(kind, src_id, trg_id, T); }
+
+// Pinhole view of the same synthetic room (test data of the pinhole path): pixel (r, c)
+// looks along ((c - ox) / fx, (r - oy) / fy, 1) in the camera frame of frame `id`; depth_mm is the z-depth.
+void orc_synth_pinhole_frame(int kind, int id, int rows, int cols, float fx, float fy, float ox, float oy,
+                             uint8_t* rgb, uint16_t* depth_mm) {
+    double Rd[9], td[3];
+    r360_synth_pose(kind, id, Rd, td);
+    float R[9], t[3];
+    for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
+    for (int i = 0; i < 3; ++i) t[i] = (float)td[i];
+#pragma omp parallel for
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const double x = (c - ox) / fx, y = (r - oy) / fy;
+            const double n = sqrt(x * x + y * y + 1.0);
+            const double dx = x / n, dy = y / n, dz = 1.0 / n;
+            // r360_synth_pixel's ray is (sphi, -cphi sth, -cphi cth)
+            const double cphi = sqrt(dy * dy + dz * dz);
+            uint8_t g; uint16_t range_mm;
+            r360_synth_pixel(R, t, (float)dx, (float)cphi, (float)(-dy / cphi), (float)(-dz / cphi), &g, &range_mm);
+            const size_t i = (size_t)r * cols + c;
+            rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = g;
+            depth_mm[i] = (uint16_t)lround((double)range_mm * dz);
+        }
+}
 
 void orc_stitch(int size_h, int size_w, float fx, float fy, float cx, float cy, const float* Rt_inv,
                 const uint8_t* sensor_rgb, const uint16_t* sensor_depth, uint8_t* rgb, uint16_t* depth) {
@@ -1045,6 +1410,7 @@ int orc_rank6(const float* M) { return r360_rank6(M); }
 int orc_inverse6(const float* M, float* inv) { return r360_inverse6(M, inv); }
 void orc_solve_update(const float* inv, const float* g, float* upd) { r360_solve_update(inv, g, upd); }
 void orc_pseudo_exp(const double* v, double* T) { r360_pseudo_exp(v, T); }
+void orc_se3_exp(const double* v, double* T) { r360_se3_exp(v, T); }
 void orc_mat4_mul(const float* A, const float* B, float* C) { r360_mat4_mul(A, B, C); }
 int orc_omp_threads(void);
 }

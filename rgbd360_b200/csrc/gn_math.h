@@ -74,6 +74,31 @@ R360_HD void r360_pseudo_exp(const double v[6], double T[16]) {
     r360_pseudo_exp_AB(v, A, B, T);
 }
 
+// MRPT CPose3D::exp(v) with pseudo_exponential = false (what the pinhole alignFrames calls, RPI.h:4375):
+// the rotation of the pseudo-exponential and the translation t = V u, V = I + B [w]x + C [w]x^2,
+// C = (1 - A) / theta^2 (1/6 for tiny angles).  Overwrites the translation column of a pseudo-exp T.
+R360_HD void r360_exp_translation(const double v[6], double A, double B, double theta_sq, double T[16]) {
+    const double C = theta_sq < 1e-8 ? 1.0 / 6.0 : (1 - A) / theta_sq;
+    const double w[3] = { v[3], v[4], v[5] }, u[3] = { v[0], v[1], v[2] };
+    const double wu[3] = { w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0] };
+    const double wwu[3] = { w[1] * wu[2] - w[2] * wu[1], w[2] * wu[0] - w[0] * wu[2], w[0] * wu[1] - w[1] * wu[0] };
+    for (int i = 0; i < 3; ++i) T[12 + i] = u[i] + B * wu[i] + C * wwu[i];
+}
+R360_HD void r360_se3_exp(const double v[6], double T[16]) {
+    const double theta_sq = v[3] * v[3] + v[4] * v[4] + v[5] * v[5];
+    double A, B;
+    if (r360_rodrigues_small(theta_sq, &A, &B)) {
+        const double theta = sqrt(theta_sq);
+        double s, c;
+        r360_sincos(theta, &s, &c);
+        const double inv_theta = 1.0 / theta;
+        A = s * inv_theta;
+        B = (1 - c) * (inv_theta * inv_theta);
+    }
+    r360_pseudo_exp_AB(v, A, B, T);
+    r360_exp_translation(v, A, B, theta_sq, T);
+}
+
 // Partial-pivot LU inverse of a 6x6 float matrix (column-major, symmetric input so the
 // layout is immaterial).  Returns 0 when a pivot is exactly zero (inverse undefined).
 R360_HD int r360_inverse6(const float* Hin, float* inv) {

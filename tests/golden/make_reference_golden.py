@@ -4,6 +4,7 @@ outputs as tests/golden/reference_outputs.json.  Only runnable where /root/refer
 
     python tests/golden/make_reference_golden.py          # both recordings
     python tests/golden/make_reference_golden.py occ      # reference_occlusion.json only
+    python tests/golden/make_reference_golden.py pinhole  # reference_pinhole.json only
 """
 import hashlib
 import json
@@ -119,6 +120,43 @@ def main_occ():
         json.dump(gold, f, indent=0)
 
 
+# ---- the pinhole alignFrames / errorPhotoICP / calcHessGrad (RPI.h:4254, 560, 776).
+# H and g are accumulated pixel by pixel in float under `omp critical`: recorded with ONE thread.
+def run_reference_pinhole(case, pinned):
+    refbind.lib(pinned).ref_set_threads(1)
+    R = refbind.Reference(n_levels=case["levels"], pinned=pinned)
+    R.set_camera(*case["cam"])
+    R.set_source(case["rgb_s"], case["d_s"])
+    R.set_target(case["rgb_t"], case["d_t"])
+    a = R.align_pinhole(case["guess"], case["method"])
+    out = dict(pose=a["pose"].astype(np.float64).ravel().tolist(), H=a["H"].astype(np.float64).ravel().tolist(),
+               g=a["g"].astype(np.float64).tolist(), iters=a["iters"].tolist(), ill_posed=bool(a["ill_posed"]))
+    probes = []
+    if not a["ill_posed"]:           # after an ILL-POSED return the LUT is the one of the level where the run stopped
+        for T in refcases.probe_poses() + [a["pose"]]:
+            e, avp, avd = R.error_pinhole(0, T, case["method"])
+            H, g = R.hessgrad_pinhole(0, T, case["method"])
+            probes.append(dict(pose=np.asarray(T, np.float64).ravel().tolist(), error=_f(e), av_photo=_f(avp), av_depth=_f(avd),
+                               H=H.astype(np.float64).ravel().tolist(), g=g.astype(np.float64).tolist()))
+        if not any(a["iters"]) and not np.isfinite(probes[0]["error"] if probes[0]["error"] is not None else np.nan):
+            out["H"] = out["g"] = None   # the loop never ran: uninitialised members
+    out["probes_level0"] = probes
+    R.close()
+    return out
+
+
+def main_pinhole():
+    gold = {"_how": "oracle/_ref (reference header + refshim), OMP threads = 1, setCameraMatrix + alignFrames (pinhole) and "
+                    "errorPhotoICP / calcHessGrad called directly; see this script", "cases": {}}
+    for name in refcases.PINHOLE_CASES:
+        case = refcases.make_pinhole_case(orc, name)
+        gold["cases"][name] = {"libm": run_reference_pinhole(case, False), "pinned": run_reference_pinhole(case, True)}
+        c = gold["cases"][name]
+        print(name, "iters", c["libm"]["iters"], c["pinned"]["iters"], "ill", c["pinned"]["ill_posed"])
+    with open(os.path.join(HERE, "reference_pinhole.json"), "w") as f:
+        json.dump(gold, f, indent=0)
+
+
 def main():
     gold = {"_how": "oracle/_ref (reference header + refshim), OMP threads = 1; see this script", "cases": {}}
     for name in refcases.CASES:
@@ -133,6 +171,9 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "occ":
         main_occ()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pinhole":
+        main_pinhole()
     else:
         main()
         main_occ()
+        main_pinhole()

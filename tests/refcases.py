@@ -98,3 +98,30 @@ def make_case(orc, name):
 def probe_poses(n=3):
     """Level-0 probe poses for errorPhotoICP_sphere / calcHessGrad_sphere called directly."""
     return [np.eye(4, dtype=np.float32)] + [small_guess(100 + i) for i in range(n - 1)]
+
+
+# ---- pinhole path (SURVEY 8f row 4): QVGA sensor of the rig (Calib360.h:75-77), views of the synthetic room
+PINHOLE_CAM = (262.5, 262.5, 159.5, 119.5)          # fx, fy, ox, oy
+# name -> (scene kind, target frame id, source frame id, levels, method, guess)
+PINHOLE_CASES = {
+    "pin_odo_L4_pd": (0, 0, 1, 4, 2, None),
+    "pin_odo_L3_pd": (0, 4, 5, 3, 2, None),
+    "pin_loop_L4_pd_gt": (1, 3, 17, 4, 2, "gt"),
+    "pin_far_L4_pd_rejected": (0, 0, 9, 4, 2, None),          # every first step is rejected: the damped retry runs
+    "pin_odo_L3_depth_illposed": (0, 2, 3, 3, 1, None),        # depth-only on a flat wall: ILL-POSED at the coarsest level
+    "pin_odo_L3_photo_nan": (0, 2, 3, 3, 0, None),             # photo-only: 0/0 = NaN error, the loop never runs
+    "pin_loop_L4_pd_gt2": (1, 5, 9, 4, 2, "gt"),
+    "pin_odo_L3_pd_holes": (0, 6, 7, 3, 2, None, 7),           # invalid / out-of-range depth and colour patches
+}
+
+
+def make_pinhole_case(orc, name, rows=240, cols=320):
+    kind, a, b, levels, method, gm = PINHOLE_CASES[name][:6]
+    rgb_t, d_t = orc.synth_pinhole_frame(kind, a, rows, cols, *PINHOLE_CAM)
+    rgb_s, d_s = orc.synth_pinhole_frame(kind, b, rows, cols, *PINHOLE_CAM)
+    if len(PINHOLE_CASES[name]) > 6:
+        rgb_s, d_s, rgb_t, d_t = _holes(rgb_s, d_s, rgb_t, d_t, PINHOLE_CASES[name][6])
+    guess = None
+    if gm == "gt":
+        guess = (small_guess(99).astype(np.float64) @ orc.synth_gt_pose(kind, b, a)).astype(np.float32)
+    return dict(rgb_s=rgb_s, d_s=d_s, rgb_t=rgb_t, d_t=d_t, levels=levels, method=method, guess=guess, cam=PINHOLE_CAM)
