@@ -106,6 +106,31 @@ class RegisterPhotoICP {
         if (res_.status == R360_PAIR_ILL_POSED) avResidual = 0.f;           // RPI.h:4688
     }
 
+    // ---- pinhole registration: setCameraMatrix (RPI.h:254), alignFrames (RPI.h:4254-4512), errorPhotoICP
+    //      (RPI.h:560-775), calcHessGrad (RPI.h:776-1104).  occlusion must be 0 (the pinhole Occ variants are not built).
+    void setCameraMatrix(float fx, float fy, float ox, float oy) { cam_[0] = fx; cam_[1] = fy; cam_[2] = ox; cam_[3] = oy; have_cam_ = true; if (ctx_ && p_.projection == R360_PINHOLE) check(r360_set_camera(ctx_, fx, fy, ox, oy)); }
+    void alignFrames(const Pose& pose_guess = identity(), costFuncType method_ = PHOTO_CONSISTENCY, const int occlusion = 0) {
+        if (occlusion != 0) throw std::invalid_argument("RegisterPhotoICP: the pinhole occlusion variants (RPI.h:1107-2023) are not built");
+        if (!have_[0] || !have_[1]) throw std::logic_error("RegisterPhotoICP: setSourceFrame and setTargetFrame first");
+        ensure_method(method_, 0, R360_PINHOLE);
+        const int32_t s = 0, t = 1;
+        check(r360_register_pairs(ctx_, 1, &s, &t, pose_guess.data(), &res_, nullptr));
+    }
+    double errorPhotoICP(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
+        ensure_method(method_, 0, R360_PINHOLE);
+        double pr = 0, dr = 0, e = 0; int32_t np = 0, nd = 0;
+        check(r360_eval_error_pinhole(ctx_, 0, 1, pyramidLevel, poseGuess.data(), &pr, &dr, &np, &nd, &e));
+        avPhotoResidual = std::sqrt(pr / (double)nd);                       // RPI.h:768
+        avDepthResidual = std::sqrt(dr / (double)nd);
+        avResidual = (float)(avPhotoResidual + avDepthResidual);
+        return avResidual;
+    }
+    void calcHessGrad(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
+        ensure_method(method_, 0, R360_PINHOLE);
+        int32_t nvis = 0;
+        check(r360_eval_hessgrad(ctx_, 0, 1, pyramidLevel, poseGuess.data(), res_.hessian, res_.gradient, &nvis));
+    }
+
     /*! errorPhotoICP_sphere, RPI.h:2545-2739: sqrt(error2 / numValidPts). */
     double errorPhotoICP_sphere(const int& pyramidLevel, const Pose& poseGuess, costFuncType method_ = PHOTO_CONSISTENCY) {
         ensure_method(method_, 0);
@@ -151,7 +176,11 @@ class RegisterPhotoICP {
         Pose p; std::memcpy(p.data(), pose_guess.data(), sizeof(float) * 16);
         alignFrames360(p, method_, occlusion);
     }
-    void setCameraMatrix(Eigen::Matrix3f&) {}               // pinhole path only (RPI.h:254)
+    void setCameraMatrix(Eigen::Matrix3f& K) { setCameraMatrix(K(0, 0), K(1, 1), K(0, 2), K(1, 2)); }   // RPI.h:254
+    void alignFrames(const Eigen::Matrix4f pose_guess, costFuncType method_ = PHOTO_CONSISTENCY, const int occlusion = 0) {
+        Pose p; std::memcpy(p.data(), pose_guess.data(), sizeof(float) * 16);
+        alignFrames(p, method_, occlusion);
+    }
 #else
     Pose getOptimalPose() const { return getOptimalPoseArray(); }
     Mat6 getHessian() const { return getHessianArray(); }
@@ -187,6 +216,8 @@ class RegisterPhotoICP {
     r360_result res_;
     int device_, rows_ = 0, cols_ = 0;
     bool have_[2] = {false, false};
+    float cam_[4] = {0.f, 0.f, 0.f, 0.f};
+    bool have_cam_ = false;
     std::vector<uint8_t> rgb_[2], depth_[2];
     int depth_bytes_[2] = {0, 0};
 
@@ -206,15 +237,25 @@ class RegisterPhotoICP {
         p_.method = (int)method_or_default();
         if (r360_create(&ctx_, device_, rows, cols, 2, 1, &p_) != R360_OK)
             throw std::runtime_error(std::string("r360_create: ") + r360_last_error(nullptr));
+        if (p_.projection == R360_PINHOLE) {
+            if (!have_cam_) throw std::logic_error("RegisterPhotoICP: setCameraMatrix first (RPI.h:254)");
+            check(r360_set_camera(ctx_, cam_[0], cam_[1], cam_[2], cam_[3]));
+        }
         for (int s = 0; s < 2; ++s)
             if (have_[s] && rgb_[s].size() == (size_t)rows * cols * 3) upload(s, s == 0 ? R360_ROLE_SOURCE : R360_ROLE_TARGET);
     }
     int method_or_default() const { return p_.method; }
-    void ensure_method(costFuncType m, int occlusion = 0) {
+    void ensure_method(costFuncType m, int occlusion = 0, int projection = R360_SPHERE) {
         method = m;
-        if (p_.method == (int)m && p_.occlusion == occlusion && ctx_) return;
+        if (p_.method == (int)m && p_.occlusion == occlusion && p_.projection == projection && ctx_) return;
         p_.method = (int)m;
         p_.occlusion = occlusion;
+        if (p_.projection != projection) {
+            // the two registrations differ in the constants alignFrames / alignFrames360 hard-code
+            p_.projection = projection;
+            p_.tol_residual = projection == R360_PINHOLE ? 1e-4 : 1e-3;      // RPI.h:4308 / 4594
+            p_.n_sensors_mask = projection == R360_PINHOLE ? 0 : 8;          // RPI.h:4537 (alignFrames360 only)
+        }
         const int r = rows_, c = cols_;
         drop();
         ensure_ctx(r, c);

@@ -32,6 +32,9 @@ enum { R360_PHOTO_CONSISTENCY = 0, R360_DEPTH_CONSISTENCY = 1, R360_PHOTO_DEPTH 
 /* per-pair status (the reference prints "ILL-POSED" and returns, RPI.h:4682-4690) */
 enum { R360_PAIR_OK = 0, R360_PAIR_ILL_POSED = 1 };
 
+/* which registration of the class a context runs */
+enum { R360_SPHERE = 0, R360_PINHOLE = 1 };
+
 /* frame roles for r360_set_frames */
 enum { R360_ROLE_SOURCE = 1, R360_ROLE_TARGET = 2, R360_ROLE_BOTH = 3 };
 
@@ -55,7 +58,8 @@ typedef struct r360_params {
                                 z-buffer), with the reference's single-thread (source-order) semantics */
     int32_t n_sensors_mask;  /* 8: zero the 2-px sensor-joint gradient columns
                                 (RPI.h:4537-4549) when the target pyramid is built; 0: no mask */
-    int32_t reserved;
+    int32_t projection;      /* R360_SPHERE (alignFrames360 and friends) or R360_PINHOLE (alignFrames,
+                                errorPhotoICP, calcHessGrad: RPI.h:4254, 560, 776; needs r360_set_camera) */
 } r360_params;
 
 /* What the getters and public fields of the class expose after alignFrames360
@@ -93,14 +97,18 @@ typedef struct r360_iter_record {
     float   hessian[21];     /* upper triangle, row-major (h11,h12,..,h66)              */
     float   gradient[6];
     float   pad;
-    double  err2_depth;      /* occlusion 1/2: DepthResidual (RPI.h:3348, 3725), else 0 */
-    int32_t n_valid_depth;   /* occlusion 1/2: nValidDepthPts, else 0                   */
+    double  err2_depth;      /* occlusion 1/2 and pinhole: DepthResidual (RPI.h:3348, 3725, 563), else 0 */
+    int32_t n_valid_depth;   /* occlusion 1/2 and pinhole: nValidDepthPts, else 0       */
     int32_t reserved;
 } r360_iter_record;
 
 typedef struct r360_ctx r360_ctx;
 
 void r360_default_params(r360_params* p);
+/* The constants hard-coded in the pinhole alignFrames (RPI.h:4304-4309: lambda 0.01, step 10 -- fixed in the
+ * state machine -- and tol_residual 1e-4), projection = R360_PINHOLE, no sensor-joint mask (that mask lives
+ * in alignFrames360, RPI.h:4537). */
+void r360_default_params_pinhole(r360_params* p);
 const char* r360_last_error(const r360_ctx* ctx);   /* ctx may be NULL: last create error */
 
 /* Replaces constructing RegisterPhotoICP instances (RPI.h:201) for a whole batch:
@@ -154,6 +162,18 @@ int r360_eval_error_occ(r360_ctx* ctx, int src, int trg, int level, const float 
  * params.occlusion = 1 / 2: calcHessGrad_sphereOcc1 / Occ2 (RPI.h:3373-3716, 3861-4249). */
 int r360_eval_hessgrad(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
                        float H[36], float g[6], int32_t* n_visible);
+
+/* ---- pinhole registration, contexts created with projection = R360_PINHOLE ----
+ * setCameraMatrix (RPI.h:254): fx, fy, ox, oy of the level-0 images; the levels scale them by 2^-level
+ * (RPI.h:569-573).  r360_register_pairs then runs alignFrames(guess, method, occlusion = 0) (RPI.h:4254-4512:
+ * Levenberg-Marquardt with one damped retry, full SE(3) exponential); trace needs
+ * n_pairs * n_levels * (2 * max_iters + 2) records.  r360_eval_hessgrad = calcHessGrad (RPI.h:776). */
+int r360_set_camera(r360_ctx* ctx, float fx, float fy, float ox, float oy);
+/* errorPhotoICP(level, pose, method) (RPI.h:560-775): PhotoResidual, DepthResidual, nValidPhotoPts,
+ * nValidDepthPts and the returned avResidual = (float)(sqrt(Photo / nValidDepthPts) + sqrt(Depth / nValidDepthPts)). */
+int r360_eval_error_pinhole(r360_ctx* ctx, int src, int trg, int level, const float pose[16],
+                            double* photo_residual, double* depth_residual, int32_t* n_valid_photo,
+                            int32_t* n_valid_depth, double* error);
 
 /* Parity hooks (a1-a5 planes, warp index maps).  Any output pointer may be NULL. */
 int r360_dump_level(r360_ctx* ctx, int frame, int level, float* gray, float* depth,

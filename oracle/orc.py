@@ -23,7 +23,7 @@ class Params(C.Structure):
         ("std_photo", C.c_float), ("std_depth", C.c_float), ("thres_sal_int", C.c_float),
         ("thres_sal_depth", C.c_float), ("max_iters", C.c_int32), ("tol_residual", C.c_double),
         ("tol_update", C.c_double), ("method", C.c_int32), ("occlusion", C.c_int32),
-        ("n_sensors_mask", C.c_int32), ("reserved", C.c_int32),
+        ("n_sensors_mask", C.c_int32), ("projection", C.c_int32),
     ]
 
 
@@ -242,7 +242,7 @@ def pinhole_params(n_levels=4, method=PHOTO_DEPTH, std_photo=None):
     """Defaults of the pinhole alignFrames (RPI.h:4304-4309): tol_residual 1e-4, no sensor-joint mask."""
     p = default_params(n_levels=n_levels, method=method, std_photo=std_photo, n_sensors_mask=0)
     p.tol_residual = 1e-4
-    p.reserved = 1
+    p.projection = 1
     return p
 
 

@@ -6,10 +6,10 @@ fails loudly if it is missing.  Nothing here imports the CPU oracle.
 """
 from .native import (Context, Params, Result, IterRecord, default_params, lib, build_native,
                      PHOTO_CONSISTENCY, DEPTH_CONSISTENCY, PHOTO_DEPTH, ROLE_SOURCE, ROLE_TARGET,
-                     ROLE_BOTH, R360Error, pose_to_colmajor, pose_from_colmajor, synth_gt_pose)
+                     ROLE_BOTH, R360Error, pose_to_colmajor, pose_from_colmajor, synth_gt_pose, pinhole_params)
 from .register import RegisterPhotoICP
 
 __all__ = ["Context", "Params", "Result", "IterRecord", "default_params", "lib", "build_native",
            "PHOTO_CONSISTENCY", "DEPTH_CONSISTENCY", "PHOTO_DEPTH", "ROLE_SOURCE", "ROLE_TARGET",
            "ROLE_BOTH", "R360Error", "RegisterPhotoICP", "pose_to_colmajor", "pose_from_colmajor",
-           "synth_gt_pose"]
+           "synth_gt_pose", "pinhole_params"]

@@ -67,6 +67,7 @@ struct Ctx {
     float* d_cams = nullptr; float* h_cams = nullptr;
     int* occ_head = nullptr; int* occ_next = nullptr; float* occ_dinv = nullptr;   // occlusion 1/2: per-texel candidate lists
     int occ_cap = 0;                                                                // pairs the scratch holds
+    float cam[4] = {0.f, 0.f, 0.f, 0.f}; bool have_cam = false;                     // setCameraMatrix (pinhole contexts)
     uint8_t* d_sens_rgb = nullptr; uint16_t* d_sens_depth = nullptr; size_t sens_cap = 0;   // ingest: sensor images of one chunk
     // stats
     float last_ms = 0.f, pass_ms = 0.f;
@@ -129,6 +130,8 @@ R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint, int first = 0) {
     return a;
 }
 
+int trace_per_level(const Ctx* c) { return c->P.projection == R360_PINHOLE ? 2 * c->P.max_iters + 2 : c->P.max_iters + 2; }
+
 R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) {
     R360GnArgs g{};
     g.params = c->P;
@@ -139,7 +142,7 @@ R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) 
     g.active_list = c->d_active + first;
     g.n_active = c->d_nactive;
     g.ticket = c->d_nactive + 2;
-    g.trace = trace ? trace + (size_t)first * c->L * (c->P.max_iters + 2) : nullptr;
+    g.trace = trace ? trace + (size_t)first * c->L * trace_per_level(c) : nullptr;
     return g;
 }
 
@@ -293,8 +296,20 @@ int eval_setup(Ctx* c, int src, int trg, int level, const float pose[16], R360Pa
 
 // One evaluation of the active pairs of `a` at their pose_eval: the fused pass (occlusion 0) or the
 // scatter + evaluate pair of the occlusion variants.
-void launch_evaluation(Ctx* c, const R360PassArgs& a, int n_pairs) {
-    if (c->P.occlusion == 0) {
+R360PinLevel pin_level(const Ctx* c, int level) {
+    R360PinLevel pl;
+    const float scaleFactor = 1.0 / pow(2, level);              // RPI.h:569
+    pl.fx = c->cam[0] * scaleFactor; pl.fy = c->cam[1] * scaleFactor;
+    pl.ox = c->cam[2] * scaleFactor; pl.oy = c->cam[3] * scaleFactor;
+    pl.inv_fx = 1. / pl.fx; pl.inv_fy = 1. / pl.fy;              // RPI.h:574-575
+    return pl;
+}
+
+void launch_evaluation(Ctx* c, const R360PassArgs& a, int n_pairs, int level) {
+    if (c->P.projection == R360_PINHOLE) {
+        r360_launch_pin_eval(c->st, a, pin_level(c, level), n_pairs, c->sm_count);
+        ++c->launches;
+    } else if (c->P.occlusion == 0) {
         r360_launch_pass(c->st, a, c->pass_grid);
         ++c->launches;
     } else {
@@ -307,7 +322,8 @@ int eval_pass(Ctx* c, int src, int trg, int level, const float pose[16], double 
     R360PassArgs a;
     int rc = eval_setup(c, src, trg, level, pose, &a);
     if (rc) return rc;
-    launch_evaluation(c, a, 1);
+    if (c->P.projection == R360_PINHOLE && !c->have_cam) return fail(c, R360_E_STATE, "pinhole context: call r360_set_camera first (setCameraMatrix, RPI.h:254)");
+    launch_evaluation(c, a, 1, level);
     CK(c, cudaGetLastError());
     const int slot = c->max_pairs;
     CK(c, cudaMemcpyAsync(acc, c->d_acc + (size_t)slot * R360_ACC_STRIDE, sizeof(double) * R360_ACC_STRIDE, cudaMemcpyDeviceToHost, c->st));
@@ -341,6 +357,14 @@ void r360_default_params(r360_params* p) {
     p->method = R360_PHOTO_DEPTH;          // what every caller passes
     p->occlusion = 0;
     p->n_sensors_mask = 8;                 // RPI.h:4537
+}
+
+void r360_default_params_pinhole(r360_params* p) {
+    if (!p) return;
+    r360_default_params(p);
+    p->projection = R360_PINHOLE;
+    p->tol_residual = 1e-4;                // RPI.h:4308
+    p->n_sensors_mask = 0;                 // the sensor-joint mask belongs to alignFrames360 (RPI.h:4537)
 }
 
 const char* r360_last_error(const r360_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -492,6 +516,10 @@ int r360_create(r360_ctx** out, int device, int rows, int cols, int max_frames, 
                                          "(every level keeps an even width)", cols, rows);
     if (params->occlusion < 0 || params->occlusion > 2)
         return fail(nullptr, R360_E_ARG, "r360_create: occlusion %d not in {0, 1, 2} (RPI.h:4517)", params->occlusion);
+    if (params->projection != R360_SPHERE && params->projection != R360_PINHOLE)
+        return fail(nullptr, R360_E_ARG, "r360_create: projection %d is neither R360_SPHERE nor R360_PINHOLE", params->projection);
+    if (params->projection == R360_PINHOLE && params->occlusion != 0)
+        return fail(nullptr, R360_E_ARG, "r360_create: the pinhole occlusion variants (errorPhotoICP_Occ1/2, RPI.h:1107-2023) are not built");
     if (params->method < 0 || params->method > 2) return fail(nullptr, R360_E_ARG, "r360_create: bad method %d", params->method);
     if (params->max_iters < 1 || params->max_iters > 64) return fail(nullptr, R360_E_ARG, "r360_create: max_iters %d not in [1,64]", params->max_iters);
     if ((long long)rows * cols >= (1LL << 27)) return fail(nullptr, R360_E_ARG, "r360_create: image too large");
@@ -532,11 +560,15 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
         r360_launch_level_begin(c->st, g, level);
         ++c->launches;
         R360PassArgs a = pass_args(c, level, n, first);
-        for (int k = 0; k <= c->P.max_iters; ++k) {                   // 1 initial + <= max_iters loop bodies
+        const bool pin = c->P.projection == R360_PINHOLE;
+        // sphere: 1 initial + <= max_iters loop bodies; pinhole: every loop body may add one damped retry
+        const int n_eval = pin ? 2 * c->P.max_iters + 1 : c->P.max_iters + 1;
+        for (int k = 0; k < n_eval; ++k) {
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
-            launch_evaluation(c, a, n);
+            launch_evaluation(c, a, n, level);
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
-            r360_launch_gn_step(c->st, g, level);
+            if (pin) r360_launch_gn_step_pin(c->st, g, level);
+            else r360_launch_gn_step(c->st, g, level);
             ++c->launches;
         }
     }
@@ -561,7 +593,9 @@ int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const 
         c->h_idx[p] = src_idx[p];
         c->h_idx[n_pairs + p] = trg_idx[p];
     }
-    const int per_level = c->P.max_iters + 2;
+    if (c->P.projection == R360_PINHOLE && !c->have_cam)
+        return fail(c, R360_E_STATE, "pinhole context: call r360_set_camera first (setCameraMatrix, RPI.h:254)");
+    const int per_level = trace_per_level(c);
     const size_t n_rec = (size_t)n_pairs * c->L * per_level;
     if (trace && c->trace_cap < n_rec) {
         if (c->d_trace) cudaFree(c->d_trace);
@@ -574,7 +608,8 @@ int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const 
     if (trace) CK(c, cudaMemsetAsync(c->d_trace, 0, sizeof(r360_iter_record) * n_rec, c->st));
     int n_ev = 0;
     if (c->P.occlusion == 0) {
-        int rc = enqueue_register(c, 0, n_pairs, n_pairs, init_pose != nullptr, trace ? c->d_trace : nullptr, true, &n_ev);
+        int rc = enqueue_register(c, 0, n_pairs, n_pairs, init_pose != nullptr, trace ? c->d_trace : nullptr,
+                                  c->P.projection == R360_SPHERE, &n_ev);
         if (rc) return rc;
     } else {
         // the occlusion variants keep per-texel candidate lists for every pair of a batch: bounded batches
@@ -654,13 +689,40 @@ int r360_eval_error(r360_ctx* c, int src, int trg, int level, const float pose[1
     double acc[R360_ACC_STRIDE]; int cnt[R360_ACC_INTS];
     int rc = eval_pass(c, src, trg, level, pose, acc, cnt);
     if (rc) return rc;
-    if (c->P.occlusion == 0) {
+    if (c->P.projection == R360_PINHOLE) {
+        if (err2) *err2 = acc[27] + acc[28];
+        if (n_valid) *n_valid = cnt[2];
+    } else if (c->P.occlusion == 0) {
         if (err2) *err2 = acc[27];
         if (n_valid) *n_valid = cnt[1] + cnt[2];
     } else {
         if (err2) *err2 = acc[27] + acc[28];
         if (n_valid) *n_valid = c->P.occlusion == 1 ? cnt[1] + cnt[2] : cnt[2];
     }
+    return R360_OK;
+}
+
+int r360_set_camera(r360_ctx* c, float fx, float fy, float ox, float oy) {
+    if (!c) return R360_E_ARG;
+    if (c->P.projection != R360_PINHOLE) return fail(c, R360_E_STATE, "set_camera: the context was created with projection = R360_SPHERE");
+    if (!(fx > 0.f) || !(fy > 0.f)) return fail(c, R360_E_ARG, "set_camera: focal lengths must be positive");
+    c->cam[0] = fx; c->cam[1] = fy; c->cam[2] = ox; c->cam[3] = oy;
+    c->have_cam = true;
+    return R360_OK;
+}
+
+int r360_eval_error_pinhole(r360_ctx* c, int src, int trg, int level, const float pose[16], double* photo_residual,
+                            double* depth_residual, int32_t* n_valid_photo, int32_t* n_valid_depth, double* error) {
+    if (!c) return R360_E_ARG;
+    if (c->P.projection != R360_PINHOLE) return fail(c, R360_E_STATE, "eval_error_pinhole: the context was created with projection = R360_SPHERE");
+    double acc[R360_ACC_STRIDE]; int cnt[R360_ACC_INTS];
+    int rc = eval_pass(c, src, trg, level, pose, acc, cnt);
+    if (rc) return rc;
+    if (photo_residual) *photo_residual = acc[27];
+    if (depth_residual) *depth_residual = acc[28];
+    if (n_valid_photo) *n_valid_photo = cnt[1];
+    if (n_valid_depth) *n_valid_depth = cnt[2];
+    if (error) *error = (double)(float)(std::sqrt(acc[27] / (double)cnt[2]) + std::sqrt(acc[28] / (double)cnt[2]));   // RPI.h:768-771
     return R360_OK;
 }
 

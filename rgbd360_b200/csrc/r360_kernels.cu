@@ -750,7 +750,7 @@ __global__ void k_level_begin(R360GnArgs g, int level) {
         if (ps->status != R360_PAIR_OK) { ps->active = 0; continue; }
         for (int k = 0; k < 16; ++k) ps->pose_eval[k] = ps->pose_estim[k];
         for (int k = 0; k < 6; ++k) ps->upd[k] = 1.f;
-        ps->lambda = 1.0;
+        ps->lambda = g.params.projection == R360_PINHOLE ? 0.01 : 1.0;     // RPI.h:4589 / 4304
         ps->it = 0;
         ps->phase = 0;
         ps->ev = 0;
@@ -1050,3 +1050,6 @@ void r360_launch_synth(cudaStream_t st, int kind, int first_id, int rows, int co
     dim3 grid(r360_blocks((long long)rows * cols, 256, sm_count * 8), n_frames);
     k_synth<<<grid, 256, 0, st>>>(kind, first_id, rows, cols, cams, rgb, depth_mm);
 }
+
+// =========================================================================== pinhole registration
+#include "r360_pinhole.cuh"

@@ -31,6 +31,12 @@ struct R360PassArgs {
     int* cnt;                           // device: per pair R360_ACC_INTS
 };
 
+// Pinhole intrinsics of one pyramid level, formed on the host exactly as the reference does
+// (RPI.h:569-575: scaleFactor = 1/2^level as float, fx * scaleFactor, inv_fx = 1./fx narrowed to float).
+struct R360PinLevel {
+    float fx, fy, ox, oy, inv_fx, inv_fy;
+};
+
 struct R360StitchArgs {
     R360StitchGeom g;
     float Rt_inv[8][16];                // inverse extrinsics of the 8 sensors, column-major (Calib360.h:122-131)
@@ -63,6 +69,9 @@ void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid);
 // occlusion variants (r360_occ.cu): head / next / dinv hold n_pairs * lv.n entries each
 void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, int* head, int* next, float* dinv,
                           int sm_count);
+// pinhole registration (r360_pinhole.cuh)
+void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count);
+void r360_launch_gn_step_pin(cudaStream_t st, const R360GnArgs& g, int level);
 void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
                            uint8_t* vp, uint8_t* vd, int sm_count);
 void r360_launch_index_stats(cudaStream_t st, const R360PassArgs& a, int pair, unsigned long long* out, int sm_count);

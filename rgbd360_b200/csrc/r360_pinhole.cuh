@@ -1,0 +1,278 @@
+// r360_pinhole.cuh -- the pinhole registration of RegisterPhotoICP, included by
+// r360_kernels.cu (it shares the state-machine helpers of that translation unit):
+//   k_pin_eval<METHOD>   errorPhotoICP (RPI.h:560-775) + calcHessGrad (RPI.h:776-1104) at one pose, fused:
+//                        the reference evaluates the error of a candidate and, when the step is accepted,
+//                        the Hessian at the same pose in the next loop body.
+//   k_gn_step_pin        the Levenberg-Marquardt state machine of alignFrames (RPI.h:4254-4512): accept on
+//                        diff_error > 0, one damped retry otherwise, full SE(3) exponential.
+// Same pyramids and texel layout as the spherical path (built without the sensor-joint mask).  The
+// index maps are bit-exact by construction: the projection is evaluated with the reference's own
+// operation sequence -- including its double-precision 1 / z narrowed to float (RPI.h:659) -- and the
+// file is compiled with --fmad=false.  Not a throughput path: one pixel per thread, direct gathers.
+#pragma once
+
+#define R360_PIN_THREADS 256
+
+template <int METHOD>
+__global__ void __launch_bounds__(R360_PIN_THREADS)
+k_pin_eval(R360PassArgs a, R360PinLevel pl) {
+    __shared__ float s_red[R360_PIN_THREADS / 32][R360_ACC_DOUBLES + 1];
+    __shared__ int s_cnt[R360_PIN_THREADS / 32][R360_ACC_INTS];
+    const int ap = blockIdx.y;
+    if (ap >= *a.n_active) return;
+    const R360Level lv = a.lv;
+    const r360_params P = a.params;
+    const int pair = a.active_list[ap];
+    const R360Pair* ps = a.pairs + pair;
+    float T[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) T[k] = ps->pose_eval[k];
+    const float2* __restrict__ src = a.src_base[pair] + lv.px_off;
+    const float2* __restrict__ trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
+
+    float H[21], g[6];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) H[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = 0.f;
+    float sumP = 0.f, sumD = 0.f;
+    int n_vis = 0, n_photo = 0, n_depth = 0;
+    auto accumulate = [&](const float J[6], float r) {
+        int q = 0;
+#pragma unroll
+        for (int x = 0; x < 6; ++x) {
+#pragma unroll
+            for (int y = x; y < 6; ++y, ++q) H[q] = fmaf(J[x], J[y], H[q]);
+            g[x] = fmaf(J[x], r, g[x]);
+        }
+    };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lv.n; i += gridDim.x * blockDim.x) {
+        const int r = (int)(((unsigned long long)i * lv.div_magic) >> 40), c = i - r * lv.cols;
+        const float2 s = __ldg(&src[i]);                                   // {depth, gray}
+        const float z = s.x;
+        if (!(P.min_depth < z && z < P.max_depth)) continue;               // LUT x = INVALID_POINT, RPI.h:4293-4299
+        const float X = (c - pl.ox) * z * pl.inv_fx;                       // RPI.h:4295
+        const float Y = (r - pl.oy) * z * pl.inv_fy;
+        const float px = ((T[0] * X + T[4] * Y) + T[8] * z) + T[12];
+        const float py = ((T[1] * X + T[5] * Y) + T[9] * z) + T[13];
+        const float pz = ((T[2] * X + T[6] * Y) + T[10] * z) + T[14];
+        const float iz = (float)(1.0 / (double)pz);                        // RPI.h:659
+        const float tc = (px * pl.fx) * iz + pl.ox;                        // RPI.h:662
+        const float tr = (py * pl.fy) * iz + pl.oy;
+        const int ri = r360_round_to_int_dev(tr), ci = r360_round_to_int_dev(tc);
+        if (!((unsigned)ri < (unsigned)lv.rows && (unsigned)ci < (unsigned)lv.cols)) continue;   // RPI.h:667-668
+        const float2* tx = trg + 3u * (unsigned)(ri * lv.cols + ci);
+        const float2 t0 = __ldg(tx), t1 = __ldg(tx + 1), t2 = __ldg(tx + 2);   // {gray, depth}, {Ix, Iy}, {Dx, Dy}
+        const bool fin = fabsf(t0.y) < INFINITY;
+        // weighted residuals (shared by the error and the Hessian rows)
+        float rp = 0.f, wp = 0.f, rd = 0.f, wd = 0.f;
+        if (METHOD != R360_DEPTH_CONSISTENCY) {
+            const float e = t0.x - s.y;
+            wp = a.inv_std_photo;
+            if (!(fabsf(e) < P.std_photo)) { const float u = r360_rcp_fast(fabsf(e)); wp = r360_sqrt_fast(u * (2.f * a.inv_std_photo - u)); }
+            rp = wp * e;
+        }
+        if (METHOD != R360_PHOTO_CONSISTENCY && fin) {
+            const float f = t0.y - pz;
+            const float sd = P.std_depth * pz;                             // RPI.h:694: transformed SOURCE depth
+            wd = r360_rcp_fast(sd);
+            if (!(fabsf(f) < sd)) { const float u = r360_rcp_fast(fabsf(f)); wd = r360_sqrt_fast(u * (2.f * wd - u)); }
+            rd = wd * f;
+        }
+        // ---- errorPhotoICP: no saliency test (RPI.h:669-703)
+        if (METHOD != R360_DEPTH_CONSISTENCY) { sumP += rp * rp; ++n_photo; }
+        if (METHOD != R360_PHOTO_CONSISTENCY && fin) { sumD += rd * rd; ++n_depth; }
+        // ---- calcHessGrad (RPI.h:967-1085): both saliency `continue`s drop the whole pixel
+        ++n_vis;
+        if (METHOD != R360_DEPTH_CONSISTENCY &&
+            (fabsf(t1.x) < P.thres_sal_int) & (fabsf(t1.y) < P.thres_sal_int)) continue;
+        if (METHOD != R360_PHOTO_CONSISTENCY &&
+            (fabsf(t2.x) < P.thres_sal_depth) & (fabsf(t2.y) < P.thres_sal_depth)) continue;
+        const float iz2 = iz * iz;
+        float J0[6], J1[6];                                                // jacobianWarpRt, RPI.h:970-984
+        J0[0] = pl.fx * iz; J1[0] = 0.f;
+        J0[1] = 0.f; J1[1] = pl.fy * iz;
+        J0[2] = -pl.fx * px * iz2; J1[2] = -pl.fy * py * iz2;
+        J0[3] = -pl.fx * py * px * iz2; J1[3] = -pl.fy * (1 + py * py * iz2);
+        J0[4] = pl.fx * (1 + px * px * iz2); J1[4] = pl.fy * px * py * iz2;
+        J0[5] = -pl.fx * py * iz; J1[5] = pl.fy * px * iz;
+        float J[6];
+        if (METHOD != R360_DEPTH_CONSISTENCY) {
+            const float ga = wp * t1.x, gb = wp * t1.y;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) J[q] = ga * J0[q] + gb * J1[q];
+            accumulate(J, rp);
+        }
+        if (METHOD != R360_PHOTO_CONSISTENCY && fin) {
+            const float Rz[6] = { 0.f, 0.f, 1.f, py, -px, 0.f };           // jacobianRt_z, RPI.h:1053
+#pragma unroll
+            for (int q = 0; q < 6; ++q) J[q] = wd * ((t2.x * J0[q] + t2.y * J1[q]) - Rz[q]);
+            accumulate(J, rd);
+        }
+    }
+
+    // ---- block reduction (as k_occ_eval): 27 normal-equation sums + PhotoResidual + DepthResidual, 3 counters
+    float acc[R360_ACC_DOUBLES + 1];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) acc[k] = H[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[21 + k] = g[k];
+    acc[27] = sumP;
+    acc[28] = sumD;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < R360_ACC_DOUBLES + 1; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) s_red[wid][k] = v;
+    }
+    n_vis = __reduce_add_sync(0xffffffffu, n_vis);
+    n_photo = __reduce_add_sync(0xffffffffu, n_photo);
+    n_depth = __reduce_add_sync(0xffffffffu, n_depth);
+    if (lane == 0) { s_cnt[wid][0] = n_vis; s_cnt[wid][1] = n_photo; s_cnt[wid][2] = n_depth; s_cnt[wid][3] = 0; }
+    __syncthreads();
+    if (threadIdx.x < R360_ACC_DOUBLES + 1) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < R360_PIN_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
+        atomicAdd(&a.acc[(size_t)pair * R360_ACC_STRIDE + threadIdx.x], sum);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < R360_PIN_THREADS / 32; ++k) sum += s_cnt[k][threadIdx.x - 32];
+        atomicAdd(&a.cnt[(size_t)pair * R360_ACC_INTS + threadIdx.x - 32], sum);
+    }
+}
+
+// exp(update) * pose_estim with the FULL exponential (CPose3D::exp(v), RPI.h:4375)
+__device__ void r360_pin_candidate(R360Pair* ps, const float upd[6]) {
+    double ud[6], Td[16];
+    for (int k = 0; k < 6; ++k) { ps->upd[k] = upd[k]; ud[k] = (double)upd[k]; }
+    r360_se3_exp(ud, Td);
+    float Tf[16], Tn[16];
+    for (int k = 0; k < 16; ++k) Tf[k] = (float)Td[k];
+    r360_mat4_mul(Tf, ps->pose_estim, Tn);
+    for (int k = 0; k < 16; ++k) ps->pose_eval[k] = Tn[k];
+}
+
+// One step of the per-pair state machine of alignFrames after an evaluation.
+//   phase 0: pose_estim at the start of the level;  phase 1: the Gauss-Newton candidate;
+//   phase 2: the damped candidate of the LM retry (LM_maxIters = 1, RPI.h:4306).
+__global__ void k_gn_step_pin(R360GnArgs g, int level) {
+    const r360_params P = g.params;
+    const int per_level = 2 * P.max_iters + 2;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
+        R360Pair* ps = g.pairs + p;
+        if (!ps->active) continue;
+        const double* acc = g.acc + (size_t)p * R360_ACC_STRIDE;
+        const int* cnt = g.cnt + (size_t)p * R360_ACC_INTS;
+        const double n_d = (double)cnt[2];
+        // avResidual is a float member (RPI.h:183): the value alignFrames compares has float precision
+        const double err = (double)(float)(sqrt(acc[27] / n_d) + sqrt(acc[28] / n_d));    // RPI.h:768-771
+        ps->passes[level] += 1;
+        double diff_error;
+        int accepted = 0;
+        bool retry = false;
+        if (ps->phase == 0) {
+            diff_error = err;                                   // RPI.h:4318
+            accepted = 1;
+        } else {
+            diff_error = ps->error - err;                       // RPI.h:4384 / 4411
+            accepted = diff_error > 0;                          // RPI.h:4390 / 4415
+            if (accepted) {
+                if (ps->phase == 1) ps->lambda /= 10.0;         // RPI.h:4392 (the retry keeps lambda)
+                for (int k = 0; k < 16; ++k) ps->pose_estim[k] = ps->pose_eval[k];
+                ps->it += 1;
+            } else if (ps->phase == 1 && diff_error < 0) {
+                retry = true;                                   // RPI.h:4399-4402
+            }
+        }
+        if (accepted) {
+            ps->error = err; ps->err2 = acc[27] + acc[28]; ps->n_valid = cnt[2];
+            for (int k = 0; k < 21; ++k) ps->Hc[k] = (float)acc[k];
+            for (int k = 0; k < 6; ++k) ps->gc[k] = (float)acc[21 + k];
+            ps->nvis_c = cnt[0];
+        }
+        if (g.trace && ps->ev < per_level) {
+            r360_iter_record* rec = g.trace + ((size_t)p * P.n_levels + level) * per_level + ps->ev;
+            rec->err2 = acc[27]; rec->err2_depth = acc[28]; rec->n_valid = cnt[1]; rec->n_valid_depth = cnt[2];
+            rec->n_visible = cnt[0]; rec->level = level; rec->it = ps->it; rec->accepted = accepted; rec->used = 3;
+            for (int k = 0; k < 16; ++k) rec->pose[k] = ps->pose_eval[k];
+            for (int k = 0; k < 21; ++k) rec->hessian[k] = (float)acc[k];
+            for (int k = 0; k < 6; ++k) rec->gradient[k] = (float)acc[21 + k];
+            rec->pad = 0.f; rec->reserved = 0;
+        }
+        ps->ev += 1;
+        r360_zero_acc(g.acc, g.cnt, p);
+
+        if (retry) {
+            // lambda *= step; update = -(H + lambda diag H)^-1 g with the H of the last calcHessGrad (RPI.h:4401-4404)
+            ps->lambda *= 10.0;
+            const float lam = (float)ps->lambda;
+            float Hd[36], inv[36], upd[6];
+            int q = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b, ++q) Hd[a + 6 * b] = Hd[b + 6 * a] = ps->Hl[q];
+            for (int a = 0; a < 6; ++a) Hd[a + 6 * a] = Hd[a + 6 * a] + lam * Hd[a + 6 * a];
+            r360_inverse6(Hd, inv);
+            r360_solve_update(inv, ps->gl, upd);
+            r360_pin_candidate(ps, upd);
+            ps->phase = 2;
+            continue;
+        }
+        // while (it < maxIters && update_pose.norm() > tol_update && diff_error > tol_residual)   RPI.h:4324
+        const float* u = ps->upd;
+        const float na = u[0] * u[0] + (u[1] * u[1] + u[2] * u[2]);
+        const float nb = u[3] * u[3] + (u[4] * u[4] + u[5] * u[5]);
+        const float unorm = sqrtf(na + nb);
+        const bool go = ps->it < P.max_iters && (double)unorm > P.tol_update && diff_error > P.tol_residual;
+        if (!go) {
+            ps->iters[level] = ps->it;
+            ps->active = 0;
+            continue;
+        }
+        // loop body: calcHessGrad(pose_estim) == (Hc, gc)                     RPI.h:4340
+        for (int k = 0; k < 21; ++k) ps->Hl[k] = ps->Hc[k];
+        for (int k = 0; k < 6; ++k) ps->gl[k] = ps->gc[k];
+        ps->nvis_l = ps->nvis_c;
+        ps->lvl_l = level;
+        float Hm[36], Hlam[36];
+        {
+            int q = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b, ++q) Hm[a + 6 * b] = Hm[b + 6 * a] = ps->Hc[q];
+        }
+        const float lam = (float)ps->lambda;
+        for (int k = 0; k < 36; ++k) Hlam[k] = Hm[k];
+        for (int a = 0; a < 6; ++a) Hlam[a + 6 * a] = Hm[a + 6 * a] + lam * Hm[a + 6 * a];
+        if (r360_rank6(Hlam) != 6) {                            // RPI.h:4360-4368
+            ps->status = R360_PAIR_ILL_POSED;
+            ps->active = 0;
+            continue;
+        }
+        float inv[36], upd[6];
+        r360_inverse6(Hm, inv);
+        r360_solve_update(inv, ps->gc, upd);                    // RPI.h:4371
+        r360_pin_candidate(ps, upd);
+        ps->phase = 1;
+    }
+    r360_compact_when_last(g);
+}
+
+void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count) {
+    long long blocks = ((long long)a.lv.n + R360_PIN_THREADS - 1) / R360_PIN_THREADS;
+    long long cap = 8LL * sm_count / (n_pairs > 0 ? n_pairs : 1);
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const dim3 grid((unsigned)blocks, (unsigned)n_pairs);
+    switch (a.params.method) {
+        case R360_PHOTO_CONSISTENCY: k_pin_eval<R360_PHOTO_CONSISTENCY><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
+        case R360_DEPTH_CONSISTENCY: k_pin_eval<R360_DEPTH_CONSISTENCY><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
+        default: k_pin_eval<R360_PHOTO_DEPTH><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
+    }
+}
+void r360_launch_gn_step_pin(cudaStream_t st, const R360GnArgs& g, int level) {
+    k_gn_step_pin<<<r360_blocks(g.n_pairs, 32, 1024), 32, 0, st>>>(g, level);
+}

@@ -20,6 +20,7 @@ EXPORTS = [
     "r360_device_free", "r360_synchronize", "r360_last_device_ms", "r360_kernel_launches",
     "r360_last_pass_stats", "r360_version", "r360_index_stats", "r360_register_host_pairs",
     "r360_default_rig", "r360_frame360_parse", "r360_stitch_frames", "r360_eval_error_occ",
+    "r360_default_params_pinhole", "r360_set_camera", "r360_eval_error_pinhole",
 ]
 
 
@@ -33,7 +34,7 @@ class Params(C.Structure):
         ("std_photo", C.c_float), ("std_depth", C.c_float), ("thres_sal_int", C.c_float),
         ("thres_sal_depth", C.c_float), ("max_iters", C.c_int32), ("tol_residual", C.c_double),
         ("tol_update", C.c_double), ("method", C.c_int32), ("occlusion", C.c_int32),
-        ("n_sensors_mask", C.c_int32), ("reserved", C.c_int32),
+        ("n_sensors_mask", C.c_int32), ("projection", C.c_int32),
     ]
 
 
@@ -108,6 +109,9 @@ def lib():
     L.r360_eval_error.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.r360_eval_error_occ.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.r360_eval_error_pinhole.argtypes = L.r360_eval_error_occ.argtypes
+    L.r360_default_params_pinhole.argtypes = [C.POINTER(Params)]
+    L.r360_set_camera.argtypes = [vp, f32, f32, f32, f32]
     L.r360_eval_hessgrad.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.POINTER(C.c_int32)]
     L.r360_dump_level.argtypes = [vp, i32, i32] + [vp] * 6
     L.r360_dump_source_level.argtypes = [vp, i32, i32, vp, vp]
@@ -172,6 +176,15 @@ def frame360_parse(data):
 def default_params(**kw):
     p = Params()
     lib().r360_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def pinhole_params(**kw):
+    """r360_default_params_pinhole: the constants of the pinhole alignFrames (RPI.h:4304-4309)."""
+    p = Params()
+    lib().r360_default_params_pinhole(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -278,7 +291,8 @@ class Context:
             ip = np.ascontiguousarray(init_pose, np.float32).reshape(n, 16)
         tr = None
         if trace:
-            tr = (IterRecord * (n * self.params.n_levels * (self.params.max_iters + 2)))()
+            per = (2 * self.params.max_iters + 2) if self.params.projection == 1 else (self.params.max_iters + 2)
+            tr = (IterRecord * (n * self.params.n_levels * per))()
         self._ck(self.L.r360_register_pairs(self.h, n, _p(s), _p(t), _p(ip), _p(res),
                                             C.cast(tr, C.c_void_p) if trace else None))
         return (res, tr) if trace else res
@@ -309,6 +323,19 @@ class Context:
         T = pose_to_colmajor(pose)
         self._ck(self.L.r360_eval_error_occ(self.h, src, trg, level, _p(T), C.byref(pr), C.byref(dr), C.byref(npv),
                                             C.byref(ndv), C.byref(e)))
+        return dict(photo=pr.value, depth=dr.value, n_photo=npv.value, n_depth=ndv.value, error=e.value)
+
+    def set_camera(self, fx, fy, ox, oy):
+        """setCameraMatrix (RPI.h:254) of a pinhole context."""
+        self._ck(self.L.r360_set_camera(self.h, fx, fy, ox, oy))
+
+    def eval_error_pinhole(self, src, trg, level, pose):
+        """errorPhotoICP (RPI.h:560) -> dict(photo, depth, n_photo, n_depth, error)."""
+        pr, dr, e = C.c_double(), C.c_double(), C.c_double()
+        npv, ndv = C.c_int32(), C.c_int32()
+        T = pose_to_colmajor(pose)
+        self._ck(self.L.r360_eval_error_pinhole(self.h, src, trg, level, _p(T), C.byref(pr), C.byref(dr), C.byref(npv),
+                                                C.byref(ndv), C.byref(e)))
         return dict(photo=pr.value, depth=dr.value, n_photo=npv.value, n_depth=ndv.value, error=e.value)
 
     def eval_hessgrad(self, src, trg, level, pose):

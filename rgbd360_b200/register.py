@@ -41,8 +41,11 @@ class RegisterPhotoICP:
     def setDepthVariance(self, std):
         self._p.std_depth = float(std); self._drop()
 
-    def setCameraMatrix(self, K):        # pinhole path only; accepted and ignored
-        pass
+    def setCameraMatrix(self, K):        # RPI.h:254 (3x3 camera matrix of the pinhole path)
+        K = np.asarray(K, np.float32).reshape(3, 3)
+        self._cam = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]))
+        if self._ctx is not None and self._p.projection == 1:
+            self._ctx.set_camera(*self._cam)
 
     def setVisualization(self, viz):
         pass
@@ -61,6 +64,10 @@ class RegisterPhotoICP:
             self._drop()
             self._ctx = Context(shape[0], shape[1], 2, 1, self._p, self._device)
             self._shape = shape
+            if self._p.projection == 1:
+                if getattr(self, "_cam", None) is None:
+                    raise RuntimeError("setCameraMatrix first (RPI.h:254)")
+                self._ctx.set_camera(*self._cam)
             for slot, (r, d, role) in self._pending.items():
                 if r.shape[:2] == shape:
                     self._ctx.set_frames(slot, r[None], d[None], [role])
@@ -75,14 +82,50 @@ class RegisterPhotoICP:
         self._ensure(rgb)
         self._ctx.set_frames(1, rgb[None], depth[None], [ROLE_TARGET])
 
+    def _configure(self, method, occlusion, projection):
+        """Re-create the context when the cost function, the occlusion variant or the registration changes."""
+        if self._ctx is None:
+            raise RuntimeError("setSourceFrame / setTargetFrame first")
+        if method != self._p.method or occlusion != self._p.occlusion or projection != self._p.projection:
+            self._p.method = int(method)
+            self._p.occlusion = int(occlusion)
+            if projection != self._p.projection:     # constants hard-coded in alignFrames / alignFrames360
+                self._p.projection = int(projection)
+                self._p.tol_residual = 1e-4 if projection == 1 else 1e-3      # RPI.h:4308 / 4594
+                self._p.n_sensors_mask = 0 if projection == 1 else 8          # RPI.h:4537
+            self._ctx.close(); self._ctx = None
+            self._ensure(self._pending[0][0])
+
+    def alignFrames(self, pose_guess=None, method=PHOTO_CONSISTENCY, occlusion=0):
+        """The pinhole registration (RPI.h:4254-4512); needs setCameraMatrix."""
+        if occlusion != 0:
+            raise NotImplementedError("the pinhole occlusion variants (RPI.h:1107-2023) are not built")
+        self._configure(method, 0, 1)
+        guess = None if pose_guess is None else pose_to_colmajor(pose_guess)[None]
+        self._res = self._ctx.register_pairs([0], [1], guess)[0]
+
+    def errorPhotoICP(self, level, pose, method=PHOTO_CONSISTENCY):
+        self._configure(method, 0, 1)
+        e = self._ctx.eval_error_pinhole(0, 1, level, pose)
+        return e["error"]
+
+    def calcHessGrad(self, level, pose, method=PHOTO_CONSISTENCY):
+        self._configure(method, 0, 1)
+        H, g, nv = self._ctx.eval_hessgrad(0, 1, level, pose)
+        self._hg = (H, g)
+
     def alignFrames360(self, pose_guess=None, method=PHOTO_CONSISTENCY, occlusion=0):
         if occlusion not in (0, 1, 2):
             raise ValueError("occlusion must be 0, 1 or 2 (RPI.h:4517)")
         if self._ctx is None:
             raise RuntimeError("setSourceFrame / setTargetFrame first")
-        if method != self._p.method or occlusion != self._p.occlusion:
+        if method != self._p.method or occlusion != self._p.occlusion or self._p.projection != 0:
             self._p.method = int(method)
             self._p.occlusion = int(occlusion)
+            if self._p.projection != 0:
+                self._p.projection = 0
+                self._p.tol_residual = 1e-3
+                self._p.n_sensors_mask = 8
             self._ctx.close(); self._ctx = None
             self._ensure(self._pending[0][0])
         guess = None if pose_guess is None else pose_to_colmajor(pose_guess)[None]

@@ -97,3 +97,131 @@ def test_pinhole_exponential_is_the_full_se3_exp(orc):
         w = v[3:]
         X = np.zeros((4, 4)); X[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]; X[:3, 3] = v[:3]
         assert np.allclose(T, expm(X), atol=1e-12)
+
+
+# ============================================================================ GPU (CUDA path vs the oracle, PINNED)
+def _gpu_ctx(r360, case, max_pairs=1):
+    rows, cols = case["d_s"].shape
+    p = r360.pinhole_params(n_levels=case["levels"], method=case["method"])
+    ctx = r360.Context(rows, cols, 2, max_pairs, p)
+    ctx.set_camera(*case["cam"])
+    ctx.set_frames(0, np.stack([case["rgb_s"], case["rgb_t"]]), np.stack([case["d_s"], case["d_t"]]),
+                   [r360.ROLE_SOURCE, r360.ROLE_TARGET])
+    return ctx
+
+
+def _check_eval(orc, ctx, src, trg, P, cam, level, T):
+    eo = orc.error_pinhole(src, trg, level, T, P, cam)
+    eg = ctx.eval_error_pinhole(0, 1, level, T)
+    assert (eg["n_photo"], eg["n_depth"]) == (eo["n_photo"], eo["n_depth"]), (level, eg, eo)     # integer work: exact
+    for k in ("photo", "depth"):
+        assert abs(eg[k] - eo[k]) <= REL * abs(eo[k]) + 1e-30, (level, k, eg[k], eo[k])
+    if np.isfinite(eo["error"]):
+        assert abs(eg["error"] - eo["error"]) <= REL * abs(eo["error"])
+    else:
+        assert not np.isfinite(eg["error"])
+    ho = orc.hessgrad_pinhole(src, trg, level, T, P, cam, accum=orc.ACC_STABLE)
+    Hg, gg, nv = ctx.eval_hessgrad(0, 1, level, T)
+    assert nv == ho["n_visible"], (level, nv, ho["n_visible"])
+    Ho = ho["H"].astype(np.float64)
+    dg = np.abs(np.diag(Ho)) + 1e-30
+    sc = np.sqrt(np.outer(dg, dg))
+    assert np.all(np.abs(Hg.astype(np.float64) - Ho) <= REL * sc), np.max(np.abs(Hg - Ho) / sc)
+    gs = np.sqrt(dg * max(eo["photo"] + eo["depth"], 1e-30))
+    assert np.all(np.abs(gg.astype(np.float64) - ho["g"]) <= REL * gs), np.max(np.abs(gg - ho["g"]) / gs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(refcases.PINHOLE_CASES))
+def test_gpu_pinhole_evaluations(orc, r360, gold_pin, name):
+    """errorPhotoICP + calcHessGrad at every level, at probe poses and at the reference's recorded final pose."""
+    from util import small_pose
+    case = refcases.make_pinhole_case(orc, name)
+    orc.set_math(orc.MATH_PINNED)
+    P, src, trg = _frames(orc, case)
+    ctx = _gpu_ctx(r360, case)
+    try:
+        poses = [np.eye(4, dtype=np.float32), small_pose(0.01, -0.02, 0.015, 0.03, -0.02, 0.05),
+                 np.array(gold_pin[name]["pinned"]["pose"], np.float32).reshape(4, 4)]
+        if case["guess"] is not None:
+            poses.append(np.asarray(case["guess"], np.float32))
+        for level in range(case["levels"]):
+            for T in poses:
+                _check_eval(orc, ctx, src, trg, P, case["cam"], level, T)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(refcases.PINHOLE_CASES))
+def test_gpu_pinhole_align(orc, r360, gold_pin, name):
+    """alignFrames: every pose the GPU evaluated is replayed through the oracle at the same bits (counters
+    exact, sums 1e-4); control flow, status and final pose against the oracle's own run and against the
+    recorded reference run (1e-4 rad / 1e-4 m)."""
+    from util import pose_err
+    case = refcases.make_pinhole_case(orc, name)
+    orc.set_math(orc.MATH_PINNED)
+    P, src, trg = _frames(orc, case)
+    ctx = _gpu_ctx(r360, case)
+    try:
+        L = case["levels"]
+        guess = None if case["guess"] is None else r360.pose_to_colmajor(case["guess"])[None]
+        res_g, tr_g = ctx.register_pairs([0], [1], guess, trace=True)
+        res_g = res_g[0]
+        res_o, tr_o = orc.align_pinhole(src, trg, case["guess"], P, case["cam"], accum=orc.ACC_STABLE, trace=True)
+        per = 2 * P.max_iters + 2
+        n_rec = 0
+        for lvl in range(L):
+            for k in range(per):
+                g, o = tr_g[lvl * per + k], tr_o[lvl * per + k]
+                assert bool(g.used) == bool(o.used), (lvl, k)
+                if not g.used:
+                    continue
+                n_rec += 1
+                assert (g.accepted, g.it) == (o.accepted, o.it), (lvl, k)
+                T = np.array(g.pose, np.float32).reshape(4, 4).T
+                eo = orc.error_pinhole(src, trg, lvl, T, P, case["cam"])          # replay, same bits
+                assert (g.n_valid, g.n_valid_depth) == (eo["n_photo"], eo["n_depth"]), (lvl, k)
+                assert abs(g.err2 - eo["photo"]) <= REL * abs(eo["photo"]) + 1e-30, (lvl, k)
+                assert abs(g.err2_depth - eo["depth"]) <= REL * abs(eo["depth"]) + 1e-30, (lvl, k)
+        assert n_rec >= 1
+        ref = gold_pin[name]["pinned"]
+        assert list(res_g["iters"][:L]) == list(res_o.iters)[:L]
+        assert (res_g["status"] != 0) == (res_o.status != 0) == ref["ill_posed"]
+        Tg = np.array(res_g["pose"], np.float32).reshape(4, 4).T
+        ang, dist = pose_err(Tg, orc.pose_from(res_o.pose))
+        assert ang <= POSE_TOL and dist <= POSE_TOL, (ang, dist)
+        if list(res_o.iters)[:L] == ref["iters"]:
+            ang, dist = pose_err(Tg, np.array(ref["pose"]).reshape(4, 4))
+            assert ang <= POSE_TOL and dist <= POSE_TOL, (ang, dist)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pinhole_batch_and_errors(orc, r360):
+    """A batch of pinhole pairs == one-by-one runs; the camera matrix is mandatory; sphere contexts refuse it."""
+    rows, cols, L, n = 120, 160, 3, 5
+    cam = (131.25, 131.25, 79.5, 59.5)
+    p = r360.pinhole_params(n_levels=L)
+    ctx = r360.Context(rows, cols, 2 * n, n, p)
+    frames = [orc.synth_pinhole_frame(0, k, rows, cols, *cam) for k in range(2 * n)]
+    rgb = np.stack([f[0] for f in frames]); dep = np.stack([f[1] for f in frames])
+    ctx.set_frames(0, rgb, dep, np.array([r360.ROLE_TARGET, r360.ROLE_SOURCE] * n, np.uint8))
+    trg_idx = np.arange(0, 2 * n, 2, dtype=np.int32); src_idx = trg_idx + 1
+    with pytest.raises(r360.R360Error, match="set_camera"):
+        ctx.register_pairs(src_idx, trg_idx)
+    ctx.set_camera(*cam)
+    res = ctx.register_pairs(src_idx, trg_idx)
+    one = r360.Context(rows, cols, 2, 1, p); one.set_camera(*cam)
+    for k in range(n):
+        one.set_frames(0, np.stack([rgb[2 * k + 1], rgb[2 * k]]), np.stack([dep[2 * k + 1], dep[2 * k]]))
+        r1 = one.register_pairs([0], [1])[0]
+        assert np.array_equal(r1["pose"], res[k]["pose"]) and list(r1["iters"]) == list(res[k]["iters"])
+    one.close(); ctx.close()
+    sph = r360.Context(64, 128, 2, 1, r360.default_params(n_levels=2))
+    with pytest.raises(r360.R360Error):
+        sph.set_camera(*cam)
+    sph.close()
+    with pytest.raises(r360.R360Error):
+        r360.Context(rows, cols, 2, 1, r360.pinhole_params(n_levels=L, occlusion=1))
