@@ -52,6 +52,21 @@ int main() {
         occ_ok = occ_ok && to < 2e-2 && std::fabs(eo - (reg.avPhotoResidual + reg.avDepthResidual)) < 1e-12 &&
                  reg.SSO > 0.5f && reg.SSO <= 1.0f;
     }
+    // pinhole registration through the class surface (RPI.h:254, 4254, 560, 776); the sphere images serve as
+    // generic RGB-D input here -- the numbers only have to be self-consistent
+    reg.setCameraMatrix(200.f, 200.f, 127.5f, 63.5f);
+    reg.alignFrames(RegisterPhotoICP::identity(), RegisterPhotoICP::PHOTO_DEPTH);
+    auto pp = reg.getOptimalPoseArray();
+    const double fe = reg.result().final_error;
+    const double ep = reg.errorPhotoICP(0, pp, RegisterPhotoICP::PHOTO_DEPTH);
+    reg.calcHessGrad(0, pp, RegisterPhotoICP::PHOTO_DEPTH);
+    auto Hh = reg.getHessianArray();
+    std::printf("pinhole: iters %d %d %d, final_error %g, errorPhotoICP at the optimum %g, H00 %g\n", reg.result().iters[0],
+                reg.result().iters[1], reg.result().iters[2], fe, ep, Hh[0]);
+    occ_ok = occ_ok && std::isfinite(ep) && Hh[0] > 0.f && pp[15] == 1.f;
+    reg.alignFrames360(RegisterPhotoICP::identity(), RegisterPhotoICP::PHOTO_DEPTH);          // and back to the sphere
+    auto back = reg.getOptimalPoseArray();
+    for (int k = 0; k < 16; ++k) occ_ok = occ_ok && back[k] == ref.pose[k];
     const bool ok = occ_ok && dmax == 0.0 && terr < 2e-2 && std::fabs(e - reg.result().final_error) < 1e-6 * e;
     std::printf(ok ? "OK\n" : "FAIL\n");
     return ok ? 0 : 1;

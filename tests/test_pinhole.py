@@ -152,48 +152,127 @@ def test_gpu_pinhole_evaluations(orc, r360, gold_pin, name):
         ctx.close()
 
 
+def _lm_primitives(orc):
+    """The update rule of alignFrames from the bit-exact primitives the oracle and the kernels share
+    (rgbd360_b200/csrc/gn_math.h): -> candidate(H21, g6, lam_or_None, pose_estim) = (pose 4x4 f32, update 6 f32, rank)."""
+    import ctypes as C
+    L = orc.lib()
+    L.orc_se3_exp.argtypes = [C.c_void_p, C.c_void_p]
+
+    def ptr(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def full(H21):
+        H = np.zeros((6, 6), np.float32); q = 0
+        for a in range(6):
+            for b in range(a, 6):
+                H[a, b] = H[b, a] = H21[q]; q += 1
+        return H
+
+    def damp(H, lam):
+        Hl = H.copy()
+        for a in range(6):
+            Hl[a, a] = np.float32(H[a, a] + np.float32(lam) * H[a, a])
+        return Hl
+
+    def candidate(H21, g6, lam_solve, lam_rank, pose_estim):
+        H = full(np.asarray(H21, np.float32)); g = np.ascontiguousarray(g6, np.float32)
+        rank = L.orc_rank6(ptr(np.ascontiguousarray(damp(H, lam_rank).T))) if lam_rank is not None else 6
+        Hs = np.ascontiguousarray((damp(H, lam_solve) if lam_solve is not None else H).T)
+        inv = np.zeros(36, np.float32); upd = np.zeros(6, np.float32)
+        L.orc_inverse6(ptr(Hs), ptr(inv)); L.orc_solve_update(ptr(inv), ptr(g), ptr(upd))
+        ud = upd.astype(np.float64); Td = np.zeros(16, np.float64)
+        L.orc_se3_exp(ptr(ud), ptr(Td))
+        Tf = Td.astype(np.float32); Pe = np.ascontiguousarray(np.asarray(pose_estim, np.float32).T).reshape(16)
+        out = np.zeros(16, np.float32)
+        L.orc_mat4_mul(ptr(Tf), ptr(Pe), ptr(out))
+        return out.reshape(4, 4).T.copy(), upd, rank
+    return candidate
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(refcases.PINHOLE_CASES))
 def test_gpu_pinhole_align(orc, r360, gold_pin, name):
-    """alignFrames: every pose the GPU evaluated is replayed through the oracle at the same bits (counters
-    exact, sums 1e-4); control flow, status and final pose against the oracle's own run and against the
-    recorded reference run (1e-4 rad / 1e-4 m)."""
+    """alignFrames (RPI.h:4254-4512) step by step.  Its accept test is `diff_error > 0` on an RMS of float
+    precision, so the reference's own control flow depends on the order in which it sums (STABLE vs FAITHFUL
+    accumulation of the oracle already differ in iteration counts and by millimetres on these cases); parity
+    of the loop is therefore established per step: (1) every pose the GPU evaluated is replayed through the
+    oracle at the same bits -- counters exact, sums 1e-4; (2) given the sums the GPU recorded, every decision
+    and every next pose is what the reference's rule produces, BIT FOR BIT (shared gn_math.h primitives):
+    Gauss-Newton candidate, accept on diff_error > 0 with lambda / 10, one damped retry with lambda * 10,
+    rank test, loop condition, full SE(3) exponential."""
     from util import pose_err
     case = refcases.make_pinhole_case(orc, name)
     orc.set_math(orc.MATH_PINNED)
     P, src, trg = _frames(orc, case)
     ctx = _gpu_ctx(r360, case)
+    candidate = _lm_primitives(orc)
     try:
         L = case["levels"]
         guess = None if case["guess"] is None else r360.pose_to_colmajor(case["guess"])[None]
         res_g, tr_g = ctx.register_pairs([0], [1], guess, trace=True)
         res_g = res_g[0]
-        res_o, tr_o = orc.align_pinhole(src, trg, case["guess"], P, case["cam"], accum=orc.ACC_STABLE, trace=True)
         per = 2 * P.max_iters + 2
-        n_rec = 0
-        for lvl in range(L):
-            for k in range(per):
-                g, o = tr_g[lvl * per + k], tr_o[lvl * per + k]
-                assert bool(g.used) == bool(o.used), (lvl, k)
-                if not g.used:
-                    continue
-                n_rec += 1
-                assert (g.accepted, g.it) == (o.accepted, o.it), (lvl, k)
+        pose_estim = np.eye(4, dtype=np.float32) if case["guess"] is None else np.asarray(case["guess"], np.float32)
+        ill = False
+        for lvl in range(L - 1, -1, -1):
+            recs = [tr_g[lvl * per + k] for k in range(per) if tr_g[lvl * per + k].used]
+            if ill:
+                assert not recs
+                continue
+            for g in recs:                                                        # (1) evaluations
                 T = np.array(g.pose, np.float32).reshape(4, 4).T
-                eo = orc.error_pinhole(src, trg, lvl, T, P, case["cam"])          # replay, same bits
-                assert (g.n_valid, g.n_valid_depth) == (eo["n_photo"], eo["n_depth"]), (lvl, k)
-                assert abs(g.err2 - eo["photo"]) <= REL * abs(eo["photo"]) + 1e-30, (lvl, k)
-                assert abs(g.err2_depth - eo["depth"]) <= REL * abs(eo["depth"]) + 1e-30, (lvl, k)
-        assert n_rec >= 1
+                eo = orc.error_pinhole(src, trg, lvl, T, P, case["cam"])
+                assert (g.n_valid, g.n_valid_depth) == (eo["n_photo"], eo["n_depth"]), (lvl, g.it)
+                assert abs(g.err2 - eo["photo"]) <= REL * abs(eo["photo"]) + 1e-30
+                assert abs(g.err2_depth - eo["depth"]) <= REL * abs(eo["depth"]) + 1e-30
+                assert orc.hessgrad_pinhole(src, trg, lvl, T, P, case["cam"])["n_visible"] == g.n_visible
+            # (2) the state machine, replayed from the recorded sums
+            def errf(g):
+                with np.errstate(all="ignore"):
+                    nd = np.float64(g.n_valid_depth)
+                    return np.float64(np.float32(np.sqrt(np.float64(g.err2) / nd) + np.sqrt(np.float64(g.err2_depth) / nd)))
+            assert recs and recs[0].accepted == 1
+            assert np.array_equal(np.array(recs[0].pose, np.float32).reshape(4, 4).T, pose_estim)
+            error, lam, it, k = errf(recs[0]), 0.01, 0, 1
+            H21, g6 = np.array(recs[0].hessian, np.float32), np.array(recs[0].gradient, np.float32)
+            upd, diff = np.ones(6, np.float32), error
+            while it < P.max_iters and np.float64(np.sqrt(np.float32(np.sum(upd[:3] ** 2, dtype=np.float32) + np.sum(upd[3:] ** 2, dtype=np.float32)))) > P.tol_update \
+                    and diff > P.tol_residual:
+                cand, upd, rank = candidate(H21, g6, None, lam, pose_estim)
+                if rank != 6:
+                    ill = True
+                    break
+                assert k < len(recs), (lvl, k, "the loop condition holds but the GPU stopped")
+                assert np.array_equal(np.array(recs[k].pose, np.float32).reshape(4, 4).T, cand), (lvl, k)
+                diff = error - errf(recs[k])
+                assert recs[k].accepted == int(diff > 0), (lvl, k)
+                if diff > 0:
+                    lam /= 10; pose_estim = cand; error = errf(recs[k]); it += 1
+                    H21, g6 = np.array(recs[k].hessian, np.float32), np.array(recs[k].gradient, np.float32)
+                    k += 1
+                else:
+                    k += 1
+                    if diff < 0:                                                  # one damped retry, RPI.h:4399-4424
+                        lam *= 10
+                        cand, upd, _ = candidate(H21, g6, lam, None, pose_estim)
+                        assert k < len(recs)
+                        assert np.array_equal(np.array(recs[k].pose, np.float32).reshape(4, 4).T, cand), (lvl, k)
+                        diff = error - errf(recs[k])
+                        assert recs[k].accepted == int(diff > 0), (lvl, k)
+                        if diff > 0:
+                            pose_estim = cand; error = errf(recs[k]); it += 1
+                            H21, g6 = np.array(recs[k].hessian, np.float32), np.array(recs[k].gradient, np.float32)
+                        k += 1
+            assert k == len(recs), (lvl, k, len(recs))
+            if not ill:
+                assert res_g["iters"][lvl] == it
         ref = gold_pin[name]["pinned"]
-        assert list(res_g["iters"][:L]) == list(res_o.iters)[:L]
-        assert (res_g["status"] != 0) == (res_o.status != 0) == ref["ill_posed"]
-        Tg = np.array(res_g["pose"], np.float32).reshape(4, 4).T
-        ang, dist = pose_err(Tg, orc.pose_from(res_o.pose))
-        assert ang <= POSE_TOL and dist <= POSE_TOL, (ang, dist)
-        if list(res_o.iters)[:L] == ref["iters"]:
-            ang, dist = pose_err(Tg, np.array(ref["pose"]).reshape(4, 4))
-            assert ang <= POSE_TOL and dist <= POSE_TOL, (ang, dist)
+        assert (res_g["status"] != 0) == ill == ref["ill_posed"]
+        assert np.array_equal(np.array(res_g["pose"], np.float32).reshape(4, 4).T, pose_estim)
+        # against the recorded reference run (float accumulation): same basin, not the same bits
+        ang, dist = pose_err(pose_estim, np.array(ref["pose"]).reshape(4, 4))
+        assert ang <= 1e-2 and dist <= 2e-2, (ang, dist)
     finally:
         ctx.close()
 
