@@ -68,7 +68,9 @@ def allgather_results(local, pair_ids, n_total, device=None):
     world = dist.get_world_size() if dist.is_initialized() else 1
     out = np.zeros(n_total, RESULT_DTYPE)
     if world == 1:
-        out[np.asarray(pair_ids, np.int64)] = local
+        ids = np.asarray(pair_ids, np.int64)
+        out[ids] = local
+        out["pair_id"][ids] = ids
         return out
     dev = torch.device(device) if device is not None else torch.device("cpu")
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
