@@ -570,10 +570,8 @@ k_pass(R360PassArgs a) {
             g.dist = make_float2(fabsf(g2.z), fabsf(g2.w));
             g.rho2 = f2fma(g.py, g.py, f2mul(g.pz, g.pz));
             const bool ok0 = g2.z > 0.f, ok1 = g2.w > 0.f;
-            const unsigned v = r360_rows_pair<METHOD>(g, lv.res_inv, make_float2(g2.x, g2.y), ta, tb, ok0, ok1, P,
-                                                      inv_std_photo, A);
-            n_photo += (int)(v & 1u) + (int)((v >> 1) & 1u);
-            n_depth += (int)((v >> 2) & 1u) + (int)((v >> 3) & 1u);
+            r360_rows_pair<METHOD>(g, lv.res_inv, make_float2(g2.x, g2.y), ta, tb, ok0, ok1, P, inv_std_photo, A,
+                                   &n_photo, &n_depth);
         }
 
         // ---- flush: warp shuffles, one shared-memory stage, 28 double atomics per CTA and pair
