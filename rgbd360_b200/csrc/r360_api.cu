@@ -648,6 +648,8 @@ int r360_register_host_pairs(r360_ctx* c, int n_pairs, const uint8_t* rgb, const
     if (n_pairs < 0 || n_pairs > c->max_pairs || 2 * n_pairs > c->max_frames || !rgb || !depth_mm || !out)
         return fail(c, R360_E_ARG, "register_host_pairs: n_pairs %d needs max_pairs >= n_pairs and max_frames >= 2 n_pairs, non-null buffers", n_pairs);
     if (n_pairs == 0) return R360_OK;
+    if (c->P.projection == R360_PINHOLE && !c->have_cam)
+        return fail(c, R360_E_STATE, "pinhole context: call r360_set_camera first (setCameraMatrix, RPI.h:254)");
     CK(c, cudaSetDevice(c->device));
     const size_t npx = (size_t)c->rows * c->cols;
     for (int p = 0; p < n_pairs; ++p) {                               // allocate before the pipeline starts
