@@ -1,6 +1,7 @@
 // r360_kernels.cu -- hand-written sm_100a kernels of the spherical dense registration path.
 //
-//   K1  k_level0 / k_down / k_texel   pyramids of equirectangular sphere images
+//   K1  k_pyr_head                    level 0 + level-0 target texels + level 1 in one tiled pass over the
+//                                      raw input; k_level0 / k_down / k_texel for the remaining levels
 //                                      (RPI.h:292-354, 365-398, 429-516, 4537-4549)
 //   K3  k_pass<METHOD>                 back-projection, SE(3) warp, spherical re-projection,
 //                                      nearest-neighbour gather, Huber-weighted photometric +
@@ -13,6 +14,8 @@
 //       k_warp_dump                    parity hook: index maps + validity masks
 //       k_synth                        synthetic sphere frames
 //       k_stitch                       Frame360 ingest: 8 sensor images -> sphere RGB8 / depth u16 (Frame360.h:1099-1148)
+//       r360_pinhole.cuh (included at the end): k_pin_eval / k_gn_step_pin, the pinhole alignFrames;
+//       r360_occ.cu: k_occ_scatter / k_occ_eval, the occlusion variants of the spherical path
 //
 // HBM-bound gather/reduction: no tensor cores.  Compiled with --fmad=false (sphere_math.h).
 #include "r360_device.cuh"
