@@ -58,6 +58,9 @@ struct Ctx {
     R360Pair* d_pairs = nullptr;
     double* d_acc = nullptr; int* d_cnt = nullptr;
     int* d_active = nullptr; int* d_nactive = nullptr;
+    int* d_active_err = nullptr;                 // pairs whose next pass is error-only
+    int pass_grid_err = 0;
+    bool speculate = true;                       // R360_SPECULATE=0 in the environment: every pass is the fused one (A/B)
     const float2** h_srcb = nullptr; const float2** d_srcb = nullptr;
     const float** h_trgb = nullptr; const float** d_trgb = nullptr;
     int32_t* h_idx = nullptr; int32_t* d_idx = nullptr;          // src idx | trg idx
@@ -105,7 +108,7 @@ int ensure_trg(Ctx* c, int slot) {
     return R360_OK;
 }
 
-R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint, int first = 0) {
+R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint, int first = 0, bool err_only = false) {
     R360PassArgs a{};
     a.lv = c->lv[level];
     a.params = c->P;
@@ -114,14 +117,14 @@ R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint, int first = 0) {
     // items: the granularity of the contiguous per-CTA runs (>= 8 items per CTA when there is enough work)
     const long long n = c->lv[level].n;
     const long long blk = 2LL * R360_PASS_THREADS;                  // pixels per CTA iteration
-    long long want = n * (long long)std::max(n_pairs_hint, 1) / (8LL * c->pass_grid);
+    long long want = n * (long long)std::max(n_pairs_hint, 1) / (8LL * (err_only ? c->pass_grid_err : c->pass_grid));
     long long ppi = ((want + blk - 1) / blk) * blk;
     ppi = std::min<long long>(std::max<long long>(ppi, blk), 16 * blk);
     a.px_per_item = (int)ppi;
     a.items_per_pair = (int)((n + ppi - 1) / ppi);
     // pair-indexed arrays are addressed relative to `first` (pair ids inside the kernels are batch-local)
-    a.n_active = c->d_nactive;
-    a.active_list = c->d_active + first;
+    a.n_active = err_only ? c->d_nactive + 3 : c->d_nactive;
+    a.active_list = (err_only ? c->d_active_err : c->d_active) + first;
     a.pairs = c->d_pairs + first;
     a.src_base = c->d_srcb + first;
     a.trg_base = c->d_trgb + first;
@@ -141,6 +144,9 @@ R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) 
     g.cnt = c->d_cnt + (size_t)first * R360_ACC_INTS;
     g.active_list = c->d_active + first;
     g.n_active = c->d_nactive;
+    g.active_list_err = c->d_active_err + first;
+    g.n_active_err = c->d_nactive + 3;
+    g.speculate = c->speculate ? 1 : 0;
     g.ticket = c->d_nactive + 2;
     g.trace = trace ? trace + (size_t)first * c->L * trace_per_level(c) : nullptr;
     return g;
@@ -383,6 +389,7 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_l0); cudaFree(c->d_l1); cudaFree(c->d_tex);
     cudaFreeHost(c->h_l0); cudaFreeHost(c->h_l1); cudaFreeHost(c->h_tex);
     cudaFree(c->d_pairs); cudaFree(c->d_acc); cudaFree(c->d_cnt); cudaFree(c->d_active); cudaFree(c->d_nactive);
+    cudaFree(c->d_active_err);
     cudaFree(c->d_srcb); cudaFree(c->d_trgb); cudaFreeHost(c->h_srcb); cudaFreeHost(c->h_trgb);
     cudaFree(c->d_idx); cudaFreeHost(c->h_idx); cudaFree(c->d_pose); cudaFreeHost(c->h_pose);
     cudaFree(c->d_res); cudaFreeHost(c->h_res); cudaFree(c->d_trace);
@@ -410,6 +417,8 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->pass_grid = c->sm_count * R360_PASS_CTAS;
+    c->pass_grid_err = c->sm_count * R360_ERR_CTAS;
+    if (const char* e = getenv("R360_SPECULATE")) c->speculate = atoi(e) != 0;
     CK(c, r360_pass_init());
     CK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
@@ -420,7 +429,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
         CK(c, cudaEventCreateWithFlags(&c->ev_copy[b], cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming));
     }
-    c->ev_pass.resize((size_t)2 * c->L * (params->max_iters + 1));
+    c->ev_pass.resize((size_t)2 * c->L * (params->max_iters + 1 + R360_SPEC_EXTRA));
     for (auto& ev : c->ev_pass) CK(c, cudaEventCreate(&ev));
 
     // ---- per-level geometry and trig tables (RPI.h:2553-2556, 4555-4569), host-computed with
@@ -484,7 +493,8 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaMalloc(&c->d_acc, sizeof(double) * R360_ACC_STRIDE * np));
     CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * R360_ACC_INTS * np));
     CK(c, cudaMalloc(&c->d_active, sizeof(int) * np));
-    CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 4));      // [0] batch, [1] eval hooks, [2] completion ticket
+    CK(c, cudaMalloc(&c->d_active_err, sizeof(int) * np));
+    CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 4));      // [0] batch (fused passes), [1] eval hooks, [2] completion ticket, [3] batch (error-only passes)
     CK(c, cudaMemset(c->d_nactive, 0, sizeof(int) * 4));
     CK(c, cudaMallocHost(&c->h_srcb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_srcb, sizeof(void*) * np));
     CK(c, cudaMallocHost(&c->h_trgb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_trgb, sizeof(void*) * np));
@@ -561,11 +571,17 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
         ++c->launches;
         R360PassArgs a = pass_args(c, level, n, first);
         const bool pin = c->P.projection == R360_PINHOLE;
+        const bool two_lists = !pin && c->P.occlusion == 0 && c->speculate;    // fused + error-only launches
+        R360PassArgs a_err = pass_args(c, level, n, first, true);
         // sphere: 1 initial + <= max_iters loop bodies; pinhole: every loop body may add one damped retry
-        const int n_eval = pin ? 2 * c->P.max_iters + 1 : c->P.max_iters + 1;
+        const int n_eval = pin ? 2 * c->P.max_iters + 1 : c->P.max_iters + 1 + (two_lists ? R360_SPEC_EXTRA : 0);
         for (int k = 0; k < n_eval; ++k) {
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
             launch_evaluation(c, a, n, level);
+            if (two_lists && k > 0) {                                       // the first pass of a level is always fused
+                r360_launch_pass(c->st, a_err, c->pass_grid_err, false);
+                ++c->launches;
+            }
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
             if (pin) r360_launch_gn_step_pin(c->st, g, level);
             else r360_launch_gn_step(c->st, g, level);

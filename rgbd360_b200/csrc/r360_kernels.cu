@@ -435,11 +435,14 @@ __device__ __forceinline__ void r360_cp_async_commit() { asm volatile("cp.async.
 __device__ __forceinline__ void r360_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void r360_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int METHOD>
+// WITH_H = false: the error-only pass (errorPhotoICP_sphere alone) of the pairs whose candidate pose the
+// Gauss-Newton model predicts will end the level: same stage A, same residuals, no Jacobians and no 56
+// accumulator registers -- one more resident CTA per SM.
+template <int METHOD, bool WITH_H>
 #ifdef R360_PASS_MAXNREG
 __global__ void __maxnreg__(R360_PASS_MAXNREG)               // explicit register cap (variant builds)
 #else
-__global__ void __launch_bounds__(R360_PASS_THREADS, R360_PASS_CTAS)
+__global__ void __launch_bounds__(R360_PASS_THREADS, WITH_H ? R360_PASS_CTAS : R360_ERR_CTAS)
 #endif
 k_pass(R360PassArgs a) {
     extern __shared__ float4 s_pipe[];                       // [stage][texel | geometry][thread][3]
@@ -573,15 +576,18 @@ k_pass(R360PassArgs a) {
             g.dist = make_float2(fabsf(g2.z), fabsf(g2.w));
             g.rho2 = f2fma(g.py, g.py, f2mul(g.pz, g.pz));
             const bool ok0 = g2.z > 0.f, ok1 = g2.w > 0.f;
-            r360_rows_pair<METHOD>(g, lv.res_inv, make_float2(g2.x, g2.y), ta, tb, ok0, ok1, P, inv_std_photo, A,
-                                   &n_photo, &n_depth);
+            if (WITH_H)
+                r360_rows_pair<METHOD>(g, lv.res_inv, make_float2(g2.x, g2.y), ta, tb, ok0, ok1, P, inv_std_photo, A,
+                                       &n_photo, &n_depth);
+            else
+                r360_err_pair<METHOD>(g, make_float2(g2.x, g2.y), ta, tb, ok0, ok1, P, inv_std_photo, A.e2, n_photo, n_depth);
         }
 
         // ---- flush: warp shuffles, one shared-memory stage, 28 double atomics per CTA and pair
         float acc[R360_ACC_DOUBLES];
         r360_acc_unpack(A, acc);
 #pragma unroll
-        for (int k = 0; k < R360_ACC_DOUBLES; ++k) {
+        for (int k = WITH_H ? 0 : R360_ACC_DOUBLES - 1; k < R360_ACC_DOUBLES; ++k) {      // error-only: just sum r^2
             float v = acc[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -593,7 +599,7 @@ k_pass(R360PassArgs a) {
         n_fb = __reduce_add_sync(0xffffffffu, n_fb);
         if (lane == 0) { s_cnt[wid][0] = n_vis; s_cnt[wid][1] = n_photo; s_cnt[wid][2] = n_depth; s_cnt[wid][3] = (int)n_fb; }
         __syncthreads();
-        if (threadIdx.x < R360_ACC_DOUBLES) {
+        if (threadIdx.x < R360_ACC_DOUBLES && (WITH_H || threadIdx.x == R360_ACC_DOUBLES - 1)) {
             double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < R360_PASS_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
@@ -712,18 +718,23 @@ __device__ void r360_zero_acc(double* acc, int* cnt, int pair) {
     for (int k = 0; k < R360_ACC_INTS; ++k) cnt[(size_t)pair * R360_ACC_INTS + k] = 0;
 }
 
-// Compacts the active flags of pairs [0, n) into active_list (ascending pair order), one warp.
-__device__ void r360_compact_active(R360Pair* pairs, int n, int* active_list, int* n_active) {
+// Compacts the active flags of pairs [0, n) into the two pass lists (ascending pair order), one warp:
+// pairs whose next pass is the fused one, and pairs whose next pass is error-only.
+__device__ void r360_compact_active(R360Pair* pairs, int n, int* active_list, int* n_active, int* list_err, int* n_err) {
     const int lane = threadIdx.x & 31;
-    int base = 0;
+    int base = 0, base_e = 0;
     for (int p0 = 0; p0 < n; p0 += 32) {
         const int p = p0 + lane;
-        const bool on = p < n && *(volatile int*)&pairs[p].active;
-        const unsigned m = __ballot_sync(0xffffffffu, on);
-        if (on) active_list[base + __popc(m & ((1u << lane) - 1))] = p;
+        const bool act = p < n && *(volatile int*)&pairs[p].active;
+        const bool full = act && *(volatile int*)&pairs[p].want_h;
+        const bool err = act && !full;
+        const unsigned m = __ballot_sync(0xffffffffu, full), me = __ballot_sync(0xffffffffu, err);
+        if (full) active_list[base + __popc(m & ((1u << lane) - 1))] = p;
+        if (err) list_err[base_e + __popc(me & ((1u << lane) - 1))] = p;
         base += __popc(m);
+        base_e += __popc(me);
     }
-    if (lane == 0) *n_active = base;
+    if (lane == 0) { *n_active = base; *n_err = base_e; }
 }
 
 // The last block of a state-machine kernel to finish rebuilds the compact active list (what a
@@ -738,7 +749,7 @@ __device__ void r360_compact_when_last(const R360GnArgs& g) {
     __syncthreads();
     if (s_last) {
         __threadfence();
-        if (threadIdx.x < 32) r360_compact_active(g.pairs, g.n_pairs, g.active_list, g.n_active);
+        if (threadIdx.x < 32) r360_compact_active(g.pairs, g.n_pairs, g.active_list, g.n_active, g.active_list_err, g.n_active_err);
         if (threadIdx.x == 0) *g.ticket = 0;
     }
 }
@@ -755,6 +766,8 @@ __global__ void k_level_begin(R360GnArgs g, int level) {
         ps->it = 0;
         ps->phase = 0;
         ps->ev = 0;
+        ps->want_h = 1;
+        ps->extra = 0;
         ps->active = 1;
     }
     r360_compact_when_last(g);
@@ -789,8 +802,24 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
             n_valid = P.occlusion == 1 ? cnt[1] + cnt[2] : cnt[2];
         }
         ps->passes[level] += 1;
-        double diff_error;
-        int accepted;
+        if (ps->phase == 3) {
+            // The accepted candidate had been evaluated by an error-only pass (its step was predicted to end the
+            // level); this pass is calcHessGrad_sphere at the same pose (RPI.h:4623), the loop goes on.
+            for (int k = 0; k < 21; ++k) ps->Hc[k] = (float)acc[k];
+            for (int k = 0; k < 6; ++k) ps->gc[k] = (float)acc[21 + k];
+            ps->nvis_c = n_vis;
+            if (g.trace && ps->ev >= 1 && ps->ev - 1 < P.max_iters + 2) {
+                r360_iter_record* pr = g.trace + ((size_t)p * P.n_levels + level) * (P.max_iters + 2) + ps->ev - 1;
+                for (int k = 0; k < 21; ++k) pr->hessian[k] = (float)acc[k];
+                for (int k = 0; k < 6; ++k) pr->gradient[k] = (float)acc[21 + k];
+                pr->n_visible = n_vis; pr->used = 3;
+            }
+        }
+        const bool resume = ps->phase == 3;
+        const bool had_h = ps->want_h != 0;                 // what the pass that just ran computed
+        double diff_error = 0.0;
+        int accepted = 0;
+        if (!resume) {
         if (ps->phase == 0) {
             diff_error = err;                               // RPI.h:4605
             accepted = 1;
@@ -809,8 +838,10 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
                 ps->it += 1;
             }
             ps->error = err; ps->err2 = e2; ps->n_valid = n_valid;
-            for (int k = 0; k < 21; ++k) ps->Hc[k] = (float)acc[k];
-            for (int k = 0; k < 6; ++k) ps->gc[k] = (float)acc[21 + k];
+            if (had_h) {
+                for (int k = 0; k < 21; ++k) ps->Hc[k] = (float)acc[k];
+                for (int k = 0; k < 6; ++k) ps->gc[k] = (float)acc[21 + k];
+            }
             ps->nvis_c = n_vis;
         }
         if (rec) {
@@ -820,25 +851,36 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
                 rec->err2 = acc[27]; rec->err2_depth = acc[28];
                 rec->n_valid = P.occlusion == 1 ? cnt[1] : cnt[2]; rec->n_valid_depth = cnt[2];
             }
-            rec->it = ps->it; rec->accepted = accepted; rec->used = 3;
+            rec->it = ps->it; rec->accepted = accepted; rec->used = had_h ? 3 : 1;   // bit 1: normal equations recorded
             for (int k = 0; k < 16; ++k) rec->pose[k] = ps->pose_eval[k];
-            for (int k = 0; k < 21; ++k) rec->hessian[k] = (float)acc[k];
-            for (int k = 0; k < 6; ++k) rec->gradient[k] = (float)acc[21 + k];
+            for (int k = 0; k < 21; ++k) rec->hessian[k] = had_h ? (float)acc[k] : 0.f;
+            for (int k = 0; k < 6; ++k) rec->gradient[k] = had_h ? (float)acc[21 + k] : 0.f;
             rec->pad = 0.f;
         }
+        }   // !resume
         ps->phase = 1;
         r360_zero_acc(g.acc, g.cnt, p);
 
-        // while (it < maxIters && update_pose.norm() > tol_update && diff_error > tol_residual)
-        const float* u = ps->upd;
-        const float na = u[0] * u[0] + (u[1] * u[1] + u[2] * u[2]);
-        const float nb = u[3] * u[3] + (u[4] * u[4] + u[5] * u[5]);
-        const float unorm = sqrtf(na + nb);
-        const bool go = ps->it < P.max_iters && (double)unorm > P.tol_update && diff_error > P.tol_residual;
-        if (!go) {
-            ps->iters[level] = ps->it;                      // RPI.h:4772
-            ps->active = 0;
-            continue;
+        if (!resume) {
+            // while (it < maxIters && update_pose.norm() > tol_update && diff_error > tol_residual)
+            const float* u = ps->upd;
+            const float na = u[0] * u[0] + (u[1] * u[1] + u[2] * u[2]);
+            const float nb = u[3] * u[3] + (u[4] * u[4] + u[5] * u[5]);
+            const float unorm = sqrtf(na + nb);
+            const bool go = ps->it < P.max_iters && (double)unorm > P.tol_update && diff_error > P.tol_residual;
+            if (!go) {
+                ps->iters[level] = ps->it;                  // RPI.h:4772
+                ps->active = 0;
+                continue;
+            }
+            if (!had_h) {
+                // mispredicted: the candidate was accepted and the loop goes on, but its pass was error-only --
+                // run the fused pass at the same pose before the loop body (one extra pass, same results)
+                ps->phase = 3;
+                ps->want_h = 1;
+                ps->extra += 1;
+                continue;
+            }
         }
         // loop body: calcHessGrad_sphere(pose_estim) == (Hc, gc)            RPI.h:4623
         for (int k = 0; k < 21; ++k) ps->Hl[k] = ps->Hc[k];
@@ -869,6 +911,20 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
         for (int k = 0; k < 16; ++k) Tf[k] = (float)Td[k];
         r360_mat4_mul(Tf, ps->pose_estim, Tn);
         for (int k = 0; k < 16; ++k) ps->pose_eval[k] = Tn[k];
+        // Which pass does this candidate need?  The reference evaluates errorPhotoICP_sphere(candidate) and only
+        // if the step is accepted AND the loop goes on calcHessGrad_sphere at the same pose.  The Gauss-Newton
+        // model predicts the new sum of squares, e2 + g^T update (= e2 - g^T H^-1 g); when the predicted RMS
+        // decrease is below tol_residual the step will most likely end the level, so its pass is error-only
+        // (fewer instructions, no accumulator registers).  A misprediction costs one extra fused pass (phase 3)
+        // and changes no result: every decision is still taken on the exactly evaluated error.
+        ps->want_h = 1;
+        if (g.speculate && P.occlusion == 0 && ps->extra < R360_SPEC_EXTRA) {    // the host enqueues max_iters + 1 + R360_SPEC_EXTRA passes
+            double gu = 0.0;
+            for (int k = 0; k < 6; ++k) gu += (double)ps->gc[k] * (double)upd[k];
+            const double e2p = ps->err2 + gu;
+            const double ep = sqrt((e2p > 0.0 ? e2p : 0.0) / (double)ps->n_valid);
+            if (ps->error - ep < P.tol_residual) ps->want_h = 0;
+        }
     }
     r360_compact_when_last(g);
 }
@@ -886,7 +942,7 @@ __global__ void k_pairs_init(R360GnArgs g, const int32_t* __restrict__ src_idx,
         for (int k = 0; k < 6; ++k) { ps->gc[k] = 0.f; ps->gl[k] = 0.f; ps->upd[k] = 1.f; }
         ps->error = 0.0; ps->err2 = 0.0; ps->lambda = 1.0;
         ps->n_valid = 0; ps->nvis_c = 0; ps->nvis_l = 0; ps->lvl_l = -1;
-        ps->it = 0; ps->phase = 0; ps->active = 0; ps->status = R360_PAIR_OK; ps->ev = 0;
+        ps->it = 0; ps->phase = 0; ps->active = 0; ps->status = R360_PAIR_OK; ps->ev = 0; ps->want_h = 1; ps->extra = 0;
         ps->src = src_idx[p]; ps->trg = trg_idx[p];
         for (int k = 0; k < R360_MAX_LEVELS; ++k) { ps->iters[k] = 0; ps->passes[k] = 0; }
     }
@@ -1008,18 +1064,30 @@ void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* d
                                                max_d, r360_mask_geom(cols, n_sensors));
 }
 // The pass kernel's pipeline slots need more than the 48 KB default of dynamic shared memory.
+template <int METHOD, bool WITH_H>
+static cudaError_t r360_pass_attr() {
+    return cudaFuncSetAttribute(k_pass<METHOD, WITH_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_PASS_DYN_SMEM);
+}
 cudaError_t r360_pass_init() {
-    cudaError_t e = cudaFuncSetAttribute(k_pass<R360_PHOTO_CONSISTENCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_PASS_DYN_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass<R360_DEPTH_CONSISTENCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_PASS_DYN_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass<R360_PHOTO_DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_PASS_DYN_SMEM);
+    cudaError_t e = r360_pass_attr<R360_PHOTO_CONSISTENCY, true>();
+    if (e == cudaSuccess) e = r360_pass_attr<R360_DEPTH_CONSISTENCY, true>();
+    if (e == cudaSuccess) e = r360_pass_attr<R360_PHOTO_DEPTH, true>();
+    if (e == cudaSuccess) e = r360_pass_attr<R360_PHOTO_CONSISTENCY, false>();
+    if (e == cudaSuccess) e = r360_pass_attr<R360_DEPTH_CONSISTENCY, false>();
+    if (e == cudaSuccess) e = r360_pass_attr<R360_PHOTO_DEPTH, false>();
     return e;
 }
-void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid) {
+template <bool WITH_H>
+static void r360_launch_pass_t(cudaStream_t st, const R360PassArgs& a, int grid) {
     switch (a.params.method) {
-        case R360_PHOTO_CONSISTENCY: k_pass<R360_PHOTO_CONSISTENCY><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
-        case R360_DEPTH_CONSISTENCY: k_pass<R360_DEPTH_CONSISTENCY><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
-        default: k_pass<R360_PHOTO_DEPTH><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
+        case R360_PHOTO_CONSISTENCY: k_pass<R360_PHOTO_CONSISTENCY, WITH_H><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
+        case R360_DEPTH_CONSISTENCY: k_pass<R360_DEPTH_CONSISTENCY, WITH_H><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
+        default: k_pass<R360_PHOTO_DEPTH, WITH_H><<<grid, R360_PASS_THREADS, R360_PASS_DYN_SMEM, st>>>(a); break;
     }
+}
+void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid, bool with_h) {
+    if (with_h) r360_launch_pass_t<true>(st, a, grid);
+    else r360_launch_pass_t<false>(st, a, grid);
 }
 void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
                            uint8_t* vp, uint8_t* vd, int sm_count) {

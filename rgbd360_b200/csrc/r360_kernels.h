@@ -15,6 +15,9 @@
 #ifndef R360_PASS_CTAS
 #define R360_PASS_CTAS 2                      // resident CTAs per SM of k_pass (persistent grid = CTAS x SMs)
 #endif
+#ifndef R360_ERR_CTAS
+#define R360_ERR_CTAS 3                       // resident CTAs per SM of the error-only pass (no 56 accumulator registers)
+#endif
 
 struct R360PassArgs {
     R360Level lv;
@@ -48,9 +51,12 @@ struct R360GnArgs {
     R360Pair* pairs;
     double* acc;
     int* cnt;
-    int* active_list;
+    int* active_list;                   // pairs whose next pass is the fused one (error + normal equations)
     int* n_active;
-    int* ticket;                        // device: block-completion counter (the last block compacts the active list)
+    int* active_list_err;               // pairs whose next pass is error-only (speculation of k_gn_step)
+    int* n_active_err;
+    int speculate;                      // 0: every pass is the fused one
+    int* ticket;                        // device: block-completion counter (the last block compacts the active lists)
     r360_iter_record* trace;            // device or nullptr
 };
 
@@ -65,7 +71,7 @@ void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* d
                           float2* const* l0_dst, float2* const* l1_dst, float* const* texel_dst, int rows, int cols,
                           float min_d, float max_d, int n_sensors, int n_frames);
 cudaError_t r360_pass_init();
-void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid);
+void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid, bool with_h = true);
 // occlusion variants (r360_occ.cu): head / next / dinv hold n_pairs * lv.n entries each
 void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, int* head, int* next, float* dinv,
                           int sm_count);

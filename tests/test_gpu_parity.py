@@ -131,6 +131,14 @@ def _check_align(orc, res_g, tr_g, res_o, tr_o, P, src, trg):
             assert abs(g.err2 - e2r) <= REL * abs(e2r), (lvl, k)
             hr = orc.hessgrad(src, trg, lvl, pose_g, P)
             assert hr["n_visible"] == g.n_visible
+            if not (g.used & 2):
+                # error-only pass: this candidate was predicted (Gauss-Newton model) to end the level, so the
+                # kernel did not form its normal equations -- exactly as the reference, which calls
+                # calcHessGrad_sphere at a pose only when the loop goes on
+                # (such a record is always the last of its level: had the loop gone on, the fused pass at the
+                # same pose would have filled it in)
+                assert k == max(kk for kk in range(per) if tr_g[lvl * per + kk].used), (lvl, k)
+                continue
             Ho = upper21(hr["H"].astype(np.float64)); Hg = np.array(g.hessian, np.float64)
             dg = np.diag(hr["H"]).astype(np.float64)
             sc = upper21(np.sqrt(np.outer(dg, dg)))
