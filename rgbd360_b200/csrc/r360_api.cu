@@ -61,6 +61,7 @@ struct Ctx {
     int* d_active_err = nullptr;                 // pairs whose next pass is error-only
     int pass_grid_err = 0;
     bool speculate = true;                       // R360_SPECULATE=0 in the environment: every pass is the fused one (A/B)
+    float spec_margin = 1.0f;                    // R360_SPEC_MARGIN: threshold of the prediction in units of tol_residual (A/B)
     const float2** h_srcb = nullptr; const float2** d_srcb = nullptr;
     const float** h_trgb = nullptr; const float** d_trgb = nullptr;
     int32_t* h_idx = nullptr; int32_t* d_idx = nullptr;          // src idx | trg idx
@@ -147,6 +148,7 @@ R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) 
     g.active_list_err = c->d_active_err + first;
     g.n_active_err = c->d_nactive + 3;
     g.speculate = c->speculate ? 1 : 0;
+    g.spec_margin = c->spec_margin;
     g.ticket = c->d_nactive + 2;
     g.trace = trace ? trace + (size_t)first * c->L * trace_per_level(c) : nullptr;
     return g;
@@ -419,7 +421,9 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     c->pass_grid = c->sm_count * R360_PASS_CTAS;
     c->pass_grid_err = c->sm_count * R360_ERR_CTAS;
     if (const char* e = getenv("R360_SPECULATE")) c->speculate = atoi(e) != 0;
+    if (const char* e = getenv("R360_SPEC_MARGIN")) c->spec_margin = (float)atof(e);
     CK(c, r360_pass_init());
+    if (params->occlusion != 0) CK(c, r360_occ_init());
     CK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
     CK(c, cudaEventCreate(&c->ev_t0));
@@ -506,6 +510,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
         const size_t n = (size_t)c->occ_cap * npx;
         CK(c, cudaMalloc(&c->occ_head, sizeof(int) * n));
         CK(c, cudaMalloc(&c->occ_next, sizeof(int) * n));
+        CK(c, cudaMemset(c->occ_next, 0xFF, sizeof(int) * n));      // k_occ_eval loads a pixel's own link before it knows whether the pixel is listed
         CK(c, cudaMalloc(&c->occ_dinv, sizeof(float) * n));
     }
     CK(c, cudaMalloc(&c->d_cams, sizeof(float) * 12 * kChunkFrames)); CK(c, cudaMallocHost(&c->h_cams, sizeof(float) * 12 * kChunkFrames));

@@ -413,28 +413,6 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
 #define R360_SLOT_BYTES 48                                   // texels of 2 pixels = geometry of 2 pixels = 48 B
 #define R360_PASS_DYN_SMEM (R360_PASS_STAGES * 2 * R360_PASS_THREADS * R360_SLOT_BYTES)
 
-// Shared-memory accesses of the pipeline go through explicit 32-bit shared addresses held in a
-// register (the compiler otherwise re-derives them from %tid every iteration).
-__device__ __forceinline__ unsigned r360_smem_addr(const void* p) {
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("" : "+r"(a));
-    return a;
-}
-__device__ __forceinline__ void r360_cp_async8(unsigned smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void r360_sts128(unsigned smem, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 r360_lds128(unsigned smem) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem) : "memory");
-    return v;
-}
-__device__ __forceinline__ void r360_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void r360_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void r360_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // WITH_H = false: the error-only pass (errorPhotoICP_sphere alone) of the pairs whose candidate pose the
 // Gauss-Newton model predicts will end the level: same stage A, same residuals, no Jacobians and no 56
 // accumulator registers -- one more resident CTA per SM.
@@ -490,11 +468,20 @@ k_pass(R360PassArgs a) {
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 s_cur = i < p_end ? __ldg(&src4[i >> 1]) : zero4;
         float4 s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
+#ifdef R360_PREFETCH_TAB
+        float2 tp_n;                                                 // trig-table entries of the next stage A,
+        float4 tt_n;                                                 // loaded one stage ahead (variant build)
+        r360_load_tabs(lv, r, c, tp_n, tt_n);
+#endif
 
         // stage A: index of pixel pair (i, i+1), async gathers + geometry into slot `st`
         auto stage_a = [&](unsigned st) {                            // st: byte offset of the stage
             R360SrcPair sp;
+#ifdef R360_PREFETCH_TAB
+            r360_load_src_pair(lv, P, s_cur, tp_n, tt_n, i < p_end, i + 1 < p_end, sp);
+#else
             r360_load_src_pair(lv, P, s_cur, r, c, i < p_end, i + 1 < p_end, sp);
+#endif
             R360Geo2 g;
             int rr[2], cc[2];
 #ifdef R360_T_IN_REGS
@@ -529,6 +516,9 @@ k_pass(R360PassArgs a) {
             r += lv.stride_r;
             c += lv.stride_c;
             if (c >= lv.cols) { c -= lv.cols; ++r; }
+#ifdef R360_PREFETCH_TAB
+            r360_load_tabs(lv, r, c, tp_n, tt_n);
+#endif
         };
 
         // prologue: pixel pairs 0 .. STAGES-2 in flight before the first stage B
@@ -923,7 +913,7 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
             for (int k = 0; k < 6; ++k) gu += (double)ps->gc[k] * (double)upd[k];
             const double e2p = ps->err2 + gu;
             const double ep = sqrt((e2p > 0.0 ? e2p : 0.0) / (double)ps->n_valid);
-            if (ps->error - ep < P.tol_residual) ps->want_h = 0;
+            if (ps->error - ep < P.tol_residual * (double)g.spec_margin) ps->want_h = 0;
         }
     }
     r360_compact_when_last(g);

@@ -56,6 +56,7 @@ struct R360GnArgs {
     int* active_list_err;               // pairs whose next pass is error-only (speculation of k_gn_step)
     int* n_active_err;
     int speculate;                      // 0: every pass is the fused one
+    float spec_margin;                  // error-only when the predicted RMS decrease < spec_margin * tol_residual (1: the plain rule)
     int* ticket;                        // device: block-completion counter (the last block compacts the active lists)
     r360_iter_record* trace;            // device or nullptr
 };
@@ -73,6 +74,7 @@ void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* d
 cudaError_t r360_pass_init();
 void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid, bool with_h = true);
 // occlusion variants (r360_occ.cu): head / next / dinv hold n_pairs * lv.n entries each
+cudaError_t r360_occ_init();
 void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, int* head, int* next, float* dinv,
                           int sm_count);
 // pinhole registration (r360_pinhole.cuh)
