@@ -18,7 +18,7 @@ namespace {
 std::string g_create_error;
 
 #ifndef R360_CHUNK_FRAMES
-#define R360_CHUNK_FRAMES 64
+#define R360_CHUNK_FRAMES 128
 #endif
 constexpr int kChunkFrames = R360_CHUNK_FRAMES;     // max frames per pyramid-build launch / H2D staging buffer
 constexpr int kStages = 4;           // staging buffers: the copy stream runs up to kStages - 1 chunks ahead
@@ -322,7 +322,7 @@ void launch_evaluation(Ctx* c, const R360PassArgs& a, int n_pairs, int level) {
         ++c->launches;
     } else {
         r360_launch_occ_pass(c->st, a, n_pairs, c->occ_head, c->occ_next, c->occ_dinv, c->sm_count);
-        c->launches += 2;
+        c->launches += 3;
     }
 }
 

@@ -79,6 +79,17 @@ __device__ __forceinline__ bool r360_occ_candidate(bool inb, float depth2, float
     return inb;
 }
 
+// Empties the candidate lists of the ACTIVE pairs (a memset over the whole batch would also pay for the pairs that
+// have already converged: every level enqueues max_iters + 1 evaluations whatever the number of active pairs).
+__global__ void __launch_bounds__(R360_OCC_THREADS)
+k_occ_reset(R360PassArgs a, int* __restrict__ head) {
+    const int ap = blockIdx.y;
+    if (ap >= *a.n_active) return;
+    int2* h = reinterpret_cast<int2*>(head + (size_t)ap * a.lv.n);          // lv.n is even at every level
+    const int n2 = a.lv.n >> 1;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += gridDim.x * blockDim.x) h[q] = make_int2(-1, -1);
+}
+
 template <int OCC>
 __global__ void __launch_bounds__(R360_OCC_THREADS)
 k_occ_scatter(R360PassArgs a, int* __restrict__ head, int* __restrict__ next, float* __restrict__ dinv) {
@@ -468,8 +479,8 @@ static dim3 occ_grid(const R360PassArgs& a, int n_pairs, int sm_count) {
 // pose_eval: list heads reset, scatter, evaluate.  scratch: head | next | dinv, each n_pairs * lv.n.
 void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, int* head, int* next, float* dinv,
                           int sm_count) {
-    cudaMemsetAsync(head, 0xFF, sizeof(int) * (size_t)n_pairs * a.lv.n, st);
     const dim3 grid = occ_grid(a, n_pairs, sm_count);
+    k_occ_reset<<<grid, R360_OCC_THREADS, 0, st>>>(a, head);
     const int occ = a.params.occlusion;
     if (occ == 1) k_occ_scatter<1><<<grid, R360_OCC_THREADS, 0, st>>>(a, head, next, dinv);
     else k_occ_scatter<2><<<grid, R360_OCC_THREADS, 0, st>>>(a, head, next, dinv);
