@@ -227,6 +227,18 @@ int r360_stitch_frames(r360_ctx* ctx, const r360_rig* rig, int first, int n, con
                        const uint16_t* sensor_depth_mm, const uint8_t* roles, uint8_t* sphere_rgb,
                        uint16_t* sphere_depth_mm);
 
+/* Multi-GPU: the path shards by pairs, one r360_ctx (and one NCCL rank) per GPU; the only exchange is
+ * ONE all-gather of the fixed-size result records over NVLink / NVSwitch.  `nccl_comm` is the caller's ncclComm_t for
+ * this ctx's device.  NCCL is resolved at run time -- the ncclAllGather already loaded in the host process, else
+ * dlopen("libnccl.so.2") -- so this library carries no NCCL dependency; R360_E_STATE when none is found.
+ * local: n_local records (host); all: n_ranks * n_local records (host), rank-major.  Every rank passes the same
+ * n_local (pad a ragged last shard with records whose pair_id is -1, as rgbd360_b200/shard.py does).  Collective: every rank of the
+ * communicator must call it; returns after the gathered records are in `all`.
+ * Replaces nothing upstream (the reference registers its pairs one after another on one host, LoopClosure360.h:291-321,
+ * OdometryRGBD360.cpp:185-193); it returns what those loops accumulate. */
+int r360_allgather_results(r360_ctx* ctx, void* nccl_comm, const r360_result* local, int n_local, int n_ranks,
+                           r360_result* all);
+
 /* Device memory / stream plumbing for callers that keep data on the GPU. */
 int r360_device_alloc(r360_ctx* ctx, size_t bytes, void** ptr_dev);
 int r360_device_free(r360_ctx* ctx, void* ptr_dev);

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <dlfcn.h>
 #include "r360_kernels.h"
 #include "synth.h"
 
@@ -72,6 +73,7 @@ struct Ctx {
     int* occ_head = nullptr; int* occ_next = nullptr; float* occ_dinv = nullptr;   // occlusion 1/2: per-texel candidate lists
     int occ_cap = 0;                                                                // pairs the scratch holds
     float cam[4] = {0.f, 0.f, 0.f, 0.f}; bool have_cam = false;                     // setCameraMatrix (pinhole contexts)
+    uint8_t* d_gather = nullptr; size_t gather_cap = 0;                             // r360_allgather_results: send | receive records
     uint8_t* d_sens_rgb = nullptr; uint16_t* d_sens_depth = nullptr; size_t sens_cap = 0;   // ingest: sensor images of one chunk
     // stats
     float last_ms = 0.f, pass_ms = 0.f;
@@ -80,6 +82,29 @@ struct Ctx {
     int64_t launches = 0;
     std::string err;
 };
+
+// NCCL entry points, resolved at run time: the library the host process already uses (a C++ host links it, a
+// Python host has it loaded by torch), else the system libnccl.  No link-time dependency.
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*NcclErrorStringFn)(int);
+struct NcclApi { NcclAllGatherFn all_gather = nullptr; NcclErrorStringFn error_string = nullptr; };
+NcclApi load_nccl() {
+    NcclApi api;
+    void* f = dlsym(RTLD_DEFAULT, "ncclAllGather");
+    void* e = f ? dlsym(RTLD_DEFAULT, "ncclGetErrorString") : nullptr;
+    if (!f) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) { f = dlsym(h, "ncclAllGather"); e = dlsym(h, "ncclGetErrorString"); }
+    }
+    api.all_gather = reinterpret_cast<NcclAllGatherFn>(f);
+    api.error_string = reinterpret_cast<NcclErrorStringFn>(e);
+    return api;
+}
+const NcclApi& nccl_api() {
+    static const NcclApi api = load_nccl();          // thread-safe initialisation: ranks may be host threads
+    return api;
+}
 
 int fail(Ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -396,7 +421,7 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_idx); cudaFreeHost(c->h_idx); cudaFree(c->d_pose); cudaFreeHost(c->h_pose);
     cudaFree(c->d_res); cudaFreeHost(c->h_res); cudaFree(c->d_trace);
     cudaFree(c->d_cams); cudaFreeHost(c->h_cams);
-    cudaFree(c->d_sens_rgb); cudaFree(c->d_sens_depth);
+    cudaFree(c->d_sens_rgb); cudaFree(c->d_sens_depth); cudaFree(c->d_gather);
     cudaFree(c->occ_head); cudaFree(c->occ_next); cudaFree(c->occ_dinv);
     for (auto e : c->ev_pass) cudaEventDestroy(e);
     for (int b = 0; b < kStages; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
@@ -1001,6 +1026,33 @@ int r360_stitch_frames(r360_ctx* c, const r360_rig* rig, int first, int n, const
 }
 
 void r360_synth_gt_pose(int kind, int src_id, int trg_id, double T[16]) { r360_synth_relpose(kind, src_id, trg_id, T); }
+
+int r360_allgather_results(r360_ctx* c, void* nccl_comm, const r360_result* local, int n_local, int n_ranks, r360_result* all) {
+    if (!c) return R360_E_ARG;
+    if (!nccl_comm || n_local < 0 || n_ranks < 1 || (n_local > 0 && (!local || !all)))
+        return fail(c, R360_E_ARG, "allgather_results: null communicator / buffer or bad counts (n_local %d, n_ranks %d)", n_local, n_ranks);
+    if (n_local == 0) return R360_OK;
+    const NcclApi& nccl = nccl_api();
+    if (!nccl.all_gather) return fail(c, R360_E_STATE, "allgather_results: no NCCL in this process and libnccl.so.2 not found");
+    CK(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(r360_result) * (size_t)n_local;
+    const size_t need = bytes * ((size_t)n_ranks + 1);
+    if (c->gather_cap < need) {
+        if (c->d_gather) cudaFree(c->d_gather);
+        c->d_gather = nullptr; c->gather_cap = 0;
+        CK(c, cudaMalloc(&c->d_gather, need));
+        c->gather_cap = need;
+    }
+    uint8_t* d_in = c->d_gather;
+    uint8_t* d_out = c->d_gather + bytes;
+    CK(c, cudaMemcpyAsync(d_in, local, bytes, cudaMemcpyHostToDevice, c->st));
+    const int rc = nccl.all_gather(d_in, d_out, bytes, /*ncclUint8*/ 1, nccl_comm, c->st);
+    if (rc != 0)
+        return fail(c, R360_E_CUDA, "ncclAllGather failed: %s", nccl.error_string ? nccl.error_string(rc) : "unknown NCCL error");
+    CK(c, cudaMemcpyAsync(all, d_out, bytes * (size_t)n_ranks, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    return R360_OK;
+}
 
 int r360_device_alloc(r360_ctx* c, size_t bytes, void** ptr_dev) {
     if (!c || !ptr_dev) return R360_E_ARG;

@@ -21,6 +21,7 @@ EXPORTS = [
     "r360_last_pass_stats", "r360_version", "r360_index_stats", "r360_register_host_pairs",
     "r360_default_rig", "r360_frame360_parse", "r360_stitch_frames", "r360_eval_error_occ",
     "r360_default_params_pinhole", "r360_set_camera", "r360_eval_error_pinhole",
+    "r360_allgather_results",
 ]
 
 
@@ -133,6 +134,7 @@ def lib():
     L.r360_default_rig.restype = None
     L.r360_frame360_parse.argtypes = [vp, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, C.c_size_t, vp, C.c_size_t]
     L.r360_stitch_frames.argtypes = [vp, C.POINTER(Rig), i32, i32, vp, vp, vp, vp, vp]
+    L.r360_allgather_results.argtypes = [vp, vp, vp, i32, i32, vp]
     _lib = L
     return L
 
