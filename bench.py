@@ -259,6 +259,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.one_step:
+        # profiling aid (ncu launch lists / captures): exactly ONE resident step, no warm-up, no e2e leg, no JSON
+        # line -- the launch list of this command is the launch list of a step.  Never a bench number.
+        step_resident()
+        barrier()
+        sys.stderr.write("one step: %d launches, %.2f ms on the device (cold)\n" % (ctx.kernel_launches(), ctx.last_device_ms()))
+        ctx.close()
+        return
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -419,6 +427,8 @@ def main():
     ap.add_argument("--workload", default="A", choices=list(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--one-step", action="store_true",
+                    help="profiling aid: run exactly one resident step (no warm-up, no e2e, no JSON line) and exit")
     ap.add_argument("--occlusion", type=int, default=0, choices=[0, 1, 2],
                     help="alignFrames360's occlusion argument (side measurement; the headline metric is occlusion 0, "
                          "whose fused pass the roofline object describes -- with 1 / 2 that object is empty)")
