@@ -349,7 +349,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_pass<PHOTO_DEPTH> (fused warp/residual/normal-equation pass)",
+            "roofline": {"bound": "hbm", "kernel": "k_pass<PHOTO_DEPTH, WITH_H> (warp/residual/normal-equation pixel passes: the fused launches and the speculative error-only ones, 32 B per source pixel each)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,
                          "traffic": (t_ratio * pass_bytes / max(pass_launches, 1)) if t_ratio else None,
