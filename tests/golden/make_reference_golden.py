@@ -138,8 +138,12 @@ def run_reference_pinhole(case, pinned):
             H, g = R.hessgrad_pinhole(0, T, case["method"])
             probes.append(dict(pose=np.asarray(T, np.float64).ravel().tolist(), error=_f(e), av_photo=_f(avp), av_depth=_f(avd),
                                H=H.astype(np.float64).ravel().tolist(), g=g.astype(np.float64).tolist()))
-        if not any(a["iters"]) and not np.isfinite(probes[0]["error"] if probes[0]["error"] is not None else np.nan):
-            out["H"] = out["g"] = None   # the loop never ran: uninitialised members
+        # The loop body runs at a level only if the error at the level's starting pose is finite (the `while`
+        # compares diff_error = error).  When it is NaN (0/0: no valid pixel) at EVERY level the pose never leaves the
+        # guess, calcHessGrad is never called and the getters return the class's uninitialised members.
+        start = case["guess"] if case["guess"] is not None else np.eye(4, dtype=np.float32)
+        if not any(a["iters"]) and not any(np.isfinite(R.error_pinhole(l, start, case["method"])[0]) for l in range(case["levels"])):
+            out["H"] = out["g"] = None
     out["probes_level0"] = probes
     R.close()
     return out

@@ -48,6 +48,11 @@ OCC_CASES = ["synth_128x256_L3_pd", "synth_256x512_L4_pd_far", "synth_128x256_L3
 def test_oracle_occlusion_equals_recorded_reference(orc, gold_occ, name, occ, pinned):
     case = refcases.make_case(orc, name)
     ref = gold_occ[name][str(occ)]["pinned" if pinned else "libm"]
+    _check_oracle_occ_against_reference(orc, case, ref, occ, pinned)
+
+
+def _check_oracle_occ_against_reference(orc, case, ref, occ, pinned):
+    """Oracle vs one reference record (recorded or live) of an occlusion run, bit for bit at one thread."""
     orc.set_math(orc.MATH_PINNED if pinned else orc.MATH_LIBM)
     orc.lib().orc_set_threads(1)
     try:
@@ -88,6 +93,22 @@ def test_live_reference_occlusion_matches_recording(orc, gold_occ):
         for occ in (1, 2):
             live = m.run_reference_occ(case, True, occ)
             assert json.loads(json.dumps(live)) == gold_occ[name][str(occ)]["pinned"], (name, occ)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_occlusion_equals_live_reference_on_random_cases(orc, seed):
+    """Seeded random problems through the compiled reference HERE (one thread) and through the oracle."""
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    import importlib.util
+    from test_reference import _random_case
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(GOLD, "make_reference_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    case = _random_case(orc, 500 + seed)
+    occ, pinned = 1 + (seed & 1), bool(seed & 2)
+    live = json.loads(json.dumps(m.run_reference_occ(case, pinned, occ)))
+    _check_oracle_occ_against_reference(orc, case, live, occ, pinned)
 
 
 def test_occlusion_semantics_properties(orc):

@@ -42,6 +42,11 @@ def _frames(orc, case):
 def test_oracle_pinhole_equals_recorded_reference(orc, gold_pin, name, pinned):
     case = refcases.make_pinhole_case(orc, name)
     ref = gold_pin[name]["pinned" if pinned else "libm"]
+    _check_oracle_pinhole_against_reference(orc, case, ref, pinned)
+
+
+def _check_oracle_pinhole_against_reference(orc, case, ref, pinned):
+    """Oracle vs one reference record (recorded or live) of a pinhole run, bit for bit at one thread."""
     orc.set_math(orc.MATH_PINNED if pinned else orc.MATH_LIBM)
     orc.lib().orc_set_threads(1)
     try:
@@ -79,6 +84,44 @@ def test_live_reference_pinhole_matches_recording(orc, gold_pin):
         case = refcases.make_pinhole_case(orc, name)
         live = m.run_reference_pinhole(case, True)
         assert json.loads(json.dumps(live)) == gold_pin[name]["pinned"], name
+
+
+def _random_pinhole_case(orc, seed):
+    """A seeded random pinhole problem: resolution (QVGA or half of it, intrinsics scaled), pyramid depth, cost
+    function, views of either scene, optional holes, optional perturbed / ground-truth-based guess."""
+    rng = np.random.default_rng(7000 + seed)
+    levels = int(rng.integers(1, 5))
+    half = rng.random() < 0.5 and levels <= 3
+    rows, cols = (120, 160) if half else (240, 320)
+    cam = tuple(v * (0.5 if half else 1.0) for v in refcases.PINHOLE_CAM)
+    kind = int(rng.integers(0, 2))
+    a = int(rng.integers(0, 30)); b = a + int(rng.integers(1, 3))
+    rgb_t, d_t = orc.synth_pinhole_frame(kind, a, rows, cols, *cam)
+    rgb_s, d_s = orc.synth_pinhole_frame(kind, b, rows, cols, *cam)
+    if rng.random() < 0.5:
+        rgb_s, d_s, rgb_t, d_t = refcases._holes(rgb_s, d_s, rgb_t, d_t, int(rng.integers(0, 1 << 30)))
+    u = rng.random()
+    guess = None
+    if u < 0.3:
+        guess = refcases.small_guess(int(rng.integers(0, 1 << 30)))
+    elif u < 0.65:
+        guess = (refcases.small_guess(int(rng.integers(0, 1 << 30))).astype(np.float64) @ orc.synth_gt_pose(kind, b, a)).astype(np.float32)
+    return dict(rgb_s=rgb_s, d_s=d_s, rgb_t=rgb_t, d_t=d_t, levels=levels, method=int(rng.integers(0, 3)), guess=guess, cam=cam)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_pinhole_equals_live_reference_on_random_cases(orc, seed):
+    """Seeded random problems through the compiled reference HERE (one thread) and through the oracle."""
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(GOLD, "make_reference_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    case = _random_pinhole_case(orc, seed)
+    pinned = bool(seed & 1)
+    live = json.loads(json.dumps(m.run_reference_pinhole(case, pinned)))
+    _check_oracle_pinhole_against_reference(orc, case, live, pinned)
 
 
 def test_pinhole_exponential_is_the_full_se3_exp(orc):

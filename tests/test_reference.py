@@ -56,6 +56,12 @@ def _trace_in_call_order(tr, levels):
 def test_oracle_equals_recorded_reference(orc, gold, name, pinned):
     case = refcases.make_case(orc, name)
     ref = gold[name]["pinned" if pinned else "libm"]
+    _check_oracle_against_reference(orc, case, ref, pinned)
+
+
+def _check_oracle_against_reference(orc, case, ref, pinned):
+    """The oracle run on `case` against one reference record (recorded or live): planes, LUT, counters and
+    iteration counts exactly, error2 to 1e-12, pose / Hessian / gradient / SSO bit for bit at one thread."""
     try:
         P, src, trg, res, tr = _oracle_run(orc, case, pinned)
         L = case["levels"]
@@ -110,6 +116,48 @@ def test_live_reference_library_matches_recording(orc, gold):
             live = m.run_reference(case, pinned)
             rec = gold[name]["pinned" if pinned else "libm"]
             assert json.loads(json.dumps(live)) == rec, (name, pinned)
+
+
+def _random_case(orc, seed):
+    """A seeded random registration problem: size, pyramid depth, cost function, frames of either scene,
+    optional holes / colour noise, optional perturbed or ground-truth-based guess."""
+    rng = np.random.default_rng(1000 + seed)
+    levels = int(rng.integers(1, 5))
+    rows = int(rng.choice([32, 48, 64, 96, 128])) * (1 << max(levels - 2, 0))
+    rows = min(rows, 256)
+    rows -= rows % (1 << (levels - 1))
+    cols = 2 * rows if rng.random() < 0.7 else 3 * rows        # the sample frames are 6 : 1, the synthetic ones 2 : 1
+    cols -= cols % (8 << (levels - 1))                          # 8 sensor joints at every level
+    kind = int(rng.integers(0, 2))
+    a = int(rng.integers(0, 40)); b = a + int(rng.integers(1, 4))
+    rgb_t, d_t = orc.synth_frame(kind, a, rows, cols)
+    rgb_s, d_s = orc.synth_frame(kind, b, rows, cols)
+    if rng.random() < 0.5:
+        rgb_s, d_s, rgb_t, d_t = refcases._holes(rgb_s, d_s, rgb_t, d_t, int(rng.integers(0, 1 << 30)))
+    u = rng.random()
+    guess = None
+    if u < 0.35:
+        guess = refcases.small_guess(int(rng.integers(0, 1 << 30)))
+    elif u < 0.7:
+        guess = (refcases.small_guess(int(rng.integers(0, 1 << 30))).astype(np.float64) @ orc.synth_gt_pose(kind, b, a)).astype(np.float32)
+    return dict(rgb_s=rgb_s, d_s=d_s, rgb_t=rgb_t, d_t=d_t, levels=levels, method=int(rng.integers(0, 3)), guess=guess,
+                std_photo=float(rng.choice([6.0 / 255, 3.0 / 255])))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_oracle_equals_live_reference_on_random_cases(orc, seed):
+    """Beyond the recorded cases: seeded random problems run through the compiled reference HERE (container only:
+    /root/reference does not travel) and through the oracle, compared like the recorded ones."""
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(GOLD, "make_reference_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    case = _random_case(orc, seed)
+    pinned = bool(seed & 1)
+    live = json.loads(json.dumps(m.run_reference(case, pinned)))
+    _check_oracle_against_reference(orc, case, live, pinned)
 
 
 def test_reference_multithreaded_reduction_within_tolerance(orc, gold):
