@@ -7,6 +7,8 @@ nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
 stamp tests
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+stamp "opt-in tests written at the end of round 1 without GPU minutes (random problems replayed through the oracle)"
+R360_TEST_RANDOM_GPU=1 timeout 600 python -m pytest tests/test_gpu_random.py -m gpu -q 2>&1 | tail -15
 stamp bench
 timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cut -c1-400 gpurun_out/bench.json
 stamp "launch list of one step (512 pairs)"
@@ -21,3 +23,4 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_py
     python bench.py --one-step --pairs 128 > gpurun_out/b_ncu3.log 2>&1
 stamp done
 ls -la gpurun_out
+# then, on two GPUs:  gpurun --gpus 2 -- 'R360_TEST_MULTI_GPU=1 python -m pytest tests/test_multi_gpu.py -m gpu -q'
