@@ -113,10 +113,19 @@ class BatchRegistrar {
 
     /*! Sequence odometry over resident frames [first, first+n): pair k = (target first+k, source first+k+1),
      *  guess Identity; returns n-1 robot-frame edges. */
-    std::vector<Edge> odometry(int first, int n) {
+    std::vector<Edge> odometry(int first, int n) { return odometry(first, n, nullptr); }
+    /*! Same with one robot-frame guess per pair (n-1 of them).  The reference seeds pair k with the previous pair's
+     *  result (rigidTransf_dense, OdometryRGBD360.cpp:191) -- a serial dependency a batched call cannot have; callers
+     *  with a motion prior pass it here, nullptr = Identity (MethodsRegisterRGBD360.cpp:448). */
+    std::vector<Edge> odometry(int first, int n, const std::vector<Pose>* robot_guess) {
         std::vector<int32_t> s, t;
+        std::vector<float> g;
         for (int k = 0; k + 1 < n; ++k) { t.push_back(first + k); s.push_back(first + k + 1); }
-        return registerPairs(s, t, nullptr);
+        if (robot_guess) {
+            if (robot_guess->size() != s.size()) throw std::invalid_argument("odometry: one guess per pair (n - 1)");
+            for (const Pose& P : *robot_guess) { const Pose gi = toSphereFrame(P); g.insert(g.end(), gi.begin(), gi.end()); }
+        }
+        return registerPairs(s, t, robot_guess ? g.data() : nullptr);
     }
     /*! Loop-closure candidates over resident keyframes: (compare id = SOURCE, new id = TARGET) as
      *  LoopClosure360.h:308-309; robot_guess[i] = relativePose of candidate i in the robot frame. */

@@ -239,6 +239,17 @@ int r360_stitch_frames(r360_ctx* ctx, const r360_rig* rig, int first, int n, con
 int r360_allgather_results(r360_ctx* ctx, void* nccl_comm, const r360_result* local, int n_local, int n_ranks,
                            r360_result* all);
 
+/* Pinned host staging memory for the frames a caller hands to r360_set_frames / r360_register_host_pairs
+ * (the reference's callers hold them as cv::Mat, OdometryRGBD360.cpp:185-193), placed on the NUMA node the
+ * ctx's GPU hangs off: with one rank per GPU all uploading at once, staging memory on the wrong socket
+ * halves the host-to-device rate.  The node comes from the GPU's PCI entry in sysfs; the pages are bound
+ * with mbind(2) when the process may, else first-touched by this thread pinned to the node's CPUs, then
+ * page-locked with cudaHostRegister.  *numa_node: the node the first page actually sits on afterwards
+ * (get_mempolicy), or -1 when the platform exposes no NUMA topology for the device (single node, VM) -- then
+ * the memory is plain cudaHostAlloc memory and r360_last_error(ctx) says why.  Free with r360_host_free. */
+int r360_host_alloc(r360_ctx* ctx, size_t bytes, void** ptr, int32_t* numa_node);
+int r360_host_free(r360_ctx* ctx, void* ptr);
+
 /* Device memory / stream plumbing for callers that keep data on the GPU. */
 int r360_device_alloc(r360_ctx* ctx, size_t bytes, void** ptr_dev);
 int r360_device_free(r360_ctx* ctx, void* ptr_dev);

@@ -11,12 +11,18 @@
 #include <vector>
 #include <algorithm>
 #include <dlfcn.h>
+#include <cctype>
+#include <map>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include "r360_kernels.h"
 #include "synth.h"
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;     // r360_create failures (no ctx yet); ranks may be host threads
 
 #ifndef R360_CHUNK_FRAMES
 #define R360_CHUNK_FRAMES 128
@@ -43,6 +49,9 @@ struct Ctx {
     // frame slots
     std::vector<float2*> src;                    // {depth, gray} pyramids
     std::vector<float*> trg;                     // texel pyramids
+    // which pyramid of a slot holds the frame LAST set there: an allocation outlives a re-set with a narrower
+    // role, its content must not be used afterwards (check_pair / dump_* test these, not the pointers)
+    std::vector<uint8_t> have_src, have_trg;
     float2* scratch = nullptr;                   // `chunk` source-format pyramids (target-only frames)
     uint8_t* stage_rgb[kStages]{};
     uint16_t* stage_depth[kStages]{};            // also holds float depth (sized for it)
@@ -57,7 +66,7 @@ struct Ctx {
     float** h_tex = nullptr; float** d_tex = nullptr;
     // pair batch
     R360Pair* d_pairs = nullptr;
-    double* d_acc = nullptr; int* d_cnt = nullptr;
+    R360Fx* d_acc = nullptr; int* d_cnt = nullptr;     // per pair: R360_ACC_STRIDE fixed-point sums, R360_ACC_INTS counters
     int* d_active = nullptr; int* d_nactive = nullptr;
     int* d_active_err = nullptr;                 // pairs whose next pass is error-only
     int pass_grid_err = 0;
@@ -73,6 +82,7 @@ struct Ctx {
     int* occ_head = nullptr; int* occ_next = nullptr; float* occ_dinv = nullptr;   // occlusion 1/2: per-texel candidate lists
     int occ_cap = 0;                                                                // pairs the scratch holds
     float cam[4] = {0.f, 0.f, 0.f, 0.f}; bool have_cam = false;                     // setCameraMatrix (pinhole contexts)
+    std::map<void*, std::pair<size_t, bool>> host_allocs;                           // r360_host_alloc: ptr -> (bytes, mmap'ed + registered?)
     uint8_t* d_gather = nullptr; size_t gather_cap = 0;                             // r360_allgather_results: send | receive records
     uint8_t* d_sens_rgb = nullptr; uint16_t* d_sens_depth = nullptr; size_t sens_cap = 0;   // ingest: sensor images of one chunk
     // stats
@@ -186,6 +196,8 @@ int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t
     for (int k = 0; k < n; ++k) {
         const int slot = first + k;
         const int role = roles ? roles[k] : R360_ROLE_BOTH;
+        c->have_src[slot] = (role & R360_ROLE_SOURCE) ? 1 : 0;
+        c->have_trg[slot] = (role & R360_ROLE_TARGET) ? 1 : 0;
         if (role & R360_ROLE_SOURCE) {
             int rc = ensure_src(c, slot);
             if (rc) return rc;
@@ -293,8 +305,8 @@ int set_frames_impl(Ctx* c, int first, int n, const uint8_t* rgb, const void* de
 int check_pair(Ctx* c, int src, int trg) {
     if (src < 0 || src >= c->max_frames || trg < 0 || trg >= c->max_frames)
         return fail(c, R360_E_ARG, "frame index out of range (src %d, trg %d, %d slots)", src, trg, c->max_frames);
-    if (!c->src[src]) return fail(c, R360_E_STATE, "frame %d has no source pyramid (r360_set_frames with a SOURCE role first)", src);
-    if (!c->trg[trg]) return fail(c, R360_E_STATE, "frame %d has no target pyramid (r360_set_frames with a TARGET role first)", trg);
+    if (!c->have_src[src]) return fail(c, R360_E_STATE, "frame %d has no source pyramid (r360_set_frames with a SOURCE role first)", src);
+    if (!c->have_trg[trg]) return fail(c, R360_E_STATE, "frame %d has no target pyramid (r360_set_frames with a TARGET role first)", trg);
     return R360_OK;
 }
 
@@ -318,7 +330,7 @@ int eval_setup(Ctx* c, int src, int trg, int level, const float pose[16], R360Pa
     const int one = 1;
     CK(c, cudaMemcpyAsync(c->d_active + slot, &slot, sizeof(int), cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(c->d_nactive + 1, &one, sizeof(int), cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemsetAsync(c->d_acc + (size_t)slot * R360_ACC_STRIDE, 0, sizeof(double) * R360_ACC_STRIDE, c->st));
+    CK(c, cudaMemsetAsync(c->d_acc + (size_t)slot * R360_ACC_STRIDE, 0, sizeof(R360Fx) * R360_ACC_STRIDE, c->st));
     CK(c, cudaMemsetAsync(c->d_cnt + (size_t)slot * R360_ACC_INTS, 0, sizeof(int) * R360_ACC_INTS, c->st));
     CK(c, cudaStreamSynchronize(c->st));    // hp / sb / tb are stack variables
     *a = pass_args(c, level, 1);
@@ -359,9 +371,11 @@ int eval_pass(Ctx* c, int src, int trg, int level, const float pose[16], double 
     launch_evaluation(c, a, 1, level);
     CK(c, cudaGetLastError());
     const int slot = c->max_pairs;
-    CK(c, cudaMemcpyAsync(acc, c->d_acc + (size_t)slot * R360_ACC_STRIDE, sizeof(double) * R360_ACC_STRIDE, cudaMemcpyDeviceToHost, c->st));
+    R360Fx fx[R360_ACC_STRIDE];
+    CK(c, cudaMemcpyAsync(fx, c->d_acc + (size_t)slot * R360_ACC_STRIDE, sizeof(R360Fx) * R360_ACC_STRIDE, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaMemcpyAsync(cnt, c->d_cnt + (size_t)slot * R360_ACC_INTS, sizeof(int) * R360_ACC_INTS, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaStreamSynchronize(c->st));
+    for (int k = 0; k < R360_ACC_STRIDE; ++k) acc[k] = k < R360_ACC_DOUBLES + 1 ? r360_fx_get(fx, k) : 0.0;
     return R360_OK;
 }
 
@@ -423,6 +437,10 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_cams); cudaFreeHost(c->h_cams);
     cudaFree(c->d_sens_rgb); cudaFree(c->d_sens_depth); cudaFree(c->d_gather);
     cudaFree(c->occ_head); cudaFree(c->occ_next); cudaFree(c->occ_dinv);
+    for (auto& kv : c->host_allocs) {
+        if (kv.second.second) { cudaHostUnregister(kv.first); munmap(kv.first, kv.second.first); }
+        else cudaFreeHost(kv.first);
+    }
     for (auto e : c->ev_pass) cudaEventDestroy(e);
     for (int b = 0; b < kStages; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -503,6 +521,8 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
 
     c->src.assign(max_frames, nullptr);
     c->trg.assign(max_frames, nullptr);
+    c->have_src.assign(max_frames, 0);
+    c->have_trg.assign(max_frames, 0);
     const size_t npx = (size_t)rows * cols;
     CK(c, cudaMalloc(&c->scratch, sizeof(float2) * c->px_total * c->chunk));
     for (int b = 0; b < kStages; ++b) {
@@ -519,7 +539,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
 
     const int np = max_pairs + 1;     // + 1 spare slot for the eval hooks
     CK(c, cudaMalloc(&c->d_pairs, sizeof(R360Pair) * np));
-    CK(c, cudaMalloc(&c->d_acc, sizeof(double) * R360_ACC_STRIDE * np));
+    CK(c, cudaMalloc(&c->d_acc, sizeof(R360Fx) * R360_ACC_STRIDE * np));
     CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * R360_ACC_INTS * np));
     CK(c, cudaMalloc(&c->d_active, sizeof(int) * np));
     CK(c, cudaMalloc(&c->d_active_err, sizeof(int) * np));
@@ -563,6 +583,10 @@ int r360_create(r360_ctx** out, int device, int rows, int cols, int max_frames, 
     if (params->method < 0 || params->method > 2) return fail(nullptr, R360_E_ARG, "r360_create: bad method %d", params->method);
     if (params->max_iters < 1 || params->max_iters > 64) return fail(nullptr, R360_E_ARG, "r360_create: max_iters %d not in [1,64]", params->max_iters);
     if ((long long)rows * cols >= (1LL << 27)) return fail(nullptr, R360_E_ARG, "r360_create: image too large");
+    // the kernels split a pixel index into (row, col) by multiplication with ceil(2^40 / cols): exact while
+    // index * cols < 2^40, or for any index when cols is a power of two
+    if (cols > 8192 && (cols & (cols - 1)) != 0)
+        return fail(nullptr, R360_E_ARG, "r360_create: cols %d > 8192 must be a power of two", cols);
     r360_ctx* c = new r360_ctx;
     int rc = create_impl(c, device, rows, cols, max_frames, max_pairs, params);
     if (rc) { g_create_error = c->err; r360_destroy(c); return rc; }
@@ -814,8 +838,8 @@ int r360_dump_level(r360_ctx* c, int frame, int level, float* gray, float* depth
     CK(c, cudaSetDevice(c->device));
     const R360Level& v = c->lv[level];
     const bool want_grad = ggx || ggy || dgx || dgy;
-    if (want_grad && !c->trg[frame]) return fail(c, R360_E_STATE, "dump_level: frame %d has no target pyramid", frame);
-    if (c->trg[frame]) {
+    if (want_grad && !c->have_trg[frame]) return fail(c, R360_E_STATE, "dump_level: frame %d has no target pyramid", frame);
+    if (c->have_trg[frame]) {
         std::vector<float> buf((size_t)v.n * R360_TEXEL_FLOATS);
         CK(c, cudaMemcpy(buf.data(), c->trg[frame] + v.px_off * R360_TEXEL_FLOATS, buf.size() * sizeof(float), cudaMemcpyDeviceToHost));
         for (int i = 0; i < v.n; ++i) {
@@ -827,7 +851,7 @@ int r360_dump_level(r360_ctx* c, int frame, int level, float* gray, float* depth
             if (dgx) dgx[i] = t[4];
             if (dgy) dgy[i] = t[5];
         }
-    } else if (c->src[frame]) {
+    } else if (c->have_src[frame]) {
         std::vector<float2> buf(v.n);
         CK(c, cudaMemcpy(buf.data(), c->src[frame] + v.px_off, buf.size() * sizeof(float2), cudaMemcpyDeviceToHost));
         for (int i = 0; i < v.n; ++i) { if (depth) depth[i] = buf[i].x; if (gray) gray[i] = buf[i].y; }
@@ -841,7 +865,7 @@ int r360_dump_level(r360_ctx* c, int frame, int level, float* gray, float* depth
 int r360_dump_source_level(r360_ctx* c, int frame, int level, float* gray, float* depth) {
     if (!c) return R360_E_ARG;
     if (frame < 0 || frame >= c->max_frames || level < 0 || level >= c->L) return fail(c, R360_E_ARG, "dump_source_level: bad frame/level");
-    if (!c->src[frame]) return fail(c, R360_E_STATE, "dump_source_level: frame %d has no source pyramid", frame);
+    if (!c->have_src[frame]) return fail(c, R360_E_STATE, "dump_source_level: frame %d has no source pyramid", frame);
     CK(c, cudaSetDevice(c->device));
     const R360Level& v = c->lv[level];
     std::vector<float2> buf(v.n);
@@ -1051,6 +1075,99 @@ int r360_allgather_results(r360_ctx* c, void* nccl_comm, const r360_result* loca
         return fail(c, R360_E_CUDA, "ncclAllGather failed: %s", nccl.error_string ? nccl.error_string(rc) : "unknown NCCL error");
     CK(c, cudaMemcpyAsync(all, d_out, bytes * (size_t)n_ranks, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaStreamSynchronize(c->st));
+    return R360_OK;
+}
+
+// NUMA node of the ctx's GPU from sysfs (-1: not exposed), and the CPUs of that node.
+static int gpu_numa_node(r360_ctx* c, std::string* why) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), c->device) != cudaSuccess) { *why = "cudaDeviceGetPCIBusId failed"; return -1; }
+    for (char* p = bus; *p; ++p) *p = (char)tolower(*p);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) { *why = path + " not readable"; return -1; }
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) *why = path + " = -1 (the platform exposes no NUMA node for this device)";
+    return node;
+}
+static bool node_cpus(int node, cpu_set_t* set) {
+    char path[96];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    CPU_ZERO(set);
+    int a, b, n = 0;
+    while (fscanf(f, "%d", &a) == 1) {
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') { if (fscanf(f, "%d", &b) != 1) break; ch = fgetc(f); }
+        for (int k = a; k <= b && k < CPU_SETSIZE; ++k) { CPU_SET(k, set); ++n; }
+        if (ch != ',') break;
+    }
+    fclose(f);
+    return n > 0;
+}
+
+int r360_host_alloc(r360_ctx* c, size_t bytes, void** ptr, int32_t* numa_node) {
+    if (!c || !ptr || bytes == 0) return R360_E_ARG;
+    *ptr = nullptr;
+    if (numa_node) *numa_node = -1;
+    CK(c, cudaSetDevice(c->device));
+    std::string why;
+    const int node = gpu_numa_node(c, &why);
+    if (node < 0) {
+        CK(c, cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+        c->host_allocs[*ptr] = std::make_pair(bytes, false);
+        c->err = "host_alloc: no NUMA placement: " + why;
+        return R360_OK;
+    }
+    const size_t page = 2u << 20;
+    const size_t len = (bytes + page - 1) / page * page;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return fail(c, R360_E_NOMEM, "host_alloc: mmap of %zu bytes failed", len);
+    // bind the range to the node (needs no privilege for the caller's own memory; seccomp profiles may refuse it) ...
+    unsigned long mask[16] = {0};
+    bool bound = false;
+    if (node < (int)(sizeof(mask) * 8)) {
+        mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
+        bound = syscall(SYS_mbind, p, len, /*MPOL_BIND*/ 2, mask, sizeof(mask) * 8, 0) == 0;
+    }
+    // ... and first-touch the pages from a CPU of that node (the default policy then places them there)
+    cpu_set_t old_set, node_set;
+    const bool have_old = sched_getaffinity(0, sizeof(old_set), &old_set) == 0;
+    bool pinned = false;
+    if (have_old && node_cpus(node, &node_set)) {
+        cpu_set_t both;
+        CPU_AND(&both, &old_set, &node_set);
+        if (CPU_COUNT(&both) > 0) pinned = sched_setaffinity(0, sizeof(both), &both) == 0;
+    }
+    for (size_t off = 0; off < len; off += 4096) ((volatile char*)p)[off] = 0;
+    if (pinned) sched_setaffinity(0, sizeof(old_set), &old_set);
+    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { munmap(p, len); return fail(c, R360_E_CUDA, "host_alloc: cudaHostRegister: %s", cudaGetErrorString(e)); }
+    int where = -1;
+    if (syscall(SYS_get_mempolicy, &where, nullptr, 0UL, p, /*MPOL_F_NODE | MPOL_F_ADDR*/ 3UL) != 0) where = -1;
+    if (numa_node) *numa_node = where;
+    char note[256];
+    snprintf(note, sizeof(note), "host_alloc: GPU %d on NUMA node %d; mbind %s, first touch %s; first page on node %d", c->device, node,
+             bound ? "ok" : "refused", pinned ? "from a CPU of the node" : "from the caller's CPU (affinity excludes the node)", where);
+    c->err = note;
+    c->host_allocs[p] = std::make_pair(len, true);
+    *ptr = p;
+    return R360_OK;
+}
+
+int r360_host_free(r360_ctx* c, void* p) {
+    if (!c) return R360_E_ARG;
+    if (!p) return R360_OK;
+    auto it = c->host_allocs.find(p);
+    if (it == c->host_allocs.end()) return fail(c, R360_E_ARG, "host_free: pointer was not returned by r360_host_alloc of this ctx");
+    CK(c, cudaSetDevice(c->device));
+    if (it->second.second) { cudaHostUnregister(p); munmap(p, it->second.first); }
+    else cudaFreeHost(p);
+    c->host_allocs.erase(it);
     return R360_OK;
 }
 

@@ -32,8 +32,9 @@ k_level0(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_mm,
     const uint8_t* c = rgb + (size_t)f * n_px * 3;
     float2* out = dst[f];
     const float gs = (float)(1. / 255), ds = (float)0.001;
-    // 4 pixels per thread: 12 B of RGB as 3 x u32, 8 B of depth as uint2
-    const int n4 = n_px >> 2;
+    // 4 pixels per thread: 12 B of RGB as 3 x u32, 8 B of depth as uint2.  The vector loads of frame f start at
+    // f * n_px * {3, 2, 4} bytes: aligned for every frame only when n_px is a multiple of 4 (else: the scalar loop)
+    const int n4 = (n_px & 3) ? 0 : n_px >> 2;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
         const uint32_t* c4 = reinterpret_cast<const uint32_t*>(c) + 3 * (size_t)q;
         uint32_t w0 = __ldg(c4), w1 = __ldg(c4 + 1), w2 = __ldg(c4 + 2);
@@ -400,7 +401,7 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
 // Work decomposition: the (active pair, pixel block) space is cut into `items` of px_per_item
 // pixels; every CTA of the persistent grid takes one CONTIGUOUS run of items, so it touches one
 // or two pairs, keeps its 28 packed partial sums in registers across the whole run and flushes
-// them (warp shuffles + shared memory + 28 double atomics) once per pair it touched.
+// them (warp shuffles + shared memory + 28 order-independent fixed-point atomic sums, r360_fx_add) once per pair it touched.
 //
 // Per thread and iteration one pixel pair, software-pipelined through shared memory in two stages:
 //   stage A (pair k+1): LDG.128 of {depth, gray} x 2 (loaded two iterations ahead), back-projection,
@@ -573,7 +574,7 @@ k_pass(R360PassArgs a) {
                 r360_err_pair<METHOD>(g, make_float2(g2.x, g2.y), ta, tb, ok0, ok1, P, inv_std_photo, A.e2, n_photo, n_depth);
         }
 
-        // ---- flush: warp shuffles, one shared-memory stage, 28 double atomics per CTA and pair
+        // ---- flush: warp shuffles, one shared-memory stage, 28 fixed-point atomic sums per CTA and pair (order-independent)
         float acc[R360_ACC_DOUBLES];
         r360_acc_unpack(A, acc);
 #pragma unroll
@@ -593,7 +594,7 @@ k_pass(R360PassArgs a) {
             double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < R360_PASS_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
-            atomicAdd(&a.acc[(size_t)pair * R360_ACC_STRIDE + threadIdx.x], sum);
+            r360_fx_add(a.acc + (size_t)pair * R360_ACC_STRIDE, threadIdx.x, sum);
         } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
             int sum = 0;
 #pragma unroll
@@ -703,8 +704,8 @@ k_index_stats(R360PassArgs a, int pair, unsigned long long* __restrict__ out) {
 }
 
 // =========================================================================== K4: Gauss-Newton state machine
-__device__ void r360_zero_acc(double* acc, int* cnt, int pair) {
-    for (int k = 0; k < R360_ACC_STRIDE; ++k) acc[(size_t)pair * R360_ACC_STRIDE + k] = 0.0;
+__device__ void r360_zero_acc(R360Fx* acc, int* cnt, int pair) {
+    for (int k = 0; k < R360_ACC_STRIDE; ++k) { acc[(size_t)pair * R360_ACC_STRIDE + k].lo = 0ull; acc[(size_t)pair * R360_ACC_STRIDE + k].hi = 0ll; }
     for (int k = 0; k < R360_ACC_INTS; ++k) cnt[(size_t)pair * R360_ACC_INTS + k] = 0;
 }
 
@@ -773,7 +774,8 @@ __global__ void k_gn_step(R360GnArgs g, int level) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
         R360Pair* ps = g.pairs + p;
         if (!ps->active) continue;
-        const double* acc = g.acc + (size_t)p * R360_ACC_STRIDE;
+        double acc[R360_ACC_DOUBLES + 1];
+        for (int k = 0; k < R360_ACC_DOUBLES + 1; ++k) acc[k] = r360_fx_get(g.acc + (size_t)p * R360_ACC_STRIDE, k);
         const int* cnt = g.cnt + (size_t)p * R360_ACC_INTS;
         const int n_vis = cnt[0];
         double e2, err;

@@ -30,7 +30,7 @@ struct R360PassArgs {
     const R360Pair* pairs;              // device
     const float2* const* src_base;      // device: per pair, source pyramid {depth, gray}
     const float* const* trg_base;       // device: per pair, target texel pyramid
-    double* acc;                        // device: per pair R360_ACC_STRIDE doubles
+    R360Fx* acc;                        // device: per pair R360_ACC_STRIDE fixed-point sums (r360_fx_add / r360_fx_get)
     int* cnt;                           // device: per pair R360_ACC_INTS
 };
 
@@ -49,7 +49,7 @@ struct R360GnArgs {
     r360_params params;
     int n_pairs;
     R360Pair* pairs;
-    double* acc;
+    R360Fx* acc;
     int* cnt;
     int* active_list;                   // pairs whose next pass is the fused one (error + normal equations)
     int* n_active;

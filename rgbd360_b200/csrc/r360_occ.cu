@@ -339,7 +339,7 @@ k_occ_eval(R360PassArgs a, const int* __restrict__ head, const int* __restrict__
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < R360_OCC_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
-        atomicAdd(&a.acc[(size_t)pair * R360_ACC_STRIDE + threadIdx.x], sum);
+        r360_fx_add(a.acc + (size_t)pair * R360_ACC_STRIDE, threadIdx.x, sum);
     } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
         int sum = 0;
 #pragma unroll
@@ -443,7 +443,7 @@ k_occ_eval_simple(R360PassArgs a, const int* __restrict__ head, const int* __res
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < R360_OCC_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
-        atomicAdd(&a.acc[(size_t)pair * R360_ACC_STRIDE + threadIdx.x], sum);
+        r360_fx_add(a.acc + (size_t)pair * R360_ACC_STRIDE, threadIdx.x, sum);
     } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
         int sum = 0;
 #pragma unroll

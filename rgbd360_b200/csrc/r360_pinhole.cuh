@@ -136,7 +136,7 @@ k_pin_eval(R360PassArgs a, R360PinLevel pl) {
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < R360_PIN_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
-        atomicAdd(&a.acc[(size_t)pair * R360_ACC_STRIDE + threadIdx.x], sum);
+        r360_fx_add(a.acc + (size_t)pair * R360_ACC_STRIDE, threadIdx.x, sum);
     } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
         int sum = 0;
 #pragma unroll
@@ -165,7 +165,8 @@ __global__ void k_gn_step_pin(R360GnArgs g, int level) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
         R360Pair* ps = g.pairs + p;
         if (!ps->active) continue;
-        const double* acc = g.acc + (size_t)p * R360_ACC_STRIDE;
+        double acc[R360_ACC_DOUBLES + 1];
+        for (int k = 0; k < R360_ACC_DOUBLES + 1; ++k) acc[k] = r360_fx_get(g.acc + (size_t)p * R360_ACC_STRIDE, k);
         const int* cnt = g.cnt + (size_t)p * R360_ACC_INTS;
         const double n_d = (double)cnt[2];
         // avResidual is a float member (RPI.h:183): the value alignFrames compares has float precision

@@ -72,9 +72,18 @@ class BatchRegistrar:
                      SSO=float(r["sso"]), status=int(r["status"]), iterations=list(r["iters"][:self.params.n_levels]))
                 for s, t, r in zip(src, trg, res)]
 
-    def odometry(self, first, n):
+    def odometry(self, first, n, robot_guesses=None):
+        """Edges (k+1 -> k) of frames [first, first + n).  robot_guesses: optional n-1 robot-frame guesses.  The
+        reference seeds pair k with the PREVIOUS pair's result (rigidTransf_dense, OdometryRGBD360.cpp:191), a serial
+        dependency a batched call cannot have: the default here is Identity (the alternative the reference's own
+        driver offers, MethodsRegisterRGBD360.cpp:448); callers with a motion prior pass it explicitly."""
         trg = np.arange(first, first + n - 1, dtype=np.int32)
-        return self._edges(trg + 1, trg, None)
+        g = None
+        if robot_guesses is not None:
+            if len(robot_guesses) != n - 1:
+                raise ValueError(f"{len(robot_guesses)} guesses for {n - 1} pairs")
+            g = np.stack([pose_to_colmajor(to_sphere_frame(G)) for G in robot_guesses])
+        return self._edges(trg + 1, trg, g)
 
     def loop_closures(self, candidates, robot_guesses):
         src = np.array([c[0] for c in candidates], np.int32)

@@ -21,7 +21,7 @@ EXPORTS = [
     "r360_last_pass_stats", "r360_version", "r360_index_stats", "r360_register_host_pairs",
     "r360_default_rig", "r360_frame360_parse", "r360_stitch_frames", "r360_eval_error_occ",
     "r360_default_params_pinhole", "r360_set_camera", "r360_eval_error_pinhole",
-    "r360_allgather_results",
+    "r360_allgather_results", "r360_host_alloc", "r360_host_free",
 ]
 
 
@@ -135,6 +135,8 @@ def lib():
     L.r360_frame360_parse.argtypes = [vp, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, C.c_size_t, vp, C.c_size_t]
     L.r360_stitch_frames.argtypes = [vp, C.POINTER(Rig), i32, i32, vp, vp, vp, vp, vp]
     L.r360_allgather_results.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.r360_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.r360_host_free.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -244,10 +246,23 @@ class Context:
             raise R360Error(f"r360 error {rc}: {self.L.r360_last_error(self.h).decode()}")
 
     # ---- frames
+    def _check_frames(self, first, n, roles):
+        if n < 0 or first < 0 or first + n > self.max_frames:
+            raise ValueError(f"frames [{first}, {first + n}) outside the {self.max_frames} slots of the context")
+        if roles is not None and roles.size != n:
+            raise ValueError(f"roles has {roles.size} entries for {n} frames")
+
     def set_frames(self, first, rgb, depth, roles=None):
         rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth = np.asarray(depth)
         n = rgb.shape[0] if rgb.ndim == 4 else 1
         r = None if roles is None else np.ascontiguousarray(roles, np.uint8)
+        # the C library reads n * rows * cols [* 3] elements from raw pointers: check here, raise here
+        if rgb.shape[-3:] != (self.rows, self.cols, 3) or rgb.ndim not in (3, 4):
+            raise ValueError(f"rgb has shape {rgb.shape}, expected [n x] {self.rows} x {self.cols} x 3")
+        if depth.size != n * self.rows * self.cols or depth.shape[-2:] != (self.rows, self.cols):
+            raise ValueError(f"depth has shape {depth.shape}, expected [{n} x] {self.rows} x {self.cols}")
+        self._check_frames(first, n, r)
         if depth.dtype == np.uint16:
             d = np.ascontiguousarray(depth)
             self._ck(self.L.r360_set_frames(self.h, first, n, _p(rgb), _p(d), _p(r)))
@@ -258,6 +273,7 @@ class Context:
     def set_frames_ptr(self, first, n, rgb_ptr, depth_ptr, roles=None, device=False):
         """Raw-pointer form (host pinned buffers or device pointers)."""
         r = None if roles is None else np.ascontiguousarray(roles, np.uint8)
+        self._check_frames(first, n, r)
         fn = self.L.r360_set_frames_dev if device else self.L.r360_set_frames
         self._ck(fn(self.h, first, n, _p(rgb_ptr), _p(depth_ptr), _p(r)))
 
@@ -267,6 +283,10 @@ class Context:
         sensor_rgb = np.ascontiguousarray(sensor_rgb, np.uint8); sensor_depth = np.ascontiguousarray(sensor_depth, np.uint16)
         n = sensor_rgb.shape[0]
         r = None if roles is None else np.ascontiguousarray(roles, np.uint8)
+        if sensor_rgb.shape != (n, 8, rig.sensor_rows, rig.sensor_cols, 3) or sensor_depth.shape != (n, 8, rig.sensor_rows, rig.sensor_cols):
+            raise ValueError(f"sensor images have shapes {sensor_rgb.shape} / {sensor_depth.shape}, expected "
+                             f"n x 8 x {rig.sensor_rows} x {rig.sensor_cols} [x 3]")
+        self._check_frames(first, n, r)
         srgb = np.zeros((n, self.rows, self.cols, 3), np.uint8) if want_sphere else None
         sdep = np.zeros((n, self.rows, self.cols), np.uint16) if want_sphere else None
         self._ck(self.L.r360_stitch_frames(self.h, C.byref(rig), first, n, _p(sensor_rgb), _p(sensor_depth), _p(r),
@@ -283,14 +303,29 @@ class Context:
         self._ck(self.L.r360_synth_frames_dev(self.h, kind, first_id, n, _p(rgb_ptr), _p(depth_ptr)))
 
     # ---- registration
+    @staticmethod
+    def _check_out(out, n):
+        if out is None:
+            return np.zeros(n, RESULT_DTYPE)
+        if not isinstance(out, np.ndarray) or out.dtype != RESULT_DTYPE or out.size < n or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a contiguous array of >= {n} RESULT_DTYPE records")
+        return out
+
     def register_pairs(self, src_idx, trg_idx, init_pose=None, trace=False, out=None):
         s = np.ascontiguousarray(src_idx, np.int32)
         t = np.ascontiguousarray(trg_idx, np.int32)
         n = s.size
-        res = out if out is not None else np.zeros(n, RESULT_DTYPE)
+        if t.size != n:
+            raise ValueError(f"src_idx has {n} entries, trg_idx {t.size}")
+        if n > self.max_pairs:
+            raise ValueError(f"{n} pairs exceed max_pairs = {self.max_pairs}")
+        res = self._check_out(out, n)
         ip = None
         if init_pose is not None:
-            ip = np.ascontiguousarray(init_pose, np.float32).reshape(n, 16)
+            ip = np.ascontiguousarray(init_pose, np.float32)
+            if ip.size != 16 * n:
+                raise ValueError(f"init_pose has {ip.size} floats, expected {n} x 16")
+            ip = ip.reshape(n, 16)
         tr = None
         if trace:
             per = (2 * self.params.max_iters + 2) if self.params.projection == 1 else (self.params.max_iters + 2)
@@ -307,8 +342,18 @@ class Context:
         if not isinstance(rgb, int):
             rgb = np.ascontiguousarray(rgb, np.uint8)
             depth_mm = np.ascontiguousarray(depth_mm, np.uint16)
-        res = out if out is not None else np.zeros(n_pairs, RESULT_DTYPE)
-        ip = None if init_pose is None else np.ascontiguousarray(init_pose, np.float32).reshape(n_pairs, 16)
+            if rgb.shape != (2 * n_pairs, self.rows, self.cols, 3) or depth_mm.shape != (2 * n_pairs, self.rows, self.cols):
+                raise ValueError(f"frames have shapes {rgb.shape} / {depth_mm.shape}, expected "
+                                 f"{2 * n_pairs} x {self.rows} x {self.cols} [x 3]")
+        if n_pairs > self.max_pairs or 2 * n_pairs > self.max_frames:
+            raise ValueError(f"{n_pairs} pairs need max_pairs >= {n_pairs} and max_frames >= {2 * n_pairs}")
+        res = self._check_out(out, n_pairs)
+        ip = None
+        if init_pose is not None:
+            ip = np.ascontiguousarray(init_pose, np.float32)
+            if ip.size != 16 * n_pairs:
+                raise ValueError(f"init_pose has {ip.size} floats, expected {n_pairs} x 16")
+            ip = ip.reshape(n_pairs, 16)
         self._ck(self.L.r360_register_host_pairs(self.h, n_pairs, _p(rgb), _p(depth_mm), _p(ip), _p(res)))
         return res
 
@@ -374,6 +419,27 @@ class Context:
         T = pose_to_colmajor(pose)
         self._ck(self.L.r360_index_stats(self.h, src, trg, level, _p(T), _p(out)))
         return dict(valid=int(out[0]), scalar=int(out[1]), mismatch=int(out[2]))
+
+    # ---- multi-GPU exchange and host staging memory
+    def allgather_results(self, nccl_comm, local, n_ranks):
+        """r360_allgather_results: `local` (RESULT_DTYPE records, the same count on every rank) -> all ranks' records,
+        rank-major, on the host.  nccl_comm: the caller's ncclComm_t for this ctx's device (an int / c_void_p)."""
+        local = np.ascontiguousarray(local)
+        if local.dtype != RESULT_DTYPE:
+            raise ValueError("local must be an array of RESULT_DTYPE records")
+        out = np.zeros(n_ranks * local.size, RESULT_DTYPE)
+        comm = nccl_comm if isinstance(nccl_comm, C.c_void_p) else C.c_void_p(int(nccl_comm))
+        self._ck(self.L.r360_allgather_results(self.h, comm, _p(local), local.size, n_ranks, _p(out)))
+        return out
+
+    def host_alloc(self, nbytes):
+        """r360_host_alloc: pinned host memory on the GPU's NUMA node -> (address, node or -1, note)."""
+        p, node = C.c_void_p(), C.c_int32(-1)
+        self._ck(self.L.r360_host_alloc(self.h, nbytes, C.byref(p), C.byref(node)))
+        return int(p.value), int(node.value), self.L.r360_last_error(self.h).decode()
+
+    def host_free(self, addr):
+        self._ck(self.L.r360_host_free(self.h, C.c_void_p(addr)))
 
     # ---- plumbing
     def synchronize(self):

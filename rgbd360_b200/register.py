@@ -15,10 +15,13 @@ class RegisterPhotoICP:
     def __init__(self, device=0):
         self._p = default_params()
         self._device = device
+        self._p.method = PHOTO_CONSISTENCY        # the default argument of every method of the class (RPI.h:4519, 2545, 2745)
         self._ctx = None
         self._shape = None
         self._pending = {}
         self._res = None
+        self._cam = None
+        self._hg = None
         self.SSO = 0.0
         self.avResidual = 0.0          # never written on the occlusion-0 spherical path
         self.avPhotoResidual = 0.0
@@ -65,7 +68,7 @@ class RegisterPhotoICP:
             self._ctx = Context(shape[0], shape[1], 2, 1, self._p, self._device)
             self._shape = shape
             if self._p.projection == 1:
-                if getattr(self, "_cam", None) is None:
+                if self._cam is None:
                     raise RuntimeError("setCameraMatrix first (RPI.h:254)")
                 self._ctx.set_camera(*self._cam)
             for slot, (r, d, role) in self._pending.items():
@@ -84,8 +87,10 @@ class RegisterPhotoICP:
 
     def _configure(self, method, occlusion, projection):
         """Re-create the context when the cost function, the occlusion variant or the registration changes."""
-        if self._ctx is None:
+        if 0 not in self._pending or 1 not in self._pending:
             raise RuntimeError("setSourceFrame / setTargetFrame first")
+        if self._ctx is None:
+            self._ensure(self._pending[0][0])
         if method != self._p.method or occlusion != self._p.occlusion or projection != self._p.projection:
             self._p.method = int(method)
             self._p.occlusion = int(occlusion)
@@ -117,26 +122,18 @@ class RegisterPhotoICP:
     def alignFrames360(self, pose_guess=None, method=PHOTO_CONSISTENCY, occlusion=0):
         if occlusion not in (0, 1, 2):
             raise ValueError("occlusion must be 0, 1 or 2 (RPI.h:4517)")
-        if self._ctx is None:
-            raise RuntimeError("setSourceFrame / setTargetFrame first")
-        if method != self._p.method or occlusion != self._p.occlusion or self._p.projection != 0:
-            self._p.method = int(method)
-            self._p.occlusion = int(occlusion)
-            if self._p.projection != 0:
-                self._p.projection = 0
-                self._p.tol_residual = 1e-3
-                self._p.n_sensors_mask = 8
-            self._ctx.close(); self._ctx = None
-            self._ensure(self._pending[0][0])
+        self._configure(method, occlusion, 0)
         guess = None if pose_guess is None else pose_to_colmajor(pose_guess)[None]
         self._res = self._ctx.register_pairs([0], [1], guess)[0]
         self.SSO = float(self._res["sso"])
 
-    def errorPhotoICP_sphere(self, level, pose, method=None):
+    def errorPhotoICP_sphere(self, level, pose, method=PHOTO_CONSISTENCY):
+        self._configure(method, 0, 0)
         e2, n = self._ctx.eval_error(0, 1, level, pose)
         return float(np.sqrt(e2 / n)) if n else float("nan")
 
-    def calcHessGrad_sphere(self, level, pose, method=None):
+    def calcHessGrad_sphere(self, level, pose, method=PHOTO_CONSISTENCY):
+        self._configure(method, 0, 0)
         H, g, nv = self._ctx.eval_hessgrad(0, 1, level, pose)
         self._hg = (H, g)
         self.SSO = nv / float((self._shape[0] >> level) * (self._shape[1] >> level))

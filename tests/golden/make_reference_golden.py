@@ -3,6 +3,7 @@ against oracle/refshim/, both arithmetic variants) on the cases of tests/refcase
 outputs as tests/golden/reference_outputs.json.  Only runnable where /root/reference exists.
 
     python tests/golden/make_reference_golden.py          # both recordings
+    python tests/golden/make_reference_golden.py sphere   # reference_outputs.json only
     python tests/golden/make_reference_golden.py occ      # reference_occlusion.json only
     python tests/golden/make_reference_golden.py pinhole  # reference_pinhole.json only
 """
@@ -161,19 +162,65 @@ def main_pinhole():
         json.dump(gold, f, indent=0)
 
 
+def sample_pair_other_branch(case, one_thread_iters, pinned=True):
+    """Config #1 sits on a knife edge of the accept test (RPI.h:4715) at level 0: with its 27 FLOAT accumulators summed
+    in another order (another OpenMP thread count) the reference takes 1 accepted step there instead of 10 and ends
+    ~1e-3 rad / 1 cm away from its own one-thread answer.  Records one run of the reference on that other branch (the
+    one a well-conditioned accumulation -- the oracle's STABLE mode, the GPU's wide sums -- follows)."""
+    for rep in range(4):
+        for th in (3, 8, 4, 2, 5, 6, 7):
+            refbind.lib(pinned).ref_set_threads(th)
+            try:
+                R = refbind.Reference(n_levels=case["levels"], std_photo=case["std_photo"], pinned=pinned)
+                R.set_source(case["rgb_s"], case["d_s"]); R.set_target(case["rgb_t"], case["d_t"])
+                a = R.align(case["guess"], case["method"])
+                R.close()
+            finally:
+                refbind.lib(pinned).ref_set_threads(1)
+            if a["iters"].tolist() == [1, 10, 10, 7]:
+                return dict(threads=th, pose=a["pose"].astype(np.float64).ravel().tolist(),
+                            H=a["H"].astype(np.float64).ravel().tolist(), g=a["g"].astype(np.float64).tolist(), sso=a["sso"],
+                            iters=a["iters"].tolist(), trace_err2=a["err2"].tolist(), trace_n_valid=a["n_valid"].tolist())
+    raise RuntimeError("no thread count reproduced the 1-step branch of the sample pair on this host")
+
+
+def sample_pair_self_spread(case, pinned=True, reps=2):
+    """The reference against ITSELF on config #1: runs at 2..8 OpenMP threads (its float accumulators are then summed
+    in other orders).  Recorded as evidence for the tolerance of the GPU test on this pair: iteration counts and poses."""
+    runs = []
+    for rep in range(reps):
+        for th in (2, 3, 4, 5, 6, 7, 8):
+            refbind.lib(pinned).ref_set_threads(th)
+            try:
+                R = refbind.Reference(n_levels=case["levels"], std_photo=case["std_photo"], pinned=pinned)
+                R.set_source(case["rgb_s"], case["d_s"]); R.set_target(case["rgb_t"], case["d_t"])
+                a = R.align(case["guess"], case["method"])
+                R.close()
+            finally:
+                refbind.lib(pinned).ref_set_threads(1)
+            runs.append(dict(threads=th, iters=a["iters"].tolist(), pose=a["pose"].astype(np.float64).ravel().tolist()))
+    return runs
+
+
 def main():
     gold = {"_how": "oracle/_ref (reference header + refshim), OMP threads = 1; see this script", "cases": {}}
     for name in refcases.CASES:
         case = refcases.make_case(orc, name)
         gold["cases"][name] = {"libm": run_reference(case, False), "pinned": run_reference(case, True)}
         c = gold["cases"][name]
-        print(name, "iters", c["libm"]["iters"], c["pinned"]["iters"], "n_valid[0]", c["libm"]["trace_n_valid"][:1])
+        print(name, "iters", c["libm"]["iters"], c["pinned"]["iters"], "n_valid[0]", c["libm"]["trace_n_valid"][:1], flush=True)
+        if name.startswith("sample_pair"):
+            c["pinned_branch_1_10_10_7"] = sample_pair_other_branch(case, c["pinned"]["iters"])
+            print("   other branch at", c["pinned_branch_1_10_10_7"]["threads"], "threads")
+            c["pinned_multithread_runs"] = sample_pair_self_spread(case)
     with open(os.path.join(HERE, "reference_outputs.json"), "w") as f:
         json.dump(gold, f, indent=0)
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "occ":
+    if len(sys.argv) > 1 and sys.argv[1] == "sphere":
+        main()
+    elif len(sys.argv) > 1 and sys.argv[1] == "occ":
         main_occ()
     elif len(sys.argv) > 1 and sys.argv[1] == "pinhole":
         main_pinhole()

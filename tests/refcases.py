@@ -53,6 +53,9 @@ CASES = {
     "synth_256x512_L5_odo": dict(rows=256, cols=512, levels=5, method=2, frames=(20, 21), std_photo=3.0 / 255),
     "loop_128x256_L3": dict(rows=128, cols=256, levels=3, method=2, kind=1, frames=(3, 17), guess_gt=True),
     "sample_pair_1920x320_L4": dict(sample=True, levels=4, method=2),
+    # BASELINE.json's own sizes: configs[1] (1024x512, 3 levels) and configs[2] (2048x1024, 4 levels), batch frames 2j / 2j+1
+    "synth_512x1024_L3_pd": dict(rows=512, cols=1024, levels=3, method=2, frames=(10, 11)),
+    "synth_1024x2048_L4_pd": dict(rows=1024, cols=2048, levels=4, method=2, frames=(12, 13)),
     # quirk 9: ILL-POSED (RPI.h:4682-4690) -- photo-only on a texture that varies along columns only over a
     # constant-range sphere: the first twist column of J is identically 0, rank(H + lambda diag H) = 5
     "illposed_cols_only_photo": dict(special="illposed", rows=64, cols=128, levels=2, method=0),

@@ -123,8 +123,6 @@ def _check_align(orc, res_g, tr_g, res_o, tr_o, P, src, trg):
             if not o.used:
                 continue
             assert o.accepted == g.accepted and o.it == g.it
-            assert abs(g.err2 - o.err2) <= 10 * REL * abs(o.err2), (lvl, k)      # run vs run
-            assert abs(g.n_valid - o.n_valid) <= 1e-3 * o.n_valid + 2
             pose_g = np.array(g.pose, np.float32).reshape(4, 4).T
             e2r, nvr = orc.error(src, trg, lvl, pose_g, P)                        # replay, same bits
             assert nvr == g.n_valid, (lvl, k)                                    # integer: bit-exact
@@ -149,13 +147,11 @@ def _check_align(orc, res_g, tr_g, res_o, tr_o, P, src, trg):
     Tg = np.array(res_g["pose"], np.float32).reshape(4, 4).T
     ang, dist = pose_err(Tg, To)
     assert ang <= POSE_RAD and dist <= POSE_M, (ang, dist)
-    assert abs(res_g["final_err2"] - res_o.final_err2) <= 10 * REL * res_o.final_err2
-    assert abs(res_g["final_n_valid"] - res_o.final_n_valid) <= 1e-3 * res_o.final_n_valid + 2
-    assert abs(res_g["sso"] - res_o.sso) < 1e-3
-    Ho = np.array(res_o.hessian, np.float64).reshape(6, 6)
-    Hg = np.array(res_g["hessian"], np.float64).reshape(6, 6)
-    sc = np.sqrt(np.outer(np.diag(Ho), np.diag(Ho)))
-    assert np.all(np.abs(Hg - Ho) <= 10 * REL * sc)
+    # the final record replayed at the GPU's own final pose: count exact, sum 1e-4 (the getters' Hessian / SSO belong
+    # to the last calcHessGrad_sphere call, replayed above with the trace)
+    e2r, nvr = orc.error(src, trg, 0, Tg, P) if res_g["status"] == 0 else (res_g["final_err2"], res_g["final_n_valid"])
+    assert nvr == res_g["final_n_valid"]
+    assert abs(res_g["final_err2"] - e2r) <= REL * abs(e2r)
 
 
 def test_align_identity_guess(pair_small):
@@ -270,12 +266,88 @@ def test_register_host_pairs_streaming(r360):
     for k in range(n):
         assert got[k]["pair_id"] == k and got[k]["status"] == ref[k]["status"]
         assert list(got[k]["iters"]) == list(ref[k]["iters"])
+        # (two batch compositions -- 64 + 6 pairs here, 70 there -- cut the pixels of a pair into other per-thread
+        # float partial sums: same decisions, last bits of the sums may differ; a repeated call is bit-identical,
+        # test_deterministic_run_to_run)
         assert np.allclose(got[k]["pose"], ref[k]["pose"], atol=1e-6)
         assert got[k]["final_n_valid"] == ref[k]["final_n_valid"]
     # frames stay resident in slots 2p / 2p+1: a second registration through the slot API agrees
     again = ctx2.register_pairs(src_idx[:3], trg_idx[:3], guesses[:3])
     assert np.allclose(again["pose"], ref["pose"][:3], atol=1e-6)
     ctx.close(); ctx2.close()
+
+
+def test_deterministic_run_to_run(r360):
+    """The same call twice gives the same BYTES in every field of every record and of every trace entry: the per-pair sums
+    are accumulated across CTAs in fixed point (integer atomics: order-independent), everything else is a fixed
+    function of the inputs.  Also across a fresh context, through the host-pairs entry point and the evaluation hooks."""
+    rows, cols, L, n = 128, 256, 3, 12
+    ctx = r360.Context(rows, cols, 2 * n, n, r360.default_params(n_levels=L))
+    rgb, dep = ctx.synth_frames(0, 0, 2 * n)
+    roles = np.array([r360.ROLE_TARGET, r360.ROLE_SOURCE] * n, np.uint8)
+    ctx.set_frames(0, rgb, dep, roles)
+    trg_idx = np.arange(0, 2 * n, 2); src_idx = trg_idx + 1
+    rng = np.random.default_rng(11)
+    guesses = np.stack([r360.pose_to_colmajor(small_pose(*(rng.uniform(-1, 1, 6) * 0.02))) for _ in range(n)])
+    a, tr_a = ctx.register_pairs(src_idx, trg_idx, guesses, trace=True)
+    for _ in range(3):
+        b, tr_b = ctx.register_pairs(src_idx, trg_idx, guesses, trace=True)
+        assert a.tobytes() == b.tobytes()
+        assert bytes(tr_a) == bytes(tr_b)
+    ctx2 = r360.Context(rows, cols, 2 * n, n, r360.default_params(n_levels=L))
+    ctx2.set_frames(0, rgb, dep, roles)
+    assert ctx2.register_pairs(src_idx, trg_idx, guesses).tobytes() == a.tobytes()
+    h1 = ctx2.register_host_pairs(rgb, dep, n, guesses)
+    h2 = ctx2.register_host_pairs(rgb, dep, n, guesses)
+    assert h1.tobytes() == h2.tobytes() == a.tobytes()          # n <= one internal batch: the same decomposition
+    for level in range(L):
+        H1, g1, n1 = ctx.eval_hessgrad(1, 0, level, POSES[1]); H2, g2, n2 = ctx.eval_hessgrad(1, 0, level, POSES[1])
+        assert H1.tobytes() == H2.tobytes() and g1.tobytes() == g2.tobytes() and n1 == n2
+        assert ctx.eval_error(1, 0, level, POSES[1]) == ctx.eval_error(1, 0, level, POSES[1])
+    ctx.close(); ctx2.close()
+
+
+def test_slot_reset_with_narrower_role_invalidates_the_other_pyramid(r360):
+    """A slot set as BOTH and later re-set as TARGET only no longer has a source pyramid (the allocation stays, its
+    content is another frame's): registering it as a source is a state error, not a silent use of the old frame."""
+    ctx = r360.Context(64, 128, 2, 1, r360.default_params(n_levels=2))
+    rgb, dep = ctx.synth_frames(0, 0, 3)
+    ctx.set_frames(0, rgb[:2], dep[:2])                                      # both slots, both roles
+    assert ctx.register_pairs([0], [1])[0]["status"] == 0
+    ctx.set_frames(0, rgb[2:3], dep[2:3], [r360.ROLE_TARGET])                # slot 0: another frame, target only
+    with pytest.raises(r360.R360Error):
+        ctx.register_pairs([0], [1])
+    with pytest.raises(r360.R360Error):
+        ctx.dump_source_level(0, 0)
+    assert ctx.register_pairs([1], [0])[0]["status"] == 0                    # its target pyramid is the new frame's
+    ctx.register_host_pairs(rgb[:2], dep[:2], 1)                             # slot 0 target, slot 1 source
+    with pytest.raises(r360.R360Error):
+        ctx.register_pairs([0], [1])                                         # slot 0 has no source, slot 1 no target
+    ctx.close()
+
+
+def test_python_shape_checks(r360):
+    """The ctypes wrappers pass raw pointers: mismatched arrays must raise in Python, not read out of bounds in C."""
+    ctx = r360.Context(64, 128, 4, 2, r360.default_params(n_levels=2))
+    rgb, dep = ctx.synth_frames(0, 0, 2)
+    with pytest.raises(ValueError):
+        ctx.set_frames(0, rgb[:, :32], dep)
+    with pytest.raises(ValueError):
+        ctx.set_frames(0, rgb, dep[:1])
+    with pytest.raises(ValueError):
+        ctx.set_frames(3, rgb, dep)
+    with pytest.raises(ValueError):
+        ctx.set_frames(0, rgb, dep, [r360.ROLE_BOTH])
+    ctx.set_frames(0, rgb, dep)
+    with pytest.raises(ValueError):
+        ctx.register_pairs([0, 1], [1])
+    with pytest.raises(ValueError):
+        ctx.register_pairs([0], [1], np.zeros(15, np.float32))
+    with pytest.raises(ValueError):
+        ctx.register_pairs([0], [1], out=np.zeros(1, np.float32))
+    with pytest.raises(ValueError):
+        ctx.register_host_pairs(rgb, dep, 2)
+    ctx.close()
 
 
 def test_errors_are_loud(r360):

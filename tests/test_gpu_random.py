@@ -6,11 +6,7 @@ Checks that do not depend on two independent runs taking the same knife-edge dec
 pose the GPU evaluated replayed through the oracle at the same bits (counters exact, sums 1e-4); every decision of the
 GPU's loop re-derived from the sums it recorded (RPI.h:4611, 4715); and, when the oracle's own run took the same number
 of steps, the final pose within 1e-4.
-
-OPT-IN (R360_TEST_RANDOM_GPU=1): written after the GPU minutes of its round were spent, not yet run on hardware:
-    gpurun -- 'R360_TEST_RANDOM_GPU=1 python -m pytest tests/test_gpu_random.py -m gpu -q'
 """
-import os
 import numpy as np
 import pytest
 from util import pose_err, upper21
@@ -22,8 +18,6 @@ REL = 1e-4
 
 @pytest.mark.parametrize("seed", range(24))
 def test_random_problem_replayed_through_the_oracle(orc, r360, seed):
-    if os.environ.get("R360_TEST_RANDOM_GPU") != "1":
-        pytest.skip("opt-in: R360_TEST_RANDOM_GPU=1")
     case = _random_case(orc, 2000 + seed)
     L, method = case["levels"], case["method"]
     rows, cols = case["d_s"].shape

@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 import refcases
 from util import pose_err
+from test_reference import SAMPLE_PAIR_POSE_M
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -65,11 +66,12 @@ def test_cuda_path_equals_reference(orc, r360, gold, name):
             assert abs(e2 - pr["err2"]) <= REL * pr["err2"]
             H, g, nvis = ctx.eval_hessgrad(0, 1, 0, T)
             assert np.float32(nvis) / np.float32(N0) == np.float32(pr["sso"])
-            # The reference sums H and g in 27 FLOAT accumulators (RPI.h:3117-3194); recorded at one
-            # thread that is a serial float sum of up to 2*N0 terms whose own rounding error grows
-            # like sqrt(N0)*2^-24 (1.1e-4 observed at N0 = 614400, the sample pair).  The GPU sums in
-            # double, so above 2^18 pixels the comparison allows for the reference's error.
-            rel_h = REL if N0 <= (1 << 18) else 5 * REL
+            # The reference sums H and g in 27 FLOAT accumulators (RPI.h:3117-3194); recorded at one thread that is a
+            # serial float sum of up to 2*N0 terms whose own rounding error grows with N0: measured with the oracle
+            # (float vs double accumulation of the same rows) 1.2e-4 at N0 = 614400 (the sample pair), 1.9e-4 at
+            # 1024x512 and 1.5e-3 at 2048x1024.  The GPU's sums are exact to 1e-5, so above 2^18 pixels the comparison
+            # allows for the reference's error; the poses of the runs still agree to 1e-4 (asserted below).
+            rel_h = REL * max(1.0, (N0 / float(1 << 18)) ** 1.5)
             Hr = np.array(pr["H"]).reshape(6, 6)
             sc = np.sqrt(np.outer(np.diag(Hr), np.diag(Hr)))
             assert np.all(np.abs(H - Hr) <= rel_h * sc), np.max(np.abs(H - Hr) / sc)
@@ -81,16 +83,23 @@ def test_cuda_path_equals_reference(orc, r360, gold, name):
         res = res[0]
         Tg = np.array(res["pose"], np.float32).reshape(4, 4).T
         if name.startswith("sample_pair"):
-            # the reference's own answer depends on its summation order here (see
-            # tests/test_reference.py::test_sample_pair_summation_order_sensitivity)
-            assert list(res["iters"][:L]) in ([1, 10, 10, 7], [10, 10, 10, 7])
+            # Config #1.  The reference's own answer depends on the order in which its float accumulators are summed
+            # (tests/test_reference.py::test_sample_pair_summation_order_sensitivity: four different iteration vectors
+            # in 14 recorded runs).  The GPU (wide sums) takes the branch of the exact normal equations, [1, 10, 10, 7]:
+            # asserted exactly, and its pose against the recorded reference run on THAT branch.
+            br = gold[name]["pinned_branch_1_10_10_7"]
+            assert list(res["iters"][:L]) == br["iters"] == [1, 10, 10, 7]
+            ang, dist = pose_err(Tg, np.array(br["pose"]).reshape(4, 4))
+            assert ang <= POSE_RAD and dist <= SAMPLE_PAIR_POSE_M, (ang, dist)
         else:
-            assert list(res["iters"][:L]) == ref["iters"]
-            ang, dist = pose_err(Tg, np.array(ref["pose"]).reshape(4, 4))
-            assert ang <= POSE_RAD and dist <= POSE_M, (ang, dist)
-            if ref["sso"] is not None:
-                assert abs(res["sso"] - ref["sso"]) < 1e-3
-            assert (res["status"] != 0) == ref["ill_posed"]
+            for variant in ("pinned", "libm"):           # the glibc build of the reference as well: same counts, same pose
+                rv = gold[name][variant]
+                assert list(res["iters"][:L]) == rv["iters"], variant
+                ang, dist = pose_err(Tg, np.array(rv["pose"]).reshape(4, 4))
+                assert ang <= POSE_RAD and dist <= POSE_M, (variant, ang, dist)
+                if rv["sso"] is not None:
+                    assert abs(res["sso"] - rv["sso"]) < 1e-3
+                assert (res["status"] != 0) == rv["ill_posed"]
         # every level-0 pose the GPU evaluated, replayed through the live reference at the same bits
         R = None if ref["ill_posed"] else _live_reference(case)      # ILL-POSED: level 0 is never reached
         if R is not None:

@@ -30,10 +30,8 @@ def test_allgather_demo_builds_and_entry_point_checks_arguments(r360, tmp_path):
 @pytest.mark.gpu
 def test_cpp_allgather_two_gpus(tmp_path):
     import torch
-    # Opt-in until it has been run once on a 2-GPU box (the round that added it had no GPU minutes left):
-    #   gpurun --gpus 2 -- 'R360_TEST_MULTI_GPU=1 python -m pytest tests/test_multi_gpu.py -m gpu -q'
-    if os.environ.get("R360_TEST_MULTI_GPU") != "1" or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs and R360_TEST_MULTI_GPU=1")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     exe = build_demo(tmp_path)
     out = subprocess.run([str(exe), "2", "4"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "allgather_demo ok" in out.stdout, out.stdout + out.stderr
