@@ -456,8 +456,11 @@ def test_edge_cases_empty_ragged_and_limits(orc, r360):
         ctx.register_pairs([1], [0])                                             # frame 1 has no source pyramid / 0 no target
     with pytest.raises(r360.R360Error):
         ctx.register_pairs([0], [3])                                             # slot out of range
-    with pytest.raises(r360.R360Error):
+    with pytest.raises((r360.R360Error, ValueError)):
         ctx.register_pairs([0, 2, 0], [1, 1, 2])                                 # more pairs than max_pairs
+    s3, t3 = np.array([0, 2, 0], np.int32), np.array([1, 1, 2], np.int32)        # ... and straight at the C ABI
+    out3 = np.zeros(3, r360.native.RESULT_DTYPE)
+    assert ctx.L.r360_register_pairs(ctx.h, 3, s3.ctypes.data, t3.ctypes.data, None, out3.ctypes.data, None) == -1
     with pytest.raises(r360.R360Error):
         ctx.eval_error(0, 1, 3, np.eye(4))                                       # level out of range
     ok = ctx.register_pairs([0, 2], [1, 2])                                      # ragged roles; a frame against itself
