@@ -163,3 +163,55 @@ class Reference:
         out = np.zeros((n, 3), np.float32)
         self.L.ref_lut(self.h, _ptr(out), n)
         return out
+
+
+# ---------------------------------------------------------------- ingest: the reference's own stitch
+_SO_STITCH = {False: os.path.join(_HERE, "_ref", "librpi_ref_stitch.so"),
+              True: os.path.join(_HERE, "_ref", "librpi_ref_stitch_pinned.so")}
+_stitch_libs = {}
+
+
+def stitch_available():
+    return all(os.path.exists(p) for p in _SO_STITCH.values()) or os.path.isdir(os.path.join(REFERENCE_DIR, "include"))
+
+
+def stitch_lib(pinned=False):
+    pinned = bool(pinned)
+    if pinned not in _stitch_libs:
+        if not os.path.exists(_SO_STITCH[pinned]):
+            build()
+        L = C.CDLL(_SO_STITCH[pinned])
+        L.refstitch_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p] + [C.c_void_p] * 4 + [C.POINTER(C.c_int)] * 2
+        L.refstitch_camera.argtypes = [C.c_void_p]
+        _stitch_libs[pinned] = L
+    return _stitch_libs[pinned]
+
+
+def stitch(sensor_rgb, sensor_depth, Rt_inv=None, extrinsics_dir=None, pinned=False):
+    """Frame360::stitchSphericalImage + stitchImage as the reference wrote them (oracle/ref_stitch_harness.cpp), with
+    Calib360's camera matrix.  sensor_rgb 8 x h x w x 3 u8, sensor_depth 8 x h x w u16.  Rt_inv: 8 x 4 x 4 (row-major
+    numpy) put straight into Calib360::Rt_inv, or None: Calib360::loadExtrinsicCalibration(extrinsics_dir or the
+    reference's own Calibration/Extrinsics).  -> (sphere rgb, sphere depth u16, the Rt_inv used as 8 x 4 x 4)."""
+    L = stitch_lib(pinned)
+    sensor_rgb = np.ascontiguousarray(sensor_rgb, np.uint8); sensor_depth = np.ascontiguousarray(sensor_depth, np.uint16)
+    h, w = sensor_depth.shape[1:]
+    cols = 8 * h
+    rows = int(cols * 0.5 * 60.0 / 180)
+    rgb = np.zeros((rows, cols, 3), np.uint8); d = np.zeros((rows, cols), np.uint16)
+    used = np.zeros((8, 16), np.float32)
+    rin = None
+    if Rt_inv is not None:
+        rin = np.ascontiguousarray(np.asarray(Rt_inv, np.float32).reshape(8, 4, 4).transpose(0, 2, 1)).reshape(8, 16)
+    r, c = C.c_int(), C.c_int()
+    L.refstitch_run(sensor_rgb.ctypes.data, sensor_depth.ctypes.data, h, w,
+                    None if extrinsics_dir is None else extrinsics_dir.encode(),
+                    None if rin is None else rin.ctypes.data, rgb.ctypes.data, d.ctypes.data, used.ctypes.data,
+                    C.byref(r), C.byref(c))
+    assert (r.value, c.value) == (rows, cols)
+    return rgb, d, used.reshape(8, 4, 4).transpose(0, 2, 1).copy()
+
+
+def stitch_camera(pinned=False):
+    out = np.zeros(4, np.float32)
+    stitch_lib(pinned).refstitch_camera(out.ctypes.data)
+    return tuple(float(x) for x in out)

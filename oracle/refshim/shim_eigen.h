@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <cstdio>
+#include <string>
 #include <iostream>
 #include <vector>
 #include <memory>
@@ -142,6 +144,18 @@ public:
         return m;
     }
     void setIdentity() { *this = Identity(r_, c_); }
+    // MRPT's Eigen plugin: MatrixBase::loadFromTextFile (Calib360.h:128) -- a whitespace-separated text matrix,
+    // one row per line; fixed-size matrices must find exactly their size.
+    void loadFromTextFile(const std::string& file) {
+        FILE* f = fopen(file.c_str(), "r");
+        if (!f) { std::cerr << "refshim: loadFromTextFile: cannot open " << file << "\n"; std::abort(); }
+        std::vector<double> v;
+        double x;
+        while (fscanf(f, "%lf", &x) == 1) v.push_back(x);
+        fclose(f);
+        if (!Fixed || (int)v.size() != r_ * c_) { std::cerr << "refshim: loadFromTextFile: " << file << " does not hold a " << r_ << "x" << c_ << " matrix\n"; std::abort(); }
+        for (int i = 0; i < r_; ++i) for (int j = 0; j < c_; ++j) (*this)(i, j) = (T)v[(size_t)i * c_ + j];
+    }
 
     template <typename U>
     CommaInit<T, R, C> operator<<(const U& v) {

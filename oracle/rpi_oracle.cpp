@@ -1164,7 +1164,7 @@ void stitch_sphere(const R360StitchGeom& g, const float* Rt_inv, const uint8_t* 
             const int s = 7 - c / g.size_h;
             const float theta = (c + g.offset_theta) * g.angle_pixel;
             int ui, vi;
-            double sc;
+            float sc;
             if (!r360_stitch_pixel(g, Rt_inv + 16 * s, sp, cp, M::sin_(theta), M::cos_(theta), &ui, &vi, &sc)) continue;
             const size_t j = (size_t)s * spx + (size_t)vi * g.size_w + ui, i = (size_t)r * g.cols + c;
             rgb[3 * i] = sensor_rgb[3 * j]; rgb[3 * i + 1] = sensor_rgb[3 * j + 1]; rgb[3 * i + 2] = sensor_rgb[3 * j + 2];

@@ -1005,7 +1005,7 @@ k_stitch(R360StitchArgs a, const uint8_t* __restrict__ sensor_rgb, const uint16_
         r360_sincosf((g.offset_phi - r) * g.angle_pixel, &sp, &cp);
         r360_sincosf((c + g.offset_theta) * g.angle_pixel, &st, &ct);
         int ui, vi;
-        double sc;
+        float sc;
         uint8_t p0 = 0, p1 = 0, p2 = 0;
         uint16_t d = 0;
         if (r360_stitch_pixel(g, a.Rt_inv[s], sp, cp, st, ct, &ui, &vi, &sc)) {

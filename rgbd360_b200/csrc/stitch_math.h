@@ -34,9 +34,12 @@ R360_HD R360StitchGeom r360_stitch_geom(int size_h, int size_w, float fx, float 
 // Sensor pixel hit by sphere pixel (row, col); sphi/cphi and sth/cth are sin/cos of
 // phi = (offset_phi - row) * angle_pixel and theta = (col + offset_theta) * angle_pixel.
 // Rt_inv: column-major 4x4 of the sensor.  Returns 0 when the ray misses the sensor image.
-// *range_scale = sqrt(1 + ((u-cx)/fx)^2 + ((v-cy)/fy)^2) in double (Frame360.h:1141).
+// *range_scale = sqrt(1 + ((u-cx)/fx)^2 + ((v-cy)/fy)^2) in FLOAT (Frame360.h:1141): the reference is C++98 code with
+// a leaked `using namespace std` (unqualified `cout` in Frame360.h:208; Miscellaneous.h:120-124 does not compile as
+// C++11), where `pow(float, 2)` is std::pow(float, int) = x * x in float and `sqrt` the float overload -- what the
+// reference's own lines produce when compiled here (oracle/ref_stitch_harness.cpp, tests/test_ingest.py).
 R360_HD int r360_stitch_pixel(const R360StitchGeom& g, const float* Rt_inv, float sphi, float cphi, float sth,
-                              float cth, int* ui, int* vi, double* range_scale) {
+                              float cth, int* ui, int* vi, float* range_scale) {
     const float v0 = sphi, v1 = cphi * sth, v2 = cphi * cth;
     // Eigen 3x3 * 3x1 + 3x1, coefficient sums left to right
     const float p0 = ((Rt_inv[0] * v0 + Rt_inv[4] * v1) + Rt_inv[8] * v2) + Rt_inv[12];
@@ -47,14 +50,14 @@ R360_HD int r360_stitch_pixel(const R360StitchGeom& g, const float* Rt_inv, floa
     if (!(u >= 0 && u < g.size_w && v >= 0 && v < g.size_h)) return 0;
     *ui = (int)u;
     *vi = (int)v;
-    const double a = (double)((u - g.cx) / g.fx), b = (double)((v - g.cy) / g.fy);
-    *range_scale = sqrt(1 + a * a + b * b);
+    const float a = (u - g.cx) / g.fx, b = (v - g.cy) / g.fy;
+    *range_scale = sqrtf((1 + a * a) + b * b);
     return 1;
 }
 
-// depth (u16 mm, z) -> Euclidean range (u16 mm): double product truncated (Frame360.h:1141);
+// depth (u16 mm, z) -> Euclidean range (u16 mm): float product truncated (Frame360.h:1141);
 // values beyond the u16 range saturate (the reference's conversion is undefined there).
-R360_HD unsigned short r360_stitch_range(unsigned short d, double range_scale) {
-    const double x = (double)d * range_scale;
-    return (unsigned short)(x < 65535.0 ? x : 65535.0);
+R360_HD unsigned short r360_stitch_range(unsigned short d, float range_scale) {
+    const float x = (float)d * range_scale;
+    return (unsigned short)(x < 65535.0f ? x : 65535.0f);
 }

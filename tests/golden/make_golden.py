@@ -6,8 +6,10 @@ python cv2); the GPU box only reads the fixtures.
 1. sample_pair.npz -- the reference's only data fixture (config #1 of BASELINE.json):
    samples/sphere_images_1.bin (target) and sphere_images_10.bin (source), parsed from the boost
    binary archive (third_party/cvSerialization/cvmat_serialization.h:22-54) and stitched to
-   1920x320 RGB8 + depth u16 mm following Frame360.h:386-405,1099-1148 with the extrinsics
-   Calibration/Extrinsics/Rt_0N.txt and the camera matrix of Calib360.h:75-77.
+   1920x320 RGB8 + depth u16 mm BY THE REFERENCE'S OWN CODE: Frame360::stitchSphericalImage / stitchImage
+   (Frame360.h:386-405, 1099-1148) and Calib360 (extrinsics Calibration/Extrinsics/Rt_0N.txt, camera matrix
+   Calib360.h:75-77) compiled from where they lie (oracle/ref_stitch_harness.cpp, glibc build).  The numpy
+   restatement below is kept as an independent cross-check (printed).
 2. cv2_vectors.npz -- OpenCV outputs that pin the third-party arithmetic the oracle restates:
    cvtColor(RGB2GRAY) on u8, convertTo-style scaling, pyrDown on f32 (python cv2 %s).
 3. sample_pair_oracle.json -- the oracle's own result on the sample pair (poses, iterations,
@@ -80,23 +82,26 @@ def stitch(rgb, depth):
         vi = np.clip(v, 0, size_h - 1).astype(np.int64)
         rr, cc = np.nonzero(ok)
         sphere_rgb[rows[rr], cols[cc]] = rgb[s][vi[rr, cc], ui[rr, cc]]
-        scale = np.sqrt(1 + ((u.astype(np.float64) - cx) / fx) ** 2 + ((v.astype(np.float64) - cy) / fy) ** 2)
-        dd = depth[s][vi[rr, cc], ui[rr, cc]].astype(np.float64) * scale[rr, cc]
-        sphere_d[rows[rr], cols[cc]] = np.minimum(dd, 65535).astype(np.uint16)   # double -> ushort truncation
+        a = ((u - cx) / fx).astype(f32); b = ((v - cy) / fy).astype(f32)
+        scale = np.sqrt(((f32(1) + a * a).astype(f32) + b * b).astype(f32)).astype(f32)     # C++98: pow(float, 2), sqrt(float)
+        dd = (depth[s][vi[rr, cc], ui[rr, cc]].astype(f32) * scale[rr, cc]).astype(f32)
+        sphere_d[rows[rr], cols[cc]] = np.minimum(dd, 65535).astype(np.uint16)   # float -> ushort truncation
     return sphere_rgb, sphere_d
 
 
 def main():
     import cv2
-    from oracle import orc
+    from oracle import orc, refbind
     # ---- 1. sample pair
     out = {}
     for name, fn in (("trg", "sphere_images_1.bin"), ("src", "sphere_images_10.bin")):
         rgb, depth = load_frame360(f"{REF}/samples/{fn}")
-        srgb, sd = stitch(rgb, depth)
+        srgb, sd, _ = refbind.stitch(np.stack(rgb), np.stack(depth), pinned=False)     # the reference's own stitch
+        n_rgb, n_d = stitch(rgb, depth)
         out[name + "_rgb"] = srgb
         out[name + "_depth"] = sd
-        print(name, srgb.shape, sd.shape, "valid depth %.3f" % np.mean((sd > 300) & (sd < 6000)))
+        print(name, srgb.shape, sd.shape, "valid depth %.3f" % np.mean((sd > 300) & (sd < 6000)),
+              "| numpy restatement differs on", int((n_rgb != srgb).any(-1).sum()), "rgb /", int((n_d != sd).sum()), "depth pixels")
     np.savez_compressed(os.path.join(HERE, "sample_pair.npz"), **out)
 
     # ---- 1b. raw sensor images of sphere_images_1.bin (ingest fixture, tests/test_ingest.py)

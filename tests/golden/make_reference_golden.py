@@ -202,6 +202,24 @@ def sample_pair_self_spread(case, pinned=True, reps=2):
     return runs
 
 
+def main_stitch():
+    """SURVEY 8f row 1: Frame360::stitchSphericalImage / stitchImage + Calib360 as the reference wrote them
+    (oracle/ref_stitch_harness.cpp) on the raw sensor images of samples/sphere_images_1.bin (tests/golden/
+    frame360_raw_1.npz): digests of the sphere images for both trig builds, the Rt_inv Calib360 computed."""
+    z = np.load(os.path.join(HERE, "frame360_raw_1.npz"))
+    gold = {"_how": "oracle/_ref/librpi_ref_stitch[_pinned].so: Calib360.h whole, the two Frame360 member functions verbatim "
+                    "(cut out of Frame360.h at build time), refshim third-party stand-ins; see this script",
+            "camera": list(refbind.stitch_camera())}
+    for pinned in (False, True):
+        rgb, d, Rt_inv = refbind.stitch(z["rgb"], z["depth"], pinned=pinned)
+        gold["pinned" if pinned else "libm"] = dict(rgb_sha=digest(rgb), depth_sha=digest(d), rows=int(d.shape[0]), cols=int(d.shape[1]),
+                                                    valid_depth=int((d > 0).sum()))
+        gold["Rt_inv"] = Rt_inv.astype(np.float64).reshape(8, 16).tolist()          # row-major 4x4 per sensor
+        print("stitch", "pinned" if pinned else "libm", gold["pinned" if pinned else "libm"])
+    with open(os.path.join(HERE, "reference_stitch.json"), "w") as f:
+        json.dump(gold, f, indent=0)
+
+
 def main():
     gold = {"_how": "oracle/_ref (reference header + refshim), OMP threads = 1; see this script", "cases": {}}
     for name in refcases.CASES:
@@ -220,6 +238,8 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sphere":
         main()
+    elif len(sys.argv) > 1 and sys.argv[1] == "stitch":
+        main_stitch()
     elif len(sys.argv) > 1 and sys.argv[1] == "occ":
         main_occ()
     elif len(sys.argv) > 1 and sys.argv[1] == "pinhole":
@@ -228,3 +248,4 @@ if __name__ == "__main__":
         main()
         main_occ()
         main_pinhole()
+        main_stitch()
