@@ -37,7 +37,7 @@ R360_HD R360StitchGeom r360_stitch_geom(int size_h, int size_w, float fx, float 
 // *range_scale = sqrt(1 + ((u-cx)/fx)^2 + ((v-cy)/fy)^2) in FLOAT (Frame360.h:1141): the reference is C++98 code with
 // a leaked `using namespace std` (unqualified `cout` in Frame360.h:208; Miscellaneous.h:120-124 does not compile as
 // C++11), where `pow(float, 2)` is std::pow(float, int) = x * x in float and `sqrt` the float overload -- what the
-// reference's own lines produce when compiled here (oracle/ref_stitch_harness.cpp, tests/test_ingest.py).
+// reference's own lines produce when compiled here (tests/test_ingest.py pins this against them).
 R360_HD int r360_stitch_pixel(const R360StitchGeom& g, const float* Rt_inv, float sphi, float cphi, float sth,
                               float cth, int* ui, int* vi, float* range_scale) {
     const float v0 = sphi, v1 = cphi * sth, v2 = cphi * cth;
