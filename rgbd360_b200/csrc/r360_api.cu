@@ -72,6 +72,7 @@ struct Ctx {
     int pass_grid_err = 0;
     bool speculate = true;                       // R360_SPECULATE=0 in the environment: every pass is the fused one (A/B)
     float spec_margin = 1.0f;                    // R360_SPEC_MARGIN: threshold of the prediction in units of tol_residual (A/B)
+    int dyn_permille = 150;                      // R360_DYN_PERMILLE: share of a k_pass launch's items handed out dynamically (A/B; 0 = static)
     const float2** h_srcb = nullptr; const float2** d_srcb = nullptr;
     const float** h_trgb = nullptr; const float** d_trgb = nullptr;
     int32_t* h_idx = nullptr; int32_t* d_idx = nullptr;          // src idx | trg idx
@@ -160,6 +161,8 @@ R360PassArgs pass_args(Ctx* c, int level, int n_pairs_hint, int first = 0, bool 
     a.items_per_pair = (int)((n + ppi - 1) / ppi);
     // pair-indexed arrays are addressed relative to `first` (pair ids inside the kernels are batch-local)
     a.n_active = err_only ? c->d_nactive + 3 : c->d_nactive;
+    a.work_counter = c->d_nactive + (err_only ? 5 : 4);
+    a.dyn_permille = c->dyn_permille;
     a.active_list = (err_only ? c->d_active_err : c->d_active) + first;
     a.pairs = c->d_pairs + first;
     a.src_base = c->d_srcb + first;
@@ -185,6 +188,7 @@ R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) 
     g.speculate = c->speculate ? 1 : 0;
     g.spec_margin = c->spec_margin;
     g.ticket = c->d_nactive + 2;
+    g.work_counters = c->d_nactive + 4;
     g.trace = trace ? trace + (size_t)first * c->L * trace_per_level(c) : nullptr;
     return g;
 }
@@ -330,6 +334,7 @@ int eval_setup(Ctx* c, int src, int trg, int level, const float pose[16], R360Pa
     const int one = 1;
     CK(c, cudaMemcpyAsync(c->d_active + slot, &slot, sizeof(int), cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(c->d_nactive + 1, &one, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(c->d_nactive + 4, 0, sizeof(int) * 2, c->st));     // dynamic-item counters
     CK(c, cudaMemsetAsync(c->d_acc + (size_t)slot * R360_ACC_STRIDE, 0, sizeof(R360Fx) * R360_ACC_STRIDE, c->st));
     CK(c, cudaMemsetAsync(c->d_cnt + (size_t)slot * R360_ACC_INTS, 0, sizeof(int) * R360_ACC_INTS, c->st));
     CK(c, cudaStreamSynchronize(c->st));    // hp / sb / tb are stack variables
@@ -465,6 +470,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     c->pass_grid_err = c->sm_count * R360_ERR_CTAS;
     if (const char* e = getenv("R360_SPECULATE")) c->speculate = atoi(e) != 0;
     if (const char* e = getenv("R360_SPEC_MARGIN")) c->spec_margin = (float)atof(e);
+    if (const char* e = getenv("R360_DYN_PERMILLE")) c->dyn_permille = std::min(1000, std::max(0, atoi(e)));
     CK(c, r360_pass_init());
     if (params->occlusion != 0) CK(c, r360_occ_init());
     CK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
@@ -543,8 +549,10 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * R360_ACC_INTS * np));
     CK(c, cudaMalloc(&c->d_active, sizeof(int) * np));
     CK(c, cudaMalloc(&c->d_active_err, sizeof(int) * np));
-    CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 4));      // [0] batch (fused passes), [1] eval hooks, [2] completion ticket, [3] batch (error-only passes)
-    CK(c, cudaMemset(c->d_nactive, 0, sizeof(int) * 4));
+    // [0] batch (fused passes), [1] eval hooks, [2] completion ticket, [3] batch (error-only passes),
+    // [4] / [5] dynamic-item counters of the fused / error-only k_pass launch
+    CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 8));
+    CK(c, cudaMemset(c->d_nactive, 0, sizeof(int) * 8));
     CK(c, cudaMallocHost(&c->h_srcb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_srcb, sizeof(void*) * np));
     CK(c, cudaMallocHost(&c->h_trgb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_trgb, sizeof(void*) * np));
     CK(c, cudaMallocHost(&c->h_idx, sizeof(int32_t) * 2 * np)); CK(c, cudaMalloc(&c->d_idx, sizeof(int32_t) * 2 * np));

@@ -399,9 +399,16 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
 
 // =========================================================================== K3: fused pixel pass
 // Work decomposition: the (active pair, pixel block) space is cut into `items` of px_per_item
-// pixels; every CTA of the persistent grid takes one CONTIGUOUS run of items, so it touches one
-// or two pairs, keeps its 28 packed partial sums in registers across the whole run and flushes
-// them (warp shuffles + shared memory + 28 order-independent fixed-point atomic sums, r360_fx_add) once per pair it touched.
+// pixels.  STATIC part (the first 1 - dyn_permille / 1000 of the items): every CTA of the persistent
+// grid takes one CONTIGUOUS run of items, so it touches one or two pairs, keeps its 28 packed partial
+// sums in registers across the whole run and flushes them (warp shuffles + shared memory + 28
+// order-independent fixed-point atomic sums, r360_fx_add) once per pair it touched.  DYNAMIC part (the
+// remaining items): CTAs that are done fetch single items from a global counter and flush after each.
+// Equal pixel counts do not take equal time -- the row skips are content dependent and the SMs do not
+// stream equally fast (ncu: SMs busy 88 % of a static launch on average, 80 % the fastest) -- so the
+// dynamic tail lets the fast CTAs take what the slow ones would still be working on.  The sums stay
+// reproducible bit for bit: a static run and a dynamic item each cover a FIXED set of pixels with a fixed
+// pixel-to-thread mapping whoever executes them, and the cross-CTA accumulation is order-independent.
 //
 // Per thread and iteration one pixel pair, software-pipelined through shared memory in two stages:
 //   stage A (pair k+1): LDG.128 of {depth, gray} x 2 (loaded two iterations ahead), back-projection,
@@ -428,15 +435,20 @@ k_pass(R360PassArgs a) {
     __shared__ float s_red[R360_PASS_THREADS / 32][R360_ACC_DOUBLES];
     __shared__ int s_cnt[R360_PASS_THREADS / 32][R360_ACC_INTS];
     __shared__ __align__(16) float s_T[16];
+    __shared__ int s_next;
     const R360Level lv = a.lv;
     const r360_params P = a.params;
     const float inv_std_photo = a.inv_std_photo;
     const int ipp = a.items_per_pair, ppi = a.px_per_item;
-    const int n_items = (*a.n_active) * ipp;
-    const int per = n_items / (int)gridDim.x, rem = n_items - per * (int)gridDim.x;
-    const int bid = (int)blockIdx.x;
-    int item = bid * per + min(bid, rem);
-    const int item_end = item + per + (bid < rem ? 1 : 0);
+    int item, item_end;                                              // item_end < 0: the dynamic phase
+    {
+        const int n_items = (*a.n_active) * ipp;
+        const int n_static = n_items - (int)(((long long)n_items * a.dyn_permille) / 1000);
+        const int per = n_static / (int)gridDim.x, rem = n_static - per * (int)gridDim.x;
+        const int bid = (int)blockIdx.x;
+        item = bid * per + min(bid, rem);
+        item_end = item + per + (bid < rem ? 1 : 0);
+    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int STRIDE = 2 * R360_PASS_THREADS;
     // this thread's slots: stage s at + s * STAGE_BYTES; texels at +0, geometry at + GEO_OFF
@@ -445,11 +457,23 @@ k_pass(R360PassArgs a) {
 
     int ap = item / ipp;
     int sub = item - ap * ipp;
-    while (item < item_end) {
-        const int n_seg = min(ipp - sub, item_end - item);          // items of pair `ap` in this run
+    for (;;) {
+        __syncthreads();                                             // s_T / s_red / s_next of the previous segment
+        if (item >= item_end) {                                      // static run done (uniform over the CTA): single items from the counter
+            item_end = -1;
+            const int n_items = (*a.n_active) * ipp;
+            const int n_static = n_items - (int)(((long long)n_items * a.dyn_permille) / 1000);
+            if (n_static == n_items) break;
+            if (threadIdx.x == 0) s_next = n_static + atomicAdd(a.work_counter, 1);
+            __syncthreads();
+            item = s_next;
+            if (item >= n_items) break;
+            ap = item / ipp;
+            sub = item - ap * ipp;
+        }
+        const int n_seg = item_end < 0 ? 1 : min(ipp - sub, item_end - item);   // items of pair `ap` in this segment
         const int pair = a.active_list[ap];
         const R360Pair* __restrict__ ps = a.pairs + pair;
-        __syncthreads();                                             // s_T / s_red of the previous segment
         if (threadIdx.x < 16) s_T[threadIdx.x] = ps->pose_eval[threadIdx.x];
         __syncthreads();
         const float4* __restrict__ src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
@@ -741,7 +765,11 @@ __device__ void r360_compact_when_last(const R360GnArgs& g) {
     if (s_last) {
         __threadfence();
         if (threadIdx.x < 32) r360_compact_active(g.pairs, g.n_pairs, g.active_list, g.n_active, g.active_list_err, g.n_active_err);
-        if (threadIdx.x == 0) *g.ticket = 0;
+        if (threadIdx.x == 0) {
+            *g.ticket = 0;
+            g.work_counters[0] = 0;                                  // dynamic-item counters of the next k_pass launches
+            g.work_counters[1] = 0;
+        }
     }
 }
 

@@ -25,6 +25,8 @@ struct R360PassArgs {
     float inv_std_photo;                // (float)(1./stdDevPhoto), RPI.h:2774
     float one;                          // 1.0f, opaque to the compiler (see f2add_sep)
     int items_per_pair, px_per_item;
+    int dyn_permille;                   // share of the items (in 1/1000) handed out dynamically at the end of the launch
+    int* work_counter;                  // device: next dynamic item (0 at launch; reset by the state-machine kernels)
     const int* n_active;                // device
     const int* active_list;             // device
     const R360Pair* pairs;              // device
@@ -58,6 +60,7 @@ struct R360GnArgs {
     int speculate;                      // 0: every pass is the fused one
     float spec_margin;                  // error-only when the predicted RMS decrease < spec_margin * tol_residual (1: the plain rule)
     int* ticket;                        // device: block-completion counter (the last block compacts the active lists)
+    int* work_counters;                 // device: the two dynamic-item counters of k_pass (fused, error-only): reset with the lists
     r360_iter_record* trace;            // device or nullptr
 };
 
