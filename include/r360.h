@@ -175,6 +175,28 @@ int r360_eval_error_pinhole(r360_ctx* ctx, int src, int trg, int level, const fl
                             double* photo_residual, double* depth_residual, int32_t* n_valid_photo,
                             int32_t* n_valid_depth, double* error);
 
+/* ---- the 8-sensor rig: RegisterRGBD360::RegisterDensePhotoICP (include/RegisterRGBD360.h:344-520) ----
+ * The dense registration of two Frame360 over their 8 pinhole sensor images: per sensor calcPhotoICPError_robot
+ * (RPI.h:4905-5092) and calcHessianGradient_robot (RPI.h:5100-5407) with the sensor's extrinsics, errors / Hessians /
+ * gradients summed over the rig, one 6-DoF Levenberg-Marquardt loop on the ROBOT pose (lambda 0.001, step 10,
+ * tol_residual 0.1, tol_update 1e-6, 10 iterations: RegisterRGBD360.h:391-398, fixed here whatever the ctx params say).
+ * Contexts created with projection = R360_PINHOLE, method = R360_PHOTO_CONSISTENCY (the driver's default; upstream the
+ * Hessian's depth row reads a matrix that is never assigned, RPI.h:5366-5367, so the other methods are undefined there
+ * and refused here) and r360_set_camera(f, f, w/2 - 0.5, h/2 - 0.5), f = 525 w / 640 (RegisterRGBD360.h:361-369).
+ * A rig frame occupies 8 consecutive frame slots (sensor s at first + s): src_first / trg_first name sensor 0 of
+ * frame2 (source) / frame1 (target).  Rt: the 8 sensor poses calib->Rt_ (column-major 4x4 each), shared by all pairs.
+ * faithful_new_error != 0: `new_error` is evaluated at pose_estim, as upstream does (RegisterRGBD360.h:462, 488) --
+ * diff_error is then exactly 0, no step is ever taken, and the call returns the initial guess with the rig's summed
+ * Hessian at that guess (what upstream returns whenever its OpenMP reduction happens to sum in the same order twice);
+ * 0: the candidate pose is evaluated (the evident intent).  out[p].pose = rigidTransf, .hessian = informationM,
+ * .status = R360_PAIR_ILL_POSED where upstream returns false, .final_error = the summed squared error. */
+int r360_register_rig_pairs(r360_ctx* ctx, int n_pairs, const int32_t* src_first, const int32_t* trg_first,
+                            const float* Rt, const float* init_pose, int faithful_new_error, r360_result* out);
+/* One evaluation of the rig at `pose`: error2 = sum over the sensors of calcPhotoICPError_robot, H (column-major 6x6)
+ * and g = the sums of calcHessianGradient_robot's hessian / gradient.  Any output pointer may be NULL. */
+int r360_eval_rig(r360_ctx* ctx, int src_first, int trg_first, int level, const float pose[16], const float* Rt,
+                  double* error2, float H[36], float g[6], int32_t* n_visible, int32_t* n_error_terms);
+
 /* Parity hooks (a1-a5 planes, warp index maps).  Any output pointer may be NULL. */
 int r360_dump_level(r360_ctx* ctx, int frame, int level, float* gray, float* depth,
                     float* gray_gx, float* gray_gy, float* depth_gx, float* depth_gy);

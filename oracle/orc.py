@@ -109,6 +109,13 @@ def lib():
         L.orc_align_pinhole.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int,
                                         C.POINTER(Result), C.c_void_p, C.c_int]
         L.orc_synth_pinhole_frame.argtypes = [C.c_int] * 4 + [C.c_float] * 4 + [C.c_void_p, C.c_void_p]
+        L.orc_synth_pinhole_frame_rt.argtypes = [C.c_int] * 4 + [C.c_float] * 4 + [C.c_void_p] * 3
+        L.orc_error_robot.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.orc_hessgrad_robot.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p] + [C.c_void_p] * 5
+        L.orc_align_rig.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int, C.c_int,
+                                    C.POINTER(Result)]
+        L.orc_inverse4.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_synth_gt_pose.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_stitch.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float] + [C.c_void_p] * 5
         L.orc_pinned_vec.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -282,6 +289,74 @@ def synth_pinhole_frame(kind, fid, rows, cols, fx, fy, ox, oy):
     d = np.zeros((rows, cols), np.uint16)
     lib().orc_synth_pinhole_frame(kind, fid, rows, cols, fx, fy, ox, oy, _ptr(rgb), _ptr(d))
     return rgb, d
+
+
+# ---- the 8-sensor rig: RegisterRGBD360::RegisterDensePhotoICP and the *_robot functions it sums
+def rig_camera(rows, cols):
+    """camIntrinsicMat of RegisterDensePhotoICP (RegisterRGBD360.h:361-369): (fx, fy, ox, oy) as float32."""
+    f32 = np.float32
+    res_factor_VGA = f32(f32(cols) / f32(640.0))
+    focal = f32(f32(525) * res_factor_VGA)
+    return (float(focal), float(focal), float(f32(f32(cols) / f32(2) - f32(0.5))), float(f32(f32(rows) / f32(2) - f32(0.5))))
+
+
+def rig_params(n_levels=4, method=PHOTO):
+    """Parameters of the rig registration: the class defaults, no sensor-joint mask (that mask lives in alignFrames360)."""
+    p = default_params(n_levels=n_levels, method=method, n_sensors_mask=0)
+    p.projection = 1
+    return p
+
+
+def _rt_arg(Rt):
+    """one 4x4 or eight 4x4 (row-major numpy) -> column-major float32"""
+    M = np.asarray(Rt, np.float32)
+    if M.ndim == 2:
+        return np.ascontiguousarray(M.T).reshape(16)
+    return np.ascontiguousarray(M.transpose(0, 2, 1)).reshape(-1, 16)
+
+
+def inverse4(M):
+    A = _rt_arg(M); out = np.zeros(16, np.float32)
+    lib().orc_inverse4(_ptr(A), _ptr(out))
+    return out.reshape(4, 4).T.copy()
+
+
+def synth_rig_frame(kind, fid, rows, cols, Rt, cam=None):
+    """The 8 pinhole sensor views of the synthetic room from robot frame `fid`; Rt: 8 x 4 x 4 sensor poses in the robot
+    frame.  -> (rgb 8 x rows x cols x 3, depth 8 x rows x cols u16 z-depth mm)."""
+    cam = cam or rig_camera(rows, cols)
+    R = _rt_arg(Rt)
+    rgb = np.zeros((8, rows, cols, 3), np.uint8); d = np.zeros((8, rows, cols), np.uint16)
+    for s in range(8):
+        lib().orc_synth_pinhole_frame_rt(kind, fid, rows, cols, *[np.float32(x) for x in cam], _ptr(R[s]), _ptr(rgb[s]), _ptr(d[s]))
+    return rgb, d
+
+
+def error_robot(src, trg, level, pose, Rt, params, cam):
+    """calcPhotoICPError_robot (RPI.h:4905) of one sensor -> (error2, number of terms)."""
+    e = C.c_double(); n = C.c_int()
+    T = pose_arg(pose); K = _cam(cam); R = _rt_arg(Rt)
+    lib().orc_error_robot(src.h, trg.h, level, _ptr(T), _ptr(R), C.byref(params), _ptr(K), C.byref(e), C.byref(n))
+    return e.value, n.value
+
+
+def hessgrad_robot(src, trg, level, pose, Rt, params, cam):
+    """calcHessianGradient_robot (RPI.h:5100) of one sensor, PHOTO_CONSISTENCY: H, g float as upstream; Hd, gd double sums."""
+    H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+    Hd = np.zeros(21, np.float64); gd = np.zeros(6, np.float64); cnt = np.zeros(3, np.int32)
+    T = pose_arg(pose); K = _cam(cam); R = _rt_arg(Rt)
+    lib().orc_hessgrad_robot(src.h, trg.h, level, _ptr(T), _ptr(R), C.byref(params), _ptr(K), _ptr(H), _ptr(g), _ptr(Hd), _ptr(gd), _ptr(cnt))
+    return dict(H=H.reshape(6, 6), g=g, Hd=Hd, gd=gd, n_visible=int(cnt[0]), n_photo=int(cnt[1]))
+
+
+def align_rig(src, trg, Rt, guess, params, cam, faithful=True, accum=ACC_FAITHFUL):
+    """RegisterRGBD360::RegisterDensePhotoICP over 8 (source, target) sensor frames.  faithful: new_error is evaluated at
+    pose_estim as upstream does (RegisterRGBD360.h:462, 488); False: at the candidate."""
+    res = Result()
+    sp = (C.c_void_p * 8)(*[f.h for f in src]); tp = (C.c_void_p * 8)(*[f.h for f in trg])
+    T = pose_arg(guess); K = _cam(cam); R = _rt_arg(Rt)
+    lib().orc_align_rig(sp, tp, _ptr(R), _ptr(T), C.byref(params), _ptr(K), int(bool(faithful)), accum, C.byref(res))
+    return res
 
 
 def synth_gt_pose(kind, src_id, trg_id):

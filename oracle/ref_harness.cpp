@@ -257,4 +257,83 @@ int ref_lut(void* h, float* xyz, int cap_points) {
         for (int k = 0; k < 3; ++k) xyz[3 * i + k] = r->LUT_xyz_sphere[i](k);
     return n;
 }
+
+// ---- the 8-sensor rig: calcPhotoICPError_robot (RPI.h:4905) / calcHessianGradient_robot (RPI.h:5100)
+//      of ONE sensor (source / target frames and camera matrix set through the handle); Rt: column-major 4x4
+double ref_error_robot(void* h, int level, const float* pose, const float* Rt, int method) {
+    RegisterPhotoICP* r = (RegisterPhotoICP*)h;
+    Capture c;
+    const Eigen::Matrix4f M = to_mat4(Rt);
+    return r->calcPhotoICPError_robot(level, to_mat4(pose), M, (RegisterPhotoICP::costFuncType)method);
+}
+void ref_hessgrad_robot(void* h, int level, const float* pose, const float* Rt, int method, float* H, float* g) {
+    RegisterPhotoICP* r = (RegisterPhotoICP*)h;
+    Capture c;
+    const Eigen::Matrix4f M = to_mat4(Rt);
+    r->calcHessianGradient_robot(level, to_mat4(pose), M, (RegisterPhotoICP::costFuncType)method);
+    Eigen::Matrix<float, 6, 6> Hm = r->getHessian();
+    Eigen::Matrix<float, 6, 1> gm = r->getGradient();
+    for (int i = 0; i < 36; ++i) H[i] = Hm.data()[i];
+    for (int i = 0; i < 6; ++i) g[i] = gm.data()[i];
+}
+}  // extern "C"
+
+// ---- RegisterRGBD360::RegisterDensePhotoICP (RegisterRGBD360.h:344-520), VERBATIM: the Makefile cuts the member function
+//      out of /root/reference/include/RegisterRGBD360.h at build time into oracle/_ref/ (a build product, never committed);
+//      the scaffold below supplies what it touches -- Frame360::frameRGBD_[8] (getRGBImage / getDepthImage),
+//      Frame360::calib->Rt_[8], the members rigidTransf / informationM / bRegistrationDone and the registrationType enum.
+//      RegisterRGBD360.h as a whole needs Frame360.h (PCL, PbMap, boost).  NOTE: the function calls
+//      omp_set_num_threads(8) and sums the sensors' errors with an OpenMP reduction whose combination order is the threads'
+//      arrival order, so `error - new_error` (both evaluated at pose_estim upstream) is 0 or +-1 ulp from run to run.
+#define NUM_ASUS_SENSORS 8
+struct RefSensorFrame {
+    cv::Mat rgb, depth;
+    cv::Mat& getRGBImage() { return rgb; }
+    cv::Mat& getDepthImage() { return depth; }
+};
+struct RefRigCalib { Eigen::Matrix4f Rt_[NUM_ASUS_SENSORS]; };
+struct Frame360 {
+    RefSensorFrame frameRGBD_[NUM_ASUS_SENSORS];
+    RefRigCalib* calib;
+};
+class RegisterRGBD360 {
+public:
+    Eigen::Matrix4f rigidTransf;
+    Eigen::Matrix<float, 6, 6> informationM;
+    bool bRegistrationDone;
+    enum registrationType { DEFAULT_6DoF, PLANAR_3DoF, PLANAR_ODOMETRY_3DoF };
+    RegisterRGBD360() : bRegistrationDone(false) {}
+#include "_ref/register_rgbd360_dense_member.inc"
+};
+
+extern "C" {
+// frame1 (target) / frame2 (source): 8 x h x w x 3 u8 and 8 x h x w u16; Rt: 8 column-major 4x4; guess column-major.
+// Returns the function's bool; pose = rigidTransf, info = informationM (column-major 6x6; uninitialised upstream when
+// no loop body ran).
+int ref_rig_align(const uint8_t* rgb1, const uint16_t* d1, const uint8_t* rgb2, const uint16_t* d2, int h, int w,
+                  const float* Rt, const float* guess, int method, float* pose, float* info) {
+    RefRigCalib calib;
+    Frame360 f1, f2;
+    f1.calib = &calib; f2.calib = &calib;
+    for (int s = 0; s < NUM_ASUS_SENSORS; ++s) {
+        calib.Rt_[s] = to_mat4(Rt + 16 * s);
+        f1.frameRGBD_[s].rgb = own_rgb(rgb1 + (size_t)s * h * w * 3, h, w);
+        f1.frameRGBD_[s].depth = own_depth(d1 + (size_t)s * h * w, h, w);
+        f2.frameRGBD_[s].rgb = own_rgb(rgb2 + (size_t)s * h * w * 3, h, w);
+        f2.frameRGBD_[s].depth = own_depth(d2 + (size_t)s * h * w, h, w);
+    }
+    RegisterRGBD360 reg;
+    reg.informationM = Eigen::Matrix<float, 6, 6>::Zero();
+    bool ok;
+    {
+        // the function prints from inside its OpenMP regions: a stateless sink (a std::stringbuf is not thread-safe)
+        struct NullBuf : std::streambuf { int overflow(int ch) { return ch; } std::streamsize xsputn(const char*, std::streamsize n) { return n; } } sink;
+        struct Redirect { std::streambuf* old; Redirect(std::streambuf* b) { old = std::cout.rdbuf(b); } ~Redirect() { std::cout.rdbuf(old); } } redirect(&sink);
+        omp_set_dynamic(0);
+        ok = reg.RegisterDensePhotoICP(&f1, &f2, to_mat4(guess), (RegisterPhotoICP::costFuncType)method, RegisterRGBD360::DEFAULT_6DoF);
+    }
+    for (int i = 0; i < 16; ++i) pose[i] = reg.rigidTransf.data()[i];
+    for (int i = 0; i < 36; ++i) info[i] = reg.informationM.data()[i];
+    return ok ? 1 : 0;
+}
 }

@@ -54,6 +54,10 @@ def lib(pinned=False):
         L.ref_error_pinhole.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_hessgrad_pinhole.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_lut.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_error_robot.restype = C.c_double
+        L.ref_error_robot.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_hessgrad_robot.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_rig_align.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _libs[pinned] = L
     return _libs[pinned]
 
@@ -158,6 +162,15 @@ class Reference:
         self.L.ref_hessgrad_pinhole(self.h, level, _ptr(_pose_arg(pose)), method, _ptr(H), _ptr(g))
         return H.reshape(6, 6).T.copy(), g
 
+    # ---- the 8-sensor rig: calcPhotoICPError_robot / calcHessianGradient_robot of this sensor (RPI.h:4905, 5100)
+    def error_robot(self, level, pose, Rt, method=0):
+        return self.L.ref_error_robot(self.h, level, _ptr(_pose_arg(pose)), _ptr(_pose_arg(Rt)), method)
+
+    def hessgrad_robot(self, level, pose, Rt, method=0):
+        H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+        self.L.ref_hessgrad_robot(self.h, level, _ptr(_pose_arg(pose)), _ptr(_pose_arg(Rt)), method, _ptr(H), _ptr(g))
+        return H.reshape(6, 6).T.copy(), g
+
     def lut(self):
         n = self.L.ref_lut(self.h, None, 0)
         out = np.zeros((n, 3), np.float32)
@@ -215,3 +228,17 @@ def stitch_camera(pinned=False):
     out = np.zeros(4, np.float32)
     stitch_lib(pinned).refstitch_camera(out.ctypes.data)
     return tuple(float(x) for x in out)
+
+
+def rig_align(rgb1, d1, rgb2, d2, Rt, guess=None, method=0, pinned=False):
+    """RegisterRGBD360::RegisterDensePhotoICP as the reference wrote it (cut out verbatim at build time, see
+    oracle/ref_harness.cpp): frame1 = target (8 x h x w [x 3]), frame2 = source, Rt 8 x 4 x 4 row-major numpy.
+    -> dict(ok, pose 4x4, info 6x6).  Its OpenMP reduction makes the accept decisions depend on thread arrival order."""
+    L = lib(pinned)
+    rgb1 = np.ascontiguousarray(rgb1, np.uint8); rgb2 = np.ascontiguousarray(rgb2, np.uint8)
+    d1 = np.ascontiguousarray(d1, np.uint16); d2 = np.ascontiguousarray(d2, np.uint16)
+    h, w = d1.shape[1:]
+    R = np.ascontiguousarray(np.asarray(Rt, np.float32).reshape(8, 4, 4).transpose(0, 2, 1)).reshape(8, 16)
+    pose = np.zeros(16, np.float32); info = np.zeros(36, np.float32)
+    ok = L.ref_rig_align(_ptr(rgb1), _ptr(d1), _ptr(rgb2), _ptr(d2), h, w, _ptr(R), _ptr(_pose_arg(guess)), method, _ptr(pose), _ptr(info))
+    return dict(ok=bool(ok), pose=pose.reshape(4, 4).T.copy(), info=info.reshape(6, 6).T.copy())

@@ -224,6 +224,7 @@ public:
         }
         return (T)det;
     }
+    T det() const { return determinant(); }          // MRPT's Eigen plugin (RegisterRGBD360.h:511: printed only)
     Matrix inverse() const {
         assert(r_ == c_);
         Matrix inv; inv.resize(r_, c_);
@@ -232,6 +233,13 @@ public:
             for (int i = 0; i < 36; ++i) in[i] = (float)data()[i];
             r360_inverse6(in, out);
             for (int i = 0; i < 36; ++i) inv.data()[i] = (T)out[i];
+            return inv;
+        }
+        if (r_ == 4 && sizeof(T) == sizeof(float)) {   // sensor extrinsics (RPI.h:4922, Calib360.h:129): same restatement as the product's
+            float in[16], out[16];
+            for (int i = 0; i < 16; ++i) in[i] = (float)data()[i];
+            r360_inverse4(in, out);
+            for (int i = 0; i < 16; ++i) inv.data()[i] = (T)out[i];
             return inv;
         }
         const int n = r_;

@@ -976,6 +976,298 @@ int align_pinhole(const Frame* src, const Frame* trg, const float* guess, const 
     return 0;
 }
 
+// ------------------------------------------------------------------ f4: the 8-sensor rig (RegisterRGBD360::RegisterDensePhotoICP)
+// calcPhotoICPError_robot (RPI.h:4905-5092) and calcHessianGradient_robot (RPI.h:5100-5407), the branches taken with
+// bUseSalientPixels = false, and the driver RegisterRGBD360::RegisterDensePhotoICP (RegisterRGBD360.h:344-520) that sums
+// them over the rig's 8 sensors.  What the restatement keeps:
+//   * the ERROR function warps with ONE matrix relPoseCam = Rt^-1 * pose * Rt formed in float, float intrinsics, a
+//     double 1/z and double pixel coordinates, applies no saliency test and returns the SUM of squared weighted
+//     residuals (no RMS); its depth term (methods 1, 2) uses the untransformed source depth;
+//   * the HESSIAN function warps with three matrix-vector products (Rt, pose, Rt^-1), DOUBLE intrinsics (the
+//     back-projection is formed in double and narrowed), applies the photo saliency `continue`, and accumulates H and g
+//     in float pixel by pixel in row-major order (no OpenMP: the pragma is commented out upstream);
+//   * the Hessian's depth row subtracts `jacobianRt_z`, a matrix that is DECLARED BUT NEVER ASSIGNED upstream
+//     (RPI.h:5217-5218, 5366-5367: the statement `jacobianT36.block(2,0,1,6);` has no effect): the depth methods are
+//     undefined behaviour there, so only PHOTO_CONSISTENCY (the driver's default and what its callers pass) is defined;
+//   * the driver evaluates `new_error` at pose_estim instead of pose_estim_temp (RegisterRGBD360.h:462, 488): with a
+//     deterministic summation diff_error is exactly 0, no step is ever accepted, every level runs ONE loop body and the
+//     function returns its initial guess with the summed Hessian at that guess.  `faithful = 0` evaluates the candidate
+//     instead (the evident intent); everything else is unchanged.
+// Third-party arithmetic: Matrix4f::inverse() = r360_inverse4, 4x4 / 4x1 products summed k ascending, rank / 6x6 inverse /
+// exponential as the pinhole alignFrames.
+inline int round_d_to_int(double v) {
+    const double r = round(v);
+    return (r >= -2147483648.0 && r <= 2147483647.0) ? (int)r : INT_MIN;       // x86 cvttsd2si on overflow / NaN
+}
+inline void mat4_vec4(const float* M, const float* v, float* o) {               // Eigen 4x4 * 4x1, k ascending
+    for (int i = 0; i < 4; ++i) o[i] = ((M[i] * v[0] + M[i + 4] * v[1]) + M[i + 8] * v[2]) + M[i + 12] * v[3];
+}
+double error_robot(const Frame* src, const Frame* trg, int level, const float* pose, const float* Rt,
+                   const r360_params* P, const float* cam, int* n_terms) {
+    const PinK k = pinhole_consts(src, level, cam);                                // RPI.h:4915-4921: float, as errorPhotoICP
+    float Rt_inv[16], tmp[16], rel[16];
+    r360_inverse4(Rt, Rt_inv);                                                     // RPI.h:4923
+    r360_mat4_mul(Rt_inv, pose, tmp);
+    r360_mat4_mul(tmp, Rt, rel);                                                   // RPI.h:4924
+    const double stdDevPhoto_inv = 1. / P->std_photo;                              // RPI.h:4927
+    const float* Is = src->gray[level].data();
+    const float* Ds = src->depth[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Dt = trg->depth[level].data();
+    const int method = P->method;
+    double error2 = 0.0;
+    int n = 0;
+    for (int r = 0; r < k.rows; ++r)
+        for (int c = 0; c < k.cols; ++c) {
+            const size_t i = (size_t)r * k.cols + c;
+            float p[4];
+            p[2] = Ds[i];
+            if (!(P->min_depth < p[2] && p[2] < P->max_depth)) continue;           // RPI.h:5018
+            p[0] = (c - k.ox) * p[2] * k.inv_fx;
+            p[1] = (r - k.oy) * p[2] * k.inv_fy;
+            p[3] = 1;
+            float tp[4];
+            mat4_vec4(rel, p, tp);                                                 // RPI.h:5025
+            const double inv_z = 1.0 / tp[2];
+            const double tc = (tp[0] * k.fx) * inv_z + k.ox;                       // RPI.h:5030-5031
+            const double tr = (tp[1] * k.fy) * inv_z + k.oy;
+            const int ri = round_d_to_int(tr), ci = round_d_to_int(tc);
+            if (!((ri >= 0 && ri < k.rows) && (ci >= 0 && ci < k.cols))) continue;
+            const size_t j = (size_t)ri * k.cols + ci;
+            if (method == R360_PHOTO_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+                const float photoDiff = It[j] - Is[i];
+                const double weight_photo = r360_huber(photoDiff, P->std_photo) * stdDevPhoto_inv;
+                const float werr = weight_photo * photoDiff;
+                error2 += werr * werr;
+                ++n;
+            }
+            if (method == R360_DEPTH_CONSISTENCY || method == R360_PHOTO_DEPTH) {
+                const float depth2 = Dt[j];
+                if (std::isfinite(depth2)) {
+                    const float depth1 = Ds[i];                                    // RPI.h:5066: the UNtransformed source depth
+                    const float depthDiff = depth2 - depth1;
+                    const float sd = P->std_depth * depth1;
+                    const double weight_depth = r360_huber(depthDiff, sd) / sd;
+                    const float werr = weight_depth * depthDiff;
+                    error2 += werr * werr;
+                    ++n;
+                }
+            }
+        }
+    if (n_terms) *n_terms = n;
+    return error2;
+}
+// PHOTO_CONSISTENCY only (see above).  H column-major 6x6 float, accumulated as upstream; Hd / gd: the same rows in double.
+void hessgrad_robot(const Frame* src, const Frame* trg, int level, const float* pose, const float* Rt,
+                    const r360_params* P, const float* cam, HessOut* out) {
+    const int rows = src->rows >> level, cols = src->cols >> level;
+    const double scaleFactor = 1.0 / pow(2, level);                                // RPI.h:5108-5114: double
+    const double fx = cam[0] * scaleFactor, fy = cam[1] * scaleFactor, ox = cam[2] * scaleFactor, oy = cam[3] * scaleFactor;
+    const double inv_fx = 1. / fx, inv_fy = 1. / fy;
+    const double stdDevPhoto_inv = 1. / P->std_photo;
+    float Rt_inv[16];
+    r360_inverse4(Rt, Rt_inv);
+    const float* Is = src->gray[level].data();
+    const float* Ds = src->depth[level].data();
+    const float* It = trg->gray[level].data();
+    const float* Ix = trg->ggx[level].data();
+    const float* Iy = trg->ggy[level].data();
+    float Hf[36], gf[6];
+    double Hd[36], gd[6];
+    for (int q = 0; q < 36; ++q) { Hf[q] = 0.f; Hd[q] = 0.0; }
+    for (int q = 0; q < 6; ++q) { gf[q] = 0.f; gd[q] = 0.0; }
+    int nVisible = 0, nPhoto = 0;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const size_t i = (size_t)r * cols + c;
+            float p[4];
+            p[2] = Ds[i];
+            if (!(P->min_depth < p[2] && p[2] < P->max_depth)) continue;           // RPI.h:5297
+            p[0] = (c - ox) * p[2] * inv_fx;                                       // double, narrowed (RPI.h:5299-5300)
+            p[1] = (r - oy) * p[2] * inv_fy;
+            p[3] = 1;
+            float p1[4], p2[4], tp[4];
+            mat4_vec4(Rt, p, p1);                                                  // RPI.h:5304-5306
+            mat4_vec4(pose, p1, p2);
+            mat4_vec4(Rt_inv, p2, tp);
+            const double inv_z = 1.0 / tp[2];
+            const double tc = (tp[0] * fx) * inv_z + ox;
+            const double tr = (tp[1] * fy) * inv_z + oy;
+            const int ri = round_d_to_int(tr), ci = round_d_to_int(tc);
+            if (!((ri >= 0 && ri < rows) && (ci >= 0 && ci < cols))) continue;
+            ++nVisible;
+            const size_t j = (size_t)ri * cols + ci;
+            // jacobianT36 = Rt_inv(3x3) * [I | -skew(p2)], products summed k ascending (RPI.h:5322-5326)
+            const float x = p2[0], y = p2[1], z = p2[2];
+            float T36[3][6];
+            for (int a = 0; a < 3; ++a) {
+                const float R0 = Rt_inv[a], R1 = Rt_inv[a + 4], R2 = Rt_inv[a + 8];
+                T36[a][0] = (R0 * 1.f + R1 * 0.f) + R2 * 0.f;
+                T36[a][1] = (R0 * 0.f + R1 * 1.f) + R2 * 0.f;
+                T36[a][2] = (R0 * 0.f + R1 * 0.f) + R2 * 1.f;
+                T36[a][3] = (R0 * 0.f + R1 * (-z)) + R2 * y;
+                T36[a][4] = (R0 * z + R1 * 0.f) + R2 * (-x);
+                T36[a][5] = (R0 * (-y) + R1 * x) + R2 * 0.f;
+            }
+            const float P00 = fx * inv_z, P11 = fy * inv_z;                       // RPI.h:5328-5337 (double, narrowed)
+            const float P02 = -fx * tp[0] * inv_z * inv_z, P12 = -fy * tp[1] * inv_z * inv_z;
+            float W0[6], W1[6];                                                   // jacobianWarpRt = jacobianProj23 * jacobianT36
+            for (int q = 0; q < 6; ++q) {
+                W0[q] = (P00 * T36[0][q] + 0.f * T36[1][q]) + P02 * T36[2][q];
+                W1[q] = (0.f * T36[0][q] + P11 * T36[1][q]) + P12 * T36[2][q];
+            }
+            if (fabsf(Ix[j]) < P->thres_sal_int && fabsf(Iy[j]) < P->thres_sal_int) continue;     // RPI.h:5354-5355
+            const float photoDiff = It[j] - Is[i];
+            const double weight_photo = r360_huber(photoDiff, P->std_photo) * stdDevPhoto_inv;
+            const double weightedErrorPhoto = weight_photo * photoDiff;
+            const float wf = (float)weight_photo;                                 // double * Matrix<float>: the scalar is narrowed first
+            const float a0 = wf * Ix[j], a1 = wf * Iy[j];
+            float J[6];
+            for (int q = 0; q < 6; ++q) J[q] = a0 * W0[q] + a1 * W1[q];
+            const float rf = (float)weightedErrorPhoto;
+            ++nPhoto;
+            for (int a = 0; a < 6; ++a) {
+                for (int b = 0; b < 6; ++b) { const float pr = J[a] * J[b]; Hf[a + 6 * b] += pr; Hd[a + 6 * b] += pr; }
+                const float pr = J[a] * rf; gf[a] += pr; gd[a] += pr;
+            }
+        }
+    int q = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++q) out->Hd[q] = Hd[a + 6 * b];
+    for (int a = 0; a < 36; ++a) out->H[a] = Hf[a];
+    for (int a = 0; a < 6; ++a) { out->gd[a] = gd[a]; out->g[a] = gf[a]; }
+    out->n_visible = nVisible; out->n_photo = nPhoto; out->n_depth = 0;
+}
+// RegisterRGBD360::RegisterDensePhotoICP.  src / trg: the 8 sensor frames of frame2 / frame1; Rt: 8 column-major 4x4
+// (calib->Rt_).  out->pose = rigidTransf, out->hessian = informationM (zero when no loop body ever ran: upstream
+// returns an uninitialised matrix then), out->status = ILL-POSED when the function returns false.
+// accum_mode 0: H, g of each sensor in float, summed over the sensors in float (upstream); 1: double sums.
+template <class M>
+int align_rig(Frame* const* src, Frame* const* trg, const float* Rt, const float* guess, const r360_params* P,
+              const float* cam, int faithful, int accum_mode, r360_result* out) {
+    memset(out, 0, sizeof(*out));
+    const int L = P->n_levels;
+    float pose_estim[16], pose_tmp[16];
+    memcpy(pose_estim, guess, sizeof(pose_estim));
+    float H[36], g[6];
+    memset(H, 0, sizeof(H)); memset(g, 0, sizeof(g));
+    double error = 0.0;
+    auto norm6 = [](const float* u) {
+        float a = u[0] * u[0] + (u[1] * u[1] + u[2] * u[2]);
+        float b = u[3] * u[3] + (u[4] * u[4] + u[5] * u[5]);
+        return sqrtf(a + b);
+    };
+    auto exp_mul = [&](const float* upd, float* dst) {                             // CPose3D::exp(update) * pose_estim
+        double ud[6], Td[16], A, B;
+        for (int a = 0; a < 6; ++a) ud[a] = (double)upd[a];
+        const double th2 = ud[3] * ud[3] + ud[4] * ud[4] + ud[5] * ud[5];
+        if (r360_rodrigues_small(th2, &A, &B)) {
+            const double th = sqrt(th2);
+            double sn, cs;
+            M::sincos_d(th, &sn, &cs);
+            const double inv_th = 1.0 / th;
+            A = sn * inv_th;
+            B = (1 - cs) * (inv_th * inv_th);
+        }
+        r360_pseudo_exp_AB(ud, A, B, Td);
+        r360_exp_translation(ud, A, B, th2, Td);
+        float Tf[16];
+        for (int a = 0; a < 16; ++a) Tf[a] = (float)Td[a];
+        r360_mat4_mul(Tf, pose_estim, dst);
+    };
+    auto total_error = [&](int level, const float* pose) {
+        double e = 0.0;
+        for (int s = 0; s < 8; ++s) e += error_robot(src[s], trg[s], level, pose, Rt + 16 * s, P, cam, nullptr);
+        return e;
+    };
+    auto damped_update = [&](double lambda, float* upd) {                          // -(H + lambda diag H)^-1 g
+        float Hl[36], inv[36];
+        const float lam = (float)lambda;
+        for (int q = 0; q < 36; ++q) Hl[q] = H[q];
+        for (int a = 0; a < 6; ++a) Hl[a + 6 * a] = H[a + 6 * a] + lam * H[a + 6 * a];
+        r360_inverse6(Hl, inv);
+        r360_solve_update(inv, g, upd);
+    };
+    for (int level = L - 1; level >= 0; --level) {
+        double lambda = 0.001;                                                     // RegisterRGBD360.h:391
+        const double step = 10;
+        int it = 0;
+        const double tol_residual = pow(10, -1), tol_update = pow(10, -6);
+        float upd[6] = { 1, 1, 1, 1, 1, 1 };
+        error = total_error(level, pose_estim);                                    // :403-410
+        out->passes[level] = 1;
+        double diff_error = error;
+        while (it < 10 && norm6(upd) > tol_update && diff_error > tol_residual) {
+            memset(H, 0, sizeof(H)); memset(g, 0, sizeof(g));
+            double Hd[21], gd[6];
+            memset(Hd, 0, sizeof(Hd)); memset(gd, 0, sizeof(gd));
+            int nvis = 0;
+            for (int s = 0; s < 8; ++s) {                                          // :427-440
+                HessOut ho;
+                hessgrad_robot(src[s], trg[s], level, pose_estim, Rt + 16 * s, P, cam, &ho);
+                for (int q = 0; q < 36; ++q) H[q] += ho.H[q];
+                for (int q = 0; q < 6; ++q) g[q] += ho.g[q];
+                for (int q = 0; q < 21; ++q) Hd[q] += ho.Hd[q];
+                for (int q = 0; q < 6; ++q) gd[q] += ho.gd[q];
+                nvis += ho.n_visible;
+            }
+            if (accum_mode != 0) {
+                int q = 0;
+                for (int a = 0; a < 6; ++a)
+                    for (int b = a; b < 6; ++b, ++q) H[a + 6 * b] = H[b + 6 * a] = (float)Hd[q];
+                for (int a = 0; a < 6; ++a) g[a] = (float)gd[a];
+            }
+            out->n_visible = nvis;
+            ++out->passes[level];
+            float Hl[36];
+            const float lam = (float)lambda;
+            for (int q = 0; q < 36; ++q) Hl[q] = H[q];
+            for (int a = 0; a < 6; ++a) Hl[a + 6 * a] = H[a + 6 * a] + lam * H[a + 6 * a];
+            if (r360_rank6(Hl) != 6) {                                             // :443-450
+                out->status = R360_PAIR_ILL_POSED;
+                memcpy(out->pose, pose_estim, sizeof(pose_estim));
+                memcpy(out->hessian, H, sizeof(H)); memcpy(out->gradient, g, sizeof(g));
+                out->final_error = error;
+                return 0;
+            }
+            damped_update(lambda, upd);                                            // :453
+            exp_mul(upd, pose_tmp);
+            double new_error = total_error(level, faithful ? pose_estim : pose_tmp);    // :459-462
+            ++out->passes[level];
+            diff_error = error - new_error;
+            if (diff_error > 0) {
+                lambda /= step;
+                memcpy(pose_estim, pose_tmp, sizeof(pose_estim));
+                error = new_error;
+                it = it + 1;
+            } else {
+                unsigned LM_it = 0;
+                while (LM_it < 1 && diff_error < 0) {                              // :474-500
+                    lambda = lambda * step;
+                    damped_update(lambda, upd);
+                    exp_mul(upd, pose_tmp);
+                    new_error = total_error(level, faithful ? pose_estim : pose_tmp);
+                    ++out->passes[level];
+                    diff_error = error - new_error;
+                    if (diff_error > 0) {
+                        memcpy(pose_estim, pose_tmp, sizeof(pose_estim));
+                        error = new_error;
+                        it = it + 1;
+                    }
+                    LM_it = LM_it + 1;
+                }
+            }
+        }
+        out->iters[level] = it;
+    }
+    memcpy(out->pose, pose_estim, sizeof(pose_estim));
+    memcpy(out->hessian, H, sizeof(H));
+    memcpy(out->gradient, g, sizeof(g));
+    out->final_error = error;
+    out->final_err2 = error;
+    return 0;
+}
+
 // ------------------------------------------------------------------ a10 alignFrames360
 template <class M>
 int align360(const Frame* src, const Frame* trg, const float* guess, const r360_params* P,
@@ -1326,6 +1618,33 @@ int orc_align_pinhole(void* srcv, void* trgv, const float* guess, const r360_par
     return align_pinhole<MathPinned>((Frame*)srcv, (Frame*)trgv, g0, P, cam, accum_mode, out, trace, trace_cap);
 }
 
+// ---- f4: the 8-sensor rig
+int orc_error_robot(void* srcv, void* trgv, int level, const float* pose, const float* Rt, const r360_params* P, const float* cam,
+                    double* error2, int* n_terms) {
+    const double e = error_robot((Frame*)srcv, (Frame*)trgv, level, pose, Rt, P, cam, n_terms);
+    if (error2) *error2 = e;
+    return 0;
+}
+int orc_hessgrad_robot(void* srcv, void* trgv, int level, const float* pose, const float* Rt, const r360_params* P, const float* cam,
+                       float* H, float* g, double* Hd, double* gd, int* counts) {
+    HessOut ho;
+    hessgrad_robot((Frame*)srcv, (Frame*)trgv, level, pose, Rt, P, cam, &ho);
+    if (H) memcpy(H, ho.H, sizeof(ho.H));
+    if (g) memcpy(g, ho.g, sizeof(ho.g));
+    if (Hd) memcpy(Hd, ho.Hd, sizeof(ho.Hd));
+    if (gd) memcpy(gd, ho.gd, sizeof(ho.gd));
+    if (counts) { counts[0] = ho.n_visible; counts[1] = ho.n_photo; counts[2] = 0; }
+    return 0;
+}
+int orc_align_rig(void* const* srcv, void* const* trgv, const float* Rt, const float* guess, const r360_params* P, const float* cam,
+                  int faithful, int accum_mode, r360_result* out) {
+    float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    const float* g0 = guess ? guess : ident;
+    if (g_math_mode) return align_rig<MathLibm>((Frame* const*)srcv, (Frame* const*)trgv, Rt, g0, P, cam, faithful, accum_mode, out);
+    return align_rig<MathPinned>((Frame* const*)srcv, (Frame* const*)trgv, Rt, g0, P, cam, faithful, accum_mode, out);
+}
+void orc_inverse4(const float* A, float* inv) { r360_inverse4(A, inv); }
+
 // Synthetic frame (host render of rgbd360_b200/csrc/synth.h).
 void orc_synth_frame(int kind, int id, int rows, int cols, uint8_t* rgb, uint16_t* depth_mm) {
     double Rd[9], td[3];
@@ -1354,10 +1673,19 @@ void orc_synth_gt_pose(int kind, int src_id, int trg_id, double* T) { r360_synth
 
 // Pinhole view of the same synthetic room (test data of the pinhole path): pixel (r, c)
 // looks along ((c - ox) / fx, (r - oy) / fy, 1) in the camera frame of frame `id`; depth_mm is the z-depth.
-void orc_synth_pinhole_frame(int kind, int id, int rows, int cols, float fx, float fy, float ox, float oy,
-                             uint8_t* rgb, uint16_t* depth_mm) {
+// Rt (optional, column-major 4x4): pose of the camera in the frame of synthetic frame `id` (a sensor of the rig).
+void orc_synth_pinhole_frame_rt(int kind, int id, int rows, int cols, float fx, float fy, float ox, float oy,
+                                const float* Rt, uint8_t* rgb, uint16_t* depth_mm) {
     double Rd[9], td[3];
     r360_synth_pose(kind, id, Rd, td);
+    if (Rt) {                                                      // camera-to-world = frame pose o Rt
+        double R2[9], t2[3];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) R2[3 * i + j] = Rd[3 * i] * Rt[4 * j] + Rd[3 * i + 1] * Rt[4 * j + 1] + Rd[3 * i + 2] * Rt[4 * j + 2];
+            t2[i] = Rd[3 * i] * Rt[12] + Rd[3 * i + 1] * Rt[13] + Rd[3 * i + 2] * Rt[14] + td[i];
+        }
+        memcpy(Rd, R2, sizeof(R2)); memcpy(td, t2, sizeof(t2));
+    }
     float R[9], t[3];
     for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
     for (int i = 0; i < 3; ++i) t[i] = (float)td[i];
@@ -1375,6 +1703,11 @@ void orc_synth_pinhole_frame(int kind, int id, int rows, int cols, float fx, flo
             rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = g;
             depth_mm[i] = (uint16_t)lround((double)range_mm * dz);
         }
+}
+
+void orc_synth_pinhole_frame(int kind, int id, int rows, int cols, float fx, float fy, float ox, float oy,
+                             uint8_t* rgb, uint16_t* depth_mm) {
+    orc_synth_pinhole_frame_rt(kind, id, rows, cols, fx, fy, ox, oy, nullptr, rgb, depth_mm);
 }
 
 void orc_stitch(int size_h, int size_w, float fx, float fy, float cx, float cy, const float* Rt_inv,

@@ -24,6 +24,28 @@ R360_HD void r360_mat4_mul(const float* A, const float* B, float* C) {
         }
 }
 
+// General 4x4 float inverse (column-major), Gauss-Jordan with partial pivoting on the augmented matrix: the
+// restatement of Eigen's Matrix4f::inverse() used for the sensor extrinsics (poseCamRobot.inverse(), RPI.h:4922, 5104;
+// Calib360.h:129).  Real Eigen uses a cofactor formula for fixed 4x4: third-party arithmetic, restated ONCE here for the
+// reference stand-in, the oracle and the product alike.
+R360_HD void r360_inverse4(const float* A, float* inv) {
+    const int n = 4;
+    float a[4 * 8];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) { a[i * 2 * n + j] = A[i + 4 * j]; a[i * 2 * n + n + j] = (i == j) ? 1.f : 0.f; }
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        for (int i = k + 1; i < n; ++i) if (fabsf(a[i * 2 * n + k]) > fabsf(a[p * 2 * n + k])) p = i;
+        if (p != k) for (int j = 0; j < 2 * n; ++j) { const float t = a[k * 2 * n + j]; a[k * 2 * n + j] = a[p * 2 * n + j]; a[p * 2 * n + j] = t; }
+        const float d = 1.f / a[k * 2 * n + k];
+        for (int j = 0; j < 2 * n; ++j) a[k * 2 * n + j] *= d;
+        for (int i = 0; i < n; ++i)
+            if (i != k) { const float f = a[i * 2 * n + k]; for (int j = 0; j < 2 * n; ++j) a[i * 2 * n + j] -= f * a[k * 2 * n + j]; }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) inv[i + 4 * j] = a[i * 2 * n + n + j];
+}
+
 // MRPT CPose3D::exp(..., pseudo_exponential = true): translation copied, rotation =
 // Rodrigues formula (rodrigues_so3_exp).  A = sin(theta)/theta and B = (1-cos(theta))/theta^2
 // come from r360_rodrigues_AB (Taylor fall-backs for tiny angles, as MRPT).  Output

@@ -83,6 +83,8 @@ struct Ctx {
     int* occ_head = nullptr; int* occ_next = nullptr; float* occ_dinv = nullptr;   // occlusion 1/2: per-texel candidate lists
     int occ_cap = 0;                                                                // pairs the scratch holds
     float cam[4] = {0.f, 0.f, 0.f, 0.f}; bool have_cam = false;                     // setCameraMatrix (pinhole contexts)
+    const float2** h_rig_src = nullptr; const float2** d_rig_src = nullptr;          // the 8-sensor rig: per pair 8 source /
+    const float** h_rig_trg = nullptr; const float** d_rig_trg = nullptr;            // target pyramids (allocated on first use)
     std::map<void*, std::pair<size_t, bool>> host_allocs;                           // r360_host_alloc: ptr -> (bytes, mmap'ed + registered?)
     uint8_t* d_gather = nullptr; size_t gather_cap = 0;                             // r360_allgather_results: send | receive records
     uint8_t* d_sens_rgb = nullptr; uint16_t* d_sens_depth = nullptr; size_t sens_cap = 0;   // ingest: sensor images of one chunk
@@ -442,6 +444,7 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_cams); cudaFreeHost(c->h_cams);
     cudaFree(c->d_sens_rgb); cudaFree(c->d_sens_depth); cudaFree(c->d_gather);
     cudaFree(c->occ_head); cudaFree(c->occ_next); cudaFree(c->occ_dinv);
+    cudaFreeHost(c->h_rig_src); cudaFree(c->d_rig_src); cudaFreeHost(c->h_rig_trg); cudaFree(c->d_rig_trg);
     for (auto& kv : c->host_allocs) {
         if (kv.second.second) { cudaHostUnregister(kv.first); munmap(kv.first, kv.second.first); }
         else cudaFreeHost(kv.first);
@@ -803,6 +806,134 @@ int r360_eval_error_pinhole(r360_ctx* c, int src, int trg, int level, const floa
     if (n_valid_photo) *n_valid_photo = cnt[1];
     if (n_valid_depth) *n_valid_depth = cnt[2];
     if (error) *error = (double)(float)(std::sqrt(acc[27] / (double)cnt[2]) + std::sqrt(acc[28] / (double)cnt[2]));   // RPI.h:768-771
+    return R360_OK;
+}
+
+// ---------------------------------------------------------------- the 8-sensor rig (RegisterRGBD360::RegisterDensePhotoICP)
+static int rig_check(r360_ctx* c, const float* Rt) {
+    if (c->P.projection != R360_PINHOLE) return fail(c, R360_E_STATE, "rig: the context was created with projection = R360_SPHERE");
+    if (!c->have_cam) return fail(c, R360_E_STATE, "rig: call r360_set_camera first (RegisterRGBD360.h:361-369)");
+    if (c->P.method != R360_PHOTO_CONSISTENCY)
+        return fail(c, R360_E_STATE, "rig: only PHOTO_CONSISTENCY is defined (calcHessianGradient_robot's depth row reads a matrix that "
+                                     "is never assigned upstream, RPI.h:5366-5367)");
+    if (c->P.occlusion != 0) return fail(c, R360_E_STATE, "rig: occlusion must be 0");
+    if (!Rt) return fail(c, R360_E_ARG, "rig: null extrinsics");
+    if (!c->d_rig_src) {
+        const size_t n = 8 * (size_t)(c->max_pairs + 1);
+        CK(c, cudaMallocHost(&c->h_rig_src, sizeof(void*) * n)); CK(c, cudaMalloc(&c->d_rig_src, sizeof(void*) * n));
+        CK(c, cudaMallocHost(&c->h_rig_trg, sizeof(void*) * n)); CK(c, cudaMalloc(&c->d_rig_trg, sizeof(void*) * n));
+    }
+    return R360_OK;
+}
+static int rig_frames(r360_ctx* c, int slot, int src_first, int trg_first) {
+    if (src_first < 0 || src_first + 8 > c->max_frames || trg_first < 0 || trg_first + 8 > c->max_frames)
+        return fail(c, R360_E_ARG, "rig: a rig frame occupies 8 consecutive slots (src %d, trg %d, %d slots)", src_first, trg_first, c->max_frames);
+    for (int s = 0; s < 8; ++s) {
+        int rc = check_pair(c, src_first + s, trg_first + s);
+        if (rc) return rc;
+        c->h_rig_src[8 * (size_t)slot + s] = c->src[src_first + s];
+        c->h_rig_trg[8 * (size_t)slot + s] = c->trg[trg_first + s];
+    }
+    return R360_OK;
+}
+static R360RigArgs rig_args(const r360_ctx* c, const float* Rt, int level) {
+    R360RigArgs r;
+    memcpy(r.Rt, Rt, sizeof(r.Rt));
+    for (int s = 0; s < 8; ++s) r360_inverse4(r.Rt[s], r.Rt_inv[s]);          // poseCamRobot.inverse(), RPI.h:4923 / 5125
+    r.src8 = c->d_rig_src; r.trg8 = c->d_rig_trg;
+    const R360PinLevel pl = pin_level(c, level);                              // RPI.h:4915-4921 (float)
+    r.fx = pl.fx; r.fy = pl.fy; r.ox = pl.ox; r.oy = pl.oy; r.inv_fx = pl.inv_fx; r.inv_fy = pl.inv_fy;
+    const double scaleFactor = 1.0 / pow(2, level);                           // RPI.h:5108-5114 (double)
+    r.dfx = c->cam[0] * scaleFactor; r.dfy = c->cam[1] * scaleFactor; r.dox = c->cam[2] * scaleFactor; r.doy = c->cam[3] * scaleFactor;
+    r.dinv_fx = 1. / r.dfx; r.dinv_fy = 1. / r.dfy;
+    return r;
+}
+
+int r360_eval_rig(r360_ctx* c, int src_first, int trg_first, int level, const float pose[16], const float* Rt,
+                  double* error2, float H[36], float g[6], int32_t* n_visible, int32_t* n_error_terms) {
+    if (!c) return R360_E_ARG;
+    int rc = rig_check(c, Rt);
+    if (rc) return rc;
+    const int slot = c->max_pairs;
+    rc = rig_frames(c, slot, src_first, trg_first);
+    if (rc) return rc;
+    R360PassArgs a;
+    rc = eval_setup(c, src_first, trg_first, level, pose, &a);
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(c->d_rig_src + 8 * (size_t)slot, c->h_rig_src + 8 * (size_t)slot, sizeof(void*) * 8, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_rig_trg + 8 * (size_t)slot, c->h_rig_trg + 8 * (size_t)slot, sizeof(void*) * 8, cudaMemcpyHostToDevice, c->st));
+    const R360RigArgs rig = rig_args(c, Rt, level);
+    // (the frame tables are indexed by the pair id, here the spare slot)
+    r360_launch_rig_eval(c->st, a, rig, 1, c->sm_count);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    R360Fx fx[R360_ACC_STRIDE];
+    int cnt[R360_ACC_INTS];
+    CK(c, cudaMemcpyAsync(fx, c->d_acc + (size_t)slot * R360_ACC_STRIDE, sizeof(fx), cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(cnt, c->d_cnt + (size_t)slot * R360_ACC_INTS, sizeof(cnt), cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    if (error2) *error2 = r360_fx_get(fx, 27);
+    if (H) {
+        int q = 0;
+        for (int x = 0; x < 6; ++x)
+            for (int y = x; y < 6; ++y, ++q) H[x + 6 * y] = H[y + 6 * x] = (float)r360_fx_get(fx, q);
+    }
+    if (g) for (int x = 0; x < 6; ++x) g[x] = (float)r360_fx_get(fx, 21 + x);
+    if (n_visible) *n_visible = cnt[0];
+    if (n_error_terms) *n_error_terms = cnt[1];
+    return R360_OK;
+}
+
+int r360_register_rig_pairs(r360_ctx* c, int n_pairs, const int32_t* src_first, const int32_t* trg_first, const float* Rt,
+                            const float* init_pose, int faithful_new_error, r360_result* out) {
+    if (!c) return R360_E_ARG;
+    if (n_pairs < 0 || n_pairs > c->max_pairs || !src_first || !trg_first || !out)
+        return fail(c, R360_E_ARG, "register_rig_pairs: n_pairs %d not in [0,%d] or null argument", n_pairs, c->max_pairs);
+    if (n_pairs == 0) return R360_OK;
+    int rc = rig_check(c, Rt);
+    if (rc) return rc;
+    CK(c, cudaSetDevice(c->device));
+    for (int p = 0; p < n_pairs; ++p) {
+        rc = rig_frames(c, p, src_first[p], trg_first[p]);
+        if (rc) return rc;
+        c->h_srcb[p] = c->src[src_first[p]]; c->h_trgb[p] = c->trg[trg_first[p]];
+        c->h_idx[p] = src_first[p]; c->h_idx[n_pairs + p] = trg_first[p];
+    }
+    if (init_pose) memcpy(c->h_pose, init_pose, sizeof(float) * 16 * n_pairs);
+    CK(c, cudaEventRecord(c->ev_t0, c->st));
+    CK(c, cudaMemcpyAsync(c->d_rig_src, c->h_rig_src, sizeof(void*) * 8 * n_pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_rig_trg, c->h_rig_trg, sizeof(void*) * 8 * n_pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_idx, c->h_idx, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_idx + c->max_pairs + 1, c->h_idx + n_pairs, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, c->st));
+    if (init_pose) CK(c, cudaMemcpyAsync(c->d_pose, c->h_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyHostToDevice, c->st));
+    R360GnArgs g = gn_args(c, n_pairs, nullptr, 0);
+    g.params.max_iters = 10;                                   // RegisterRGBD360.h:395-397
+    g.params.tol_residual = pow(10, -1);
+    g.params.tol_update = pow(10, -6);
+    g.lambda0 = 0.001;                                         // :391
+    g.rig_faithful = faithful_new_error ? 1 : 0;
+    r360_launch_pairs_init(c->st, g, c->d_idx, c->d_idx + c->max_pairs + 1, init_pose ? c->d_pose : nullptr);
+    ++c->launches;
+    for (int level = c->L - 1; level >= 0; --level) {
+        r360_launch_level_begin(c->st, g, level);
+        ++c->launches;
+        R360PassArgs a = pass_args(c, level, n_pairs, 0);
+        const R360RigArgs rig = rig_args(c, Rt, level);
+        const int n_eval = 2 * g.params.max_iters + 1;         // one initial evaluation; every loop body may add one damped retry
+        for (int k = 0; k < n_eval; ++k) {
+            r360_launch_rig_eval(c->st, a, rig, n_pairs, c->sm_count);
+            r360_launch_gn_step_rig(c->st, g, level);
+            c->launches += 2;
+        }
+    }
+    r360_launch_finalize(c->st, g, c->d_res, c->rows, c->cols, 0);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(c->h_res, c->d_res, sizeof(r360_result) * n_pairs, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaEventRecord(c->ev_t1, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    memcpy(out, c->h_res, sizeof(r360_result) * n_pairs);
+    CK(c, cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1));
     return R360_OK;
 }
 

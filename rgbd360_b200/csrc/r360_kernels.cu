@@ -781,7 +781,7 @@ __global__ void k_level_begin(R360GnArgs g, int level) {
         if (ps->status != R360_PAIR_OK) { ps->active = 0; continue; }
         for (int k = 0; k < 16; ++k) ps->pose_eval[k] = ps->pose_estim[k];
         for (int k = 0; k < 6; ++k) ps->upd[k] = 1.f;
-        ps->lambda = g.params.projection == R360_PINHOLE ? 0.01 : 1.0;     // RPI.h:4589 / 4304
+        ps->lambda = g.lambda0 > 0.0 ? g.lambda0 : (g.params.projection == R360_PINHOLE ? 0.01 : 1.0);     // RPI.h:4589 / 4304
         ps->it = 0;
         ps->phase = 0;
         ps->ev = 0;

@@ -42,6 +42,16 @@ struct R360PinLevel {
     float fx, fy, ox, oy, inv_fx, inv_fy;
 };
 
+// The 8-sensor rig (RegisterRGBD360::RegisterDensePhotoICP, RegisterRGBD360.h:344-520): extrinsics of the sensors,
+// the per-pair frame tables and the intrinsics of one level in the two precisions the reference uses.
+struct R360RigArgs {
+    float Rt[8][16], Rt_inv[8][16];     // poseCamRobot and its inverse (r360_inverse4), column-major
+    const float2* const* src8;          // device: per pair, the 8 source pyramids (frame2's sensors)
+    const float* const* trg8;           // device: per pair, the 8 target texel pyramids (frame1's sensors)
+    float fx, fy, ox, oy, inv_fx, inv_fy;            // calcPhotoICPError_robot: float (RPI.h:4915-4921)
+    double dfx, dfy, dox, doy, dinv_fx, dinv_fy;     // calcHessianGradient_robot: double (RPI.h:5108-5114)
+};
+
 struct R360StitchArgs {
     R360StitchGeom g;
     float Rt_inv[8][16];                // inverse extrinsics of the 8 sensors, column-major (Calib360.h:122-131)
@@ -61,6 +71,8 @@ struct R360GnArgs {
     float spec_margin;                  // error-only when the predicted RMS decrease < spec_margin * tol_residual (1: the plain rule)
     int* ticket;                        // device: block-completion counter (the last block compacts the active lists)
     int* work_counters;                 // device: the two dynamic-item counters of k_pass (fused, error-only): reset with the lists
+    double lambda0;                     // > 0: the level's initial lambda (the rig driver: 0.001, RegisterRGBD360.h:391)
+    int rig_faithful;                   // rig driver: 1 = new_error is evaluated at pose_estim, as upstream (RegisterRGBD360.h:462, 488)
     r360_iter_record* trace;            // device or nullptr
 };
 
@@ -83,6 +95,9 @@ void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, i
 // pinhole registration (r360_pinhole.cuh)
 void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count);
 void r360_launch_gn_step_pin(cudaStream_t st, const R360GnArgs& g, int level);
+// the 8-sensor rig (r360_pinhole.cuh)
+void r360_launch_rig_eval(cudaStream_t st, const R360PassArgs& a, const R360RigArgs& rig, int n_pairs, int sm_count);
+void r360_launch_gn_step_rig(cudaStream_t st, const R360GnArgs& g, int level);
 void r360_launch_warp_dump(cudaStream_t st, const R360PassArgs& a, int pair, int32_t* r_idx, int32_t* c_idx,
                            uint8_t* vp, uint8_t* vd, int sm_count);
 void r360_launch_index_stats(cudaStream_t st, const R360PassArgs& a, int pair, unsigned long long* out, int sm_count);

@@ -261,6 +261,285 @@ __global__ void k_gn_step_pin(R360GnArgs g, int level) {
     r360_compact_when_last(g);
 }
 
+// =========================================================================== the 8-sensor rig
+// calcPhotoICPError_robot (RPI.h:4905-5092) + calcHessianGradient_robot (RPI.h:5100-5407) of ONE sensor of ONE pair at
+// the pair's pose_eval, PHOTO_CONSISTENCY (the only method whose Hessian is defined upstream: the depth row uses a matrix
+// that is never assigned, RPI.h:5366-5367).  blockIdx.y = 8 * active pair + sensor; all 8 sensors add into the pair's
+// accumulators, which IS the driver's sum over the rig (RegisterRGBD360.h:403-440).  The two functions warp differently
+// (one float matrix vs three matrix-vector products with double intrinsics) and so may hit different texels: both chains
+// are evaluated, each with the reference's own operation sequence.
+__device__ __forceinline__ int r360_round_d_to_int(double v) {
+    const double r = round(v);
+    return (r >= -2147483648.0 && r <= 2147483647.0) ? (int)r : INT_MIN;
+}
+__device__ __forceinline__ void r360_mat4_vec4(const float* M, const float* v, float* o) {    // Eigen 4x4 * 4x1, k ascending
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = ((M[i] * v[0] + M[i + 4] * v[1]) + M[i + 8] * v[2]) + M[i + 12] * v[3];
+}
+__global__ void __launch_bounds__(R360_PIN_THREADS)
+k_rig_eval(R360PassArgs a, R360RigArgs rig) {
+    __shared__ float s_red[R360_PIN_THREADS / 32][R360_ACC_DOUBLES + 1];
+    __shared__ int s_cnt[R360_PIN_THREADS / 32][R360_ACC_INTS];
+    __shared__ float s_tmp[16], s_rel[16];
+    const int ap = blockIdx.y >> 3, sensor = blockIdx.y & 7;
+    if (ap >= *a.n_active) return;
+    const R360Level lv = a.lv;
+    const r360_params P = a.params;
+    const int pair = a.active_list[ap];
+    const R360Pair* ps = a.pairs + pair;
+    const float* Rt = rig.Rt[sensor];
+    const float* Rti = rig.Rt_inv[sensor];
+    // relPoseCam = Rt^-1 * pose * Rt (RPI.h:4924), float products summed k ascending (r360_mat4_mul's order)
+    if (threadIdx.x < 16) {
+        const int i = threadIdx.x & 3, j = threadIdx.x >> 2;
+        const float* B = ps->pose_eval;
+        float acc = Rti[i] * B[4 * j];
+        acc = acc + Rti[i + 4] * B[1 + 4 * j];
+        acc = acc + Rti[i + 8] * B[2 + 4 * j];
+        acc = acc + Rti[i + 12] * B[3 + 4 * j];
+        s_tmp[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int i = threadIdx.x & 3, j = threadIdx.x >> 2;
+        float acc = s_tmp[i] * Rt[4 * j];
+        acc = acc + s_tmp[i + 4] * Rt[1 + 4 * j];
+        acc = acc + s_tmp[i + 8] * Rt[2 + 4 * j];
+        acc = acc + s_tmp[i + 12] * Rt[3 + 4 * j];
+        s_rel[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    float rel[16], T[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { rel[k] = s_rel[k]; T[k] = ps->pose_eval[k]; }
+    const float2* __restrict__ src = rig.src8[pair * 8 + sensor] + lv.px_off;
+    const float2* __restrict__ trg = reinterpret_cast<const float2*>(rig.trg8[pair * 8 + sensor] + lv.px_off * R360_TEXEL_FLOATS);
+    const double stdDevPhoto_inv = 1. / (double)P.std_photo;                // RPI.h:4927 / 5122
+
+    float H[21], g[6];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) H[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = 0.f;
+    float sumE = 0.f;
+    int n_vis = 0, n_err = 0, n_photo = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lv.n; i += gridDim.x * blockDim.x) {
+        const int r = (int)(((unsigned long long)i * lv.div_magic) >> 40), c = i - r * lv.cols;
+        const float2 s = __ldg(&src[i]);                                   // {depth, gray}
+        const float z = s.x;
+        if (!(P.min_depth < z && z < P.max_depth)) continue;               // RPI.h:5018 / 5297
+        // ---- calcPhotoICPError_robot: float back-projection, ONE matrix, double 1/z and pixel coordinates, no saliency test
+        {
+            float p[4] = { (c - rig.ox) * z * rig.inv_fx, (r - rig.oy) * z * rig.inv_fy, z, 1.f }, tp[4];
+            r360_mat4_vec4(rel, p, tp);
+            const double inv_z = 1.0 / (double)tp[2];
+            const double tc = (double)(tp[0] * rig.fx) * inv_z + (double)rig.ox;
+            const double tr = (double)(tp[1] * rig.fy) * inv_z + (double)rig.oy;
+            const int ri = r360_round_d_to_int(tr), ci = r360_round_d_to_int(tc);
+            if ((unsigned)ri < (unsigned)lv.rows && (unsigned)ci < (unsigned)lv.cols) {
+                const float photoDiff = __ldg(trg + 3u * (unsigned)(ri * lv.cols + ci)).x - s.y;
+                const double weight_photo = (double)r360_huber(photoDiff, P.std_photo) * stdDevPhoto_inv;
+                const float werr = (float)(weight_photo * (double)photoDiff);
+                sumE += werr * werr;
+                ++n_err;
+            }
+        }
+        // ---- calcHessianGradient_robot: double intrinsics, three matrix-vector products, photo saliency `continue`
+        float p[4] = { (float)(((double)c - rig.dox) * (double)z * rig.dinv_fx), (float)(((double)r - rig.doy) * (double)z * rig.dinv_fy), z, 1.f };
+        float p1[4], p2[4], tp[4];
+        r360_mat4_vec4(Rt, p, p1);
+        r360_mat4_vec4(T, p1, p2);
+        r360_mat4_vec4(Rti, p2, tp);
+        const double inv_z = 1.0 / (double)tp[2];
+        const double tc = ((double)tp[0] * rig.dfx) * inv_z + rig.dox;
+        const double tr = ((double)tp[1] * rig.dfy) * inv_z + rig.doy;
+        const int ri = r360_round_d_to_int(tr), ci = r360_round_d_to_int(tc);
+        if (!((unsigned)ri < (unsigned)lv.rows && (unsigned)ci < (unsigned)lv.cols)) continue;
+        ++n_vis;
+        const float2* tx = trg + 3u * (unsigned)(ri * lv.cols + ci);
+        const float2 t0 = __ldg(tx), t1 = __ldg(tx + 1);                   // {gray, depth}, {Ix, Iy}
+        if ((fabsf(t1.x) < P.thres_sal_int) & (fabsf(t1.y) < P.thres_sal_int)) continue;      // RPI.h:5354-5355
+        const float x = p2[0], y = p2[1], zz = p2[2];
+        const float P00 = (float)(rig.dfx * inv_z), P11 = (float)(rig.dfy * inv_z);
+        const float P02 = (float)(-rig.dfx * (double)tp[0] * inv_z * inv_z), P12 = (float)(-rig.dfy * (double)tp[1] * inv_z * inv_z);
+        float W0[6], W1[6];                                                // jacobianWarpRt = jacobianProj23 * (Rt^-1(3x3) * [I | -skew(p2)])
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            float Tq[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float R0 = Rti[k], R1 = Rti[k + 4], R2 = Rti[k + 8];
+                Tq[k] = q == 0 ? (R0 * 1.f + R1 * 0.f) + R2 * 0.f
+                      : q == 1 ? (R0 * 0.f + R1 * 1.f) + R2 * 0.f
+                      : q == 2 ? (R0 * 0.f + R1 * 0.f) + R2 * 1.f
+                      : q == 3 ? (R0 * 0.f + R1 * (-zz)) + R2 * y
+                      : q == 4 ? (R0 * zz + R1 * 0.f) + R2 * (-x)
+                               : (R0 * (-y) + R1 * x) + R2 * 0.f;
+            }
+            W0[q] = (P00 * Tq[0] + 0.f * Tq[1]) + P02 * Tq[2];
+            W1[q] = (0.f * Tq[0] + P11 * Tq[1]) + P12 * Tq[2];
+        }
+        const float photoDiff = t0.x - s.y;
+        const double weight_photo = (double)r360_huber(photoDiff, P.std_photo) * stdDevPhoto_inv;
+        const double weightedErrorPhoto = weight_photo * (double)photoDiff;
+        const float wf = (float)weight_photo;
+        const float a0 = wf * t1.x, a1 = wf * t1.y;
+        const float rf = (float)weightedErrorPhoto;
+        float J[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) J[q] = a0 * W0[q] + a1 * W1[q];
+        ++n_photo;
+        int q = 0;
+#pragma unroll
+        for (int xx = 0; xx < 6; ++xx) {
+#pragma unroll
+            for (int yy = xx; yy < 6; ++yy, ++q) H[q] = fmaf(J[xx], J[yy], H[q]);
+            g[xx] = fmaf(J[xx], rf, g[xx]);
+        }
+    }
+    // ---- block reduction: 27 normal-equation sums + the error sum, 3 counters
+    float acc[R360_ACC_DOUBLES + 1];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) acc[k] = H[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[21 + k] = g[k];
+    acc[27] = sumE;
+    acc[28] = 0.f;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < R360_ACC_DOUBLES; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) s_red[wid][k] = v;
+    }
+    n_vis = __reduce_add_sync(0xffffffffu, n_vis);
+    n_err = __reduce_add_sync(0xffffffffu, n_err);
+    n_photo = __reduce_add_sync(0xffffffffu, n_photo);
+    if (lane == 0) { s_cnt[wid][0] = n_vis; s_cnt[wid][1] = n_err; s_cnt[wid][2] = n_photo; s_cnt[wid][3] = 0; }
+    __syncthreads();
+    if (threadIdx.x < R360_ACC_DOUBLES) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < R360_PIN_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
+        r360_fx_add(a.acc + (size_t)pair * R360_ACC_STRIDE, threadIdx.x, sum);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < R360_PIN_THREADS / 32; ++k) sum += s_cnt[k][threadIdx.x - 32];
+        atomicAdd(&a.cnt[(size_t)pair * R360_ACC_INTS + threadIdx.x - 32], sum);
+    }
+}
+
+// -(H + lambda diag H)^-1 g, then exp(update) * pose_estim -> `cand` (RegisterRGBD360.h:453-455, 478-480)
+__device__ void r360_rig_candidate(R360Pair* ps, float* cand) {
+    const float lam = (float)ps->lambda;
+    float Hd[36], inv[36], upd[6];
+    int q = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++q) Hd[a + 6 * b] = Hd[b + 6 * a] = ps->Hl[q];
+    for (int a = 0; a < 6; ++a) Hd[a + 6 * a] = Hd[a + 6 * a] + lam * Hd[a + 6 * a];
+    r360_inverse6(Hd, inv);
+    r360_solve_update(inv, ps->gl, upd);
+    double ud[6], Td[16];
+    for (int k = 0; k < 6; ++k) { ps->upd[k] = upd[k]; ud[k] = (double)upd[k]; }
+    r360_se3_exp(ud, Td);
+    float Tf[16];
+    for (int k = 0; k < 16; ++k) Tf[k] = (float)Td[k];
+    r360_mat4_mul(Tf, ps->pose_estim, cand);
+}
+
+// The state machine of RegisterRGBD360::RegisterDensePhotoICP after an evaluation (phases as k_gn_step_pin).  The
+// candidate pose_estim_temp is kept in Hc (16 of its 21 floats: the rig path does not use Hc otherwise); with
+// g.rig_faithful the pass that follows evaluates pose_estim again, as upstream does (RegisterRGBD360.h:462, 488): the sums
+// are bit-reproducible, so diff_error is exactly 0, the candidate is never taken and every level runs one loop body.
+__global__ void k_gn_step_rig(R360GnArgs g, int level) {
+    const r360_params P = g.params;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
+        R360Pair* ps = g.pairs + p;
+        if (!ps->active) continue;
+        double acc[R360_ACC_DOUBLES + 1];
+        for (int k = 0; k < R360_ACC_DOUBLES + 1; ++k) acc[k] = r360_fx_get(g.acc + (size_t)p * R360_ACC_STRIDE, k);
+        const int* cnt = g.cnt + (size_t)p * R360_ACC_INTS;
+        const double err = acc[27];                             // the SUM of squared weighted residuals over the 8 sensors
+        ps->passes[level] += 1;
+        double diff_error;
+        bool retry = false;
+        const bool evaluated_candidate = !g.rig_faithful;       // else: pose_estim again
+        auto take_h = [&]() {
+            for (int k = 0; k < 21; ++k) ps->Hl[k] = (float)acc[k];
+            for (int k = 0; k < 6; ++k) ps->gl[k] = (float)acc[21 + k];
+            ps->nvis_l = cnt[0];
+        };
+        if (ps->phase == 0) {
+            diff_error = err;                                   // RegisterRGBD360.h:412
+            ps->error = err; ps->err2 = err; ps->n_valid = cnt[1];
+            take_h();                                           // calcHessianGradient_robot(pose_estim) of the first loop body
+        } else {
+            diff_error = ps->error - err;                       // :464 / :489
+            if (diff_error > 0) {
+                if (ps->phase == 1) ps->lambda /= 10.0;         // :467 (the retry keeps lambda)
+                for (int k = 0; k < 16; ++k) ps->pose_estim[k] = ps->Hc[k];     // pose_estim = pose_estim_temp
+                ps->error = err; ps->err2 = err; ps->n_valid = cnt[1];
+                ps->it += 1;
+                if (evaluated_candidate) take_h();              // the pass ran at the new pose_estim: its H serves the next loop body
+            } else if (ps->phase == 1 && diff_error < 0) {
+                retry = true;                                   // :474
+            }
+        }
+        r360_zero_acc(g.acc, g.cnt, p);
+        if (retry) {
+            ps->lambda *= 10.0;                                 // :476
+            r360_rig_candidate(ps, ps->Hc);
+            for (int k = 0; k < 16; ++k) ps->pose_eval[k] = evaluated_candidate ? ps->Hc[k] : ps->pose_estim[k];
+            ps->phase = 2;
+            continue;
+        }
+        const float* u = ps->upd;
+        const float na = u[0] * u[0] + (u[1] * u[1] + u[2] * u[2]);
+        const float nb = u[3] * u[3] + (u[4] * u[4] + u[5] * u[5]);
+        const float unorm = sqrtf(na + nb);
+        const bool go = ps->it < P.max_iters && (double)unorm > P.tol_update && diff_error > P.tol_residual;   // :421
+        if (!go) {
+            ps->iters[level] = ps->it;
+            ps->active = 0;
+            continue;
+        }
+        // loop body: Hessian / Gradient summed over the sensors at pose_estim == (Hl, gl)        :424-440
+        ps->lvl_l = level;
+        float Hm[36];
+        {
+            int q = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b, ++q) Hm[a + 6 * b] = Hm[b + 6 * a] = ps->Hl[q];
+        }
+        const float lam = (float)ps->lambda;
+        for (int a = 0; a < 6; ++a) Hm[a + 6 * a] = Hm[a + 6 * a] + lam * Hm[a + 6 * a];
+        if (r360_rank6(Hm) != 6) {                              // :443-450: returns false with rigidTransf = pose_estim
+            ps->status = R360_PAIR_ILL_POSED;
+            ps->active = 0;
+            continue;
+        }
+        r360_rig_candidate(ps, ps->Hc);
+        for (int k = 0; k < 16; ++k) ps->pose_eval[k] = evaluated_candidate ? ps->Hc[k] : ps->pose_estim[k];
+        ps->phase = 1;
+    }
+    r360_compact_when_last(g);
+}
+
+void r360_launch_rig_eval(cudaStream_t st, const R360PassArgs& a, const R360RigArgs& rig, int n_pairs, int sm_count) {
+    long long blocks = ((long long)a.lv.n + R360_PIN_THREADS - 1) / R360_PIN_THREADS;
+    long long cap = 8LL * sm_count / (8LL * (n_pairs > 0 ? n_pairs : 1));
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const dim3 grid((unsigned)blocks, (unsigned)(8 * n_pairs));
+    k_rig_eval<<<grid, R360_PIN_THREADS, 0, st>>>(a, rig);
+}
+void r360_launch_gn_step_rig(cudaStream_t st, const R360GnArgs& g, int level) {
+    k_gn_step_rig<<<r360_blocks(g.n_pairs, 32, 1024), 32, 0, st>>>(g, level);
+}
+
 void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count) {
     long long blocks = ((long long)a.lv.n + R360_PIN_THREADS - 1) / R360_PIN_THREADS;
     long long cap = 8LL * sm_count / (n_pairs > 0 ? n_pairs : 1);

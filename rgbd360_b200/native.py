@@ -21,7 +21,7 @@ EXPORTS = [
     "r360_last_pass_stats", "r360_version", "r360_index_stats", "r360_register_host_pairs",
     "r360_default_rig", "r360_frame360_parse", "r360_stitch_frames", "r360_eval_error_occ",
     "r360_default_params_pinhole", "r360_set_camera", "r360_eval_error_pinhole",
-    "r360_allgather_results", "r360_host_alloc", "r360_host_free",
+    "r360_allgather_results", "r360_host_alloc", "r360_host_free", "r360_register_rig_pairs", "r360_eval_rig",
 ]
 
 
@@ -135,6 +135,8 @@ def lib():
     L.r360_frame360_parse.argtypes = [vp, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, C.c_size_t, vp, C.c_size_t]
     L.r360_stitch_frames.argtypes = [vp, C.POINTER(Rig), i32, i32, vp, vp, vp, vp, vp]
     L.r360_allgather_results.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.r360_register_rig_pairs.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
+    L.r360_eval_rig.argtypes = [vp, i32, i32, i32, vp, vp, C.POINTER(C.c_double), vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.r360_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.r360_host_free.argtypes = [vp, vp]
     _lib = L
@@ -419,6 +421,39 @@ class Context:
         T = pose_to_colmajor(pose)
         self._ck(self.L.r360_index_stats(self.h, src, trg, level, _p(T), _p(out)))
         return dict(valid=int(out[0]), scalar=int(out[1]), mismatch=int(out[2]))
+
+    # ---- the 8-sensor rig (RegisterRGBD360::RegisterDensePhotoICP)
+    @staticmethod
+    def _rt8(Rt):
+        M = np.asarray(Rt, np.float32)
+        if M.shape != (8, 4, 4):
+            raise ValueError(f"Rt has shape {M.shape}, expected 8 x 4 x 4 (calib->Rt_)")
+        return np.ascontiguousarray(M.transpose(0, 2, 1)).reshape(8, 16)              # column-major each
+
+    def register_rig_pairs(self, src_first, trg_first, Rt, init_pose=None, faithful=True, out=None):
+        """r360_register_rig_pairs: rig frames occupy 8 consecutive slots; src_first / trg_first = slot of sensor 0 of
+        frame2 / frame1.  Rt: 8 x 4 x 4 sensor poses (row-major numpy)."""
+        s = np.ascontiguousarray(src_first, np.int32); t = np.ascontiguousarray(trg_first, np.int32)
+        n = s.size
+        if t.size != n or n > self.max_pairs:
+            raise ValueError(f"{n} / {t.size} rig pairs (max_pairs = {self.max_pairs})")
+        res = self._check_out(out, n)
+        ip = None
+        if init_pose is not None:
+            ip = np.ascontiguousarray(init_pose, np.float32)
+            if ip.size != 16 * n:
+                raise ValueError(f"init_pose has {ip.size} floats, expected {n} x 16")
+        R = self._rt8(Rt)
+        self._ck(self.L.r360_register_rig_pairs(self.h, n, _p(s), _p(t), _p(R), _p(ip), int(bool(faithful)), _p(res)))
+        return res
+
+    def eval_rig(self, src_first, trg_first, level, pose, Rt):
+        """r360_eval_rig -> dict(error2, H 6x6, g, n_visible, n_terms): the rig's summed *_robot functions at `pose`."""
+        e = C.c_double(); nv = C.c_int32(); nt = C.c_int32()
+        H = np.zeros(36, np.float32); g = np.zeros(6, np.float32)
+        T = pose_to_colmajor(pose); R = self._rt8(Rt)
+        self._ck(self.L.r360_eval_rig(self.h, src_first, trg_first, level, _p(T), _p(R), C.byref(e), _p(H), _p(g), C.byref(nv), C.byref(nt)))
+        return dict(error2=e.value, H=H.reshape(6, 6), g=g, n_visible=nv.value, n_terms=nt.value)
 
     # ---- multi-GPU exchange and host staging memory
     def allgather_results(self, nccl_comm, local, n_ranks):

@@ -202,6 +202,46 @@ def sample_pair_self_spread(case, pinned=True, reps=2):
     return runs
 
 
+# ---- SURVEY 8f row 4, the rig: calcPhotoICPError_robot / calcHessianGradient_robot per sensor (one thread) and the
+# verbatim RegisterRGBD360::RegisterDensePhotoICP.  The driver's accept decisions depend on the arrival order of its OpenMP
+# threads (error and new_error are both evaluated at pose_estim and summed by a reduction): recorded is a run whose
+# returned pose IS the guess (no step taken at any level) -- the outcome of a reproducible summation.
+def run_reference_rig(case):
+    refbind.lib(False).ref_set_threads(1)
+    out = dict(sensors=[])
+    guess = case["guess"] if case["guess"] is not None else np.eye(4, dtype=np.float32)
+    for s in range(8):
+        R = refbind.Reference(n_levels=case["levels"], pinned=False)
+        R.set_camera(*case["cam"])
+        R.set_source(case["rgb2"][s], case["d2"][s]); R.set_target(case["rgb1"][s], case["d1"][s])
+        probes = []
+        for T in refcases.probe_poses(2) + [guess]:
+            for lvl in (0, case["levels"] - 1):
+                H, g = R.hessgrad_robot(lvl, T, case["Rt"][s], 0)
+                probes.append(dict(level=lvl, pose=np.asarray(T, np.float64).ravel().tolist(), error2=R.error_robot(lvl, T, case["Rt"][s], 0),
+                                   H=H.astype(np.float64).ravel().tolist(), g=g.astype(np.float64).tolist()))
+        out["sensors"].append(probes)
+        R.close()
+    runs = []
+    for k in range(12):
+        a = refbind.rig_align(case["rgb1"], case["d1"], case["rgb2"], case["d2"], case["Rt"], case["guess"], 0)
+        runs.append(bool(np.array_equal(a["pose"], guess)))
+        if runs[-1] and "driver" not in out:
+            out["driver"] = dict(ok=a["ok"], pose=a["pose"].astype(np.float64).ravel().tolist(), info=a["info"].astype(np.float64).ravel().tolist())
+    out["driver_runs_returning_the_guess"] = runs
+    return out
+
+
+def main_rig():
+    gold = {"_how": "oracle/_ref/librpi_ref.so: calcPhotoICPError_robot / calcHessianGradient_robot (RPI.h:4905, 5100) per sensor at one "
+                    "thread, and RegisterRGBD360::RegisterDensePhotoICP cut out verbatim at build time; see this script", "cases": {}}
+    for name in refcases.RIG_CASES:
+        gold["cases"][name] = run_reference_rig(refcases.make_rig_case(orc, name))
+        print(name, "driver runs returning the guess:", gold["cases"][name]["driver_runs_returning_the_guess"])
+    with open(os.path.join(HERE, "reference_rig.json"), "w") as f:
+        json.dump(gold, f, indent=0)
+
+
 def main_stitch():
     """SURVEY 8f row 1: Frame360::stitchSphericalImage / stitchImage + Calib360 as the reference wrote them
     (oracle/ref_stitch_harness.cpp) on the raw sensor images of samples/sphere_images_1.bin (tests/golden/
@@ -240,6 +280,8 @@ if __name__ == "__main__":
         main()
     elif len(sys.argv) > 1 and sys.argv[1] == "stitch":
         main_stitch()
+    elif len(sys.argv) > 1 and sys.argv[1] == "rig":
+        main_rig()
     elif len(sys.argv) > 1 and sys.argv[1] == "occ":
         main_occ()
     elif len(sys.argv) > 1 and sys.argv[1] == "pinhole":
@@ -249,3 +291,4 @@ if __name__ == "__main__":
         main_occ()
         main_pinhole()
         main_stitch()
+        main_rig()

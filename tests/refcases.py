@@ -118,6 +118,34 @@ PINHOLE_CASES = {
 }
 
 
+# ---- the 8-sensor rig: RegisterRGBD360::RegisterDensePhotoICP over QVGA views of the synthetic room
+# name -> (scene kind, frame1 = target id, frame2 = source id, levels, guess)
+RIG_CASES = {
+    "rig_odo_L4": (0, 0, 1, 4, "small"),
+    "rig_odo_L3_identity": (0, 4, 5, 3, None),
+    "rig_loop_L4_gt": (1, 3, 17, 4, "gt"),
+}
+
+
+def rig_extrinsics():
+    """calib->Rt_: the reference's own Calibration/Extrinsics/Rt_0N.txt (kept in the ingest fixture), 8 x 4 x 4 float32."""
+    return np.load(os.path.join(GOLD, "frame360_raw_1.npz"))["Rt"].astype(np.float32)
+
+
+def make_rig_case(orc, name, rows=240, cols=320):
+    kind, a, b, levels, gm = RIG_CASES[name]
+    Rt = rig_extrinsics()
+    rgb1, d1 = orc.synth_rig_frame(kind, a, rows, cols, Rt)          # frame1: target
+    rgb2, d2 = orc.synth_rig_frame(kind, b, rows, cols, Rt)          # frame2: source
+    guess = None
+    if gm == "small":
+        guess = small_guess(7)
+    elif gm == "gt":
+        guess = (small_guess(99).astype(np.float64) @ orc.synth_gt_pose(kind, b, a)).astype(np.float32)
+    return dict(rgb1=rgb1, d1=d1, rgb2=rgb2, d2=d2, Rt=Rt, levels=levels, guess=guess, cam=orc.rig_camera(rows, cols),
+                kind=kind, frames=(a, b))
+
+
 def make_pinhole_case(orc, name, rows=240, cols=320):
     kind, a, b, levels, method, gm = PINHOLE_CASES[name][:6]
     rgb_t, d_t = orc.synth_pinhole_frame(kind, a, rows, cols, *PINHOLE_CAM)
