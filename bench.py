@@ -667,6 +667,38 @@ def run_config5(D, args, n_kf=128, block=512):
     return out
 
 
+def run_latency(D, args, w, reps=20):
+    """The call shape of the reference's callers (OdometryRGBD360.cpp:189-193): ONE pair per call, frames handed over in
+    host memory -- setTargetFrame + setSourceFrame + alignFrames360.  Small calls run in latency mode: the host watches the
+    active lists and stops enqueueing the passes of a level once the pair has left it."""
+    import rgbd360_b200 as r360
+    rows, cols, L = w["rows"], w["cols"], w["levels"]
+    ctx = r360.Context(rows, cols, 2, 1, r360.default_params(n_levels=L), device=D.local)
+    out = {}
+    for pair_id in (0, 7):                                       # two different pairs (iteration counts differ)
+        rgb, dep = ctx.synth_frames(0, 2 * pair_id, 2)
+        roles = [r360.ROLE_TARGET, r360.ROLE_SOURCE]
+        t_align, t_full, launches = [], [], 0
+        for k in range(reps + 3):
+            t0 = time.perf_counter()
+            ctx.set_frames(0, rgb, dep, roles)
+            t1 = time.perf_counter()
+            l0 = ctx.kernel_launches()
+            res = ctx.register_pairs([1], [0])
+            t2 = time.perf_counter()
+            if k >= 3:
+                t_align.append(1e3 * (t2 - t1)); t_full.append(1e3 * (t2 - t0)); launches = ctx.kernel_launches() - l0
+        out["pair_%d" % pair_id] = {"ms_alignFrames360": float(np.median(t_align)),
+                                    "ms_setFrames_plus_alignFrames360": float(np.median(t_full)),
+                                    "kernel_launches_alignFrames360": int(launches),
+                                    "accepted_iters_per_level": [int(x) for x in res[0]["iters"][:L]],
+                                    "status": int(res[0]["status"])}
+    ctx.close()
+    out["what"] = ("one %dx%d pair per call through the C ABI (host wall clock, median of %d calls): frames from pageable host memory, "
+                   "pyramids, registration, result back on the host" % (cols, rows, reps))
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm: the JSON line
 def run_ours(args):
     D = Dist()
@@ -688,6 +720,7 @@ def run_ours(args):
                                      "e2e": b["e2e"], "roofline": b["roofline"], "verify": b["verify"]}
         extras["config4"] = run_config4(D, args)
         extras["config5"] = run_config5(D, args)
+    latency = run_latency(D, args, w) if (D.world == 1 and D.rank == 0 and not args.no_extra_configs) else None
     if D.rank == 0:
         line = {
             "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
@@ -699,11 +732,15 @@ def run_ours(args):
         }
         if extras:
             line["configs"] = extras
+        if latency:
+            line["latency_batch1"] = latency
         if D.world == 1 and not args.no_cpu_baseline:
             n_cpu = CPU_SAMPLE[args.workload]
             os.sched_setaffinity(0, full_affinity)                     # the CPU baseline gets every host core
             cpu_reference_run(w, 2)                                    # warm-up (library build, page-in)
             v, cores, dt = cpu_reference_run(w, n_cpu)
+            if latency:
+                latency["cpu_reference_ms_per_pair"] = 1e3 / v
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d pairs of the same workload (frame build + alignFrames360, "
                                               "FAITHFUL accumulation, glibc math, OpenMP), %.1f s" % (n_cpu, dt),

@@ -30,6 +30,8 @@ thread_local std::string g_create_error;     // r360_create failures (no ctx yet
 constexpr int kChunkFrames = R360_CHUNK_FRAMES;     // max frames per pyramid-build launch / H2D staging buffer
 constexpr int kStages = 4;           // staging buffers: the copy stream runs up to kStages - 1 chunks ahead
 constexpr int kStreamPairs = 64;     // pairs per registration batch of r360_register_host_pairs
+constexpr int kLatencyPairs = 4;     // calls with at most this many pairs watch the active lists from the host and stop enqueueing
+                                     // passes of a level once every pair has left it (the single-pair call shape of the class mirror)
 constexpr int kOccPairs = 64;        // pairs per batch of the occlusion variants (bounds their scratch: 12 B per pixel and pair)
 
 struct Ctx {
@@ -68,6 +70,8 @@ struct Ctx {
     R360Pair* d_pairs = nullptr;
     R360Fx* d_acc = nullptr; int* d_cnt = nullptr;     // per pair: R360_ACC_STRIDE fixed-point sums, R360_ACC_INTS counters
     int* d_active = nullptr; int* d_nactive = nullptr;
+    int* h_nactive = nullptr;                    // pinned copy of d_nactive (latency mode)
+    bool early_exit = true;                      // R360_EARLY_EXIT=0: always enqueue the full schedule (A/B)
     int* d_active_err = nullptr;                 // pairs whose next pass is error-only
     int pass_grid_err = 0;
     bool speculate = true;                       // R360_SPECULATE=0 in the environment: every pass is the fused one (A/B)
@@ -437,7 +441,7 @@ void r360_destroy(r360_ctx* c) {
     cudaFree(c->d_l0); cudaFree(c->d_l1); cudaFree(c->d_tex);
     cudaFreeHost(c->h_l0); cudaFreeHost(c->h_l1); cudaFreeHost(c->h_tex);
     cudaFree(c->d_pairs); cudaFree(c->d_acc); cudaFree(c->d_cnt); cudaFree(c->d_active); cudaFree(c->d_nactive);
-    cudaFree(c->d_active_err);
+    cudaFree(c->d_active_err); cudaFreeHost(c->h_nactive);
     cudaFree(c->d_srcb); cudaFree(c->d_trgb); cudaFreeHost(c->h_srcb); cudaFreeHost(c->h_trgb);
     cudaFree(c->d_idx); cudaFreeHost(c->h_idx); cudaFree(c->d_pose); cudaFreeHost(c->h_pose);
     cudaFree(c->d_res); cudaFreeHost(c->h_res); cudaFree(c->d_trace);
@@ -556,6 +560,8 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     // [4] / [5] dynamic-item counters of the fused / error-only k_pass launch
     CK(c, cudaMalloc(&c->d_nactive, sizeof(int) * 8));
     CK(c, cudaMemset(c->d_nactive, 0, sizeof(int) * 8));
+    CK(c, cudaMallocHost(&c->h_nactive, sizeof(int) * 8));
+    if (const char* e = getenv("R360_EARLY_EXIT")) c->early_exit = atoi(e) != 0;
     CK(c, cudaMallocHost(&c->h_srcb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_srcb, sizeof(void*) * np));
     CK(c, cudaMallocHost(&c->h_trgb, sizeof(void*) * np)); CK(c, cudaMalloc(&c->d_trgb, sizeof(void*) * np));
     CK(c, cudaMallocHost(&c->h_idx, sizeof(int32_t) * 2 * np)); CK(c, cudaMalloc(&c->d_idx, sizeof(int32_t) * 2 * np));
@@ -619,8 +625,11 @@ int r360_set_frames_f32(r360_ctx* c, int first, int n, const uint8_t* rgb, const
 // (no host synchronisation): per-pair tables H2D, state init, then per level max_iters + 1 fused
 // passes with the on-device Gauss-Newton step in between, results into d_res[first ..].
 // The host tables (h_srcb, h_trgb, h_idx, h_pose) must already hold the whole call.
+// latency_mode (small calls only; needs a host synchronisation per pass, so never inside the streaming pipeline): after
+// every state-machine step the two list lengths come back to the host, and the rest of a level's schedule -- up to
+// max_iters + 1 + R360_SPEC_EXTRA passes of which a converged pair needs two or three -- is not enqueued once both are 0.
 static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has_pose, r360_iter_record* d_trace,
-                            bool time_passes, int* n_ev) {
+                            bool time_passes, int* n_ev, bool latency_mode = false) {
     CK(c, cudaMemcpyAsync(c->d_srcb + first, c->h_srcb + first, sizeof(void*) * n, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(c->d_trgb + first, c->h_trgb + first, sizeof(void*) * n, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(c->d_idx + first, c->h_idx + first, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->st));
@@ -651,6 +660,11 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
             if (pin) r360_launch_gn_step_pin(c->st, g, level);
             else r360_launch_gn_step(c->st, g, level);
             ++c->launches;
+            if (latency_mode) {
+                CK(c, cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->st));
+                CK(c, cudaStreamSynchronize(c->st));
+                if (c->h_nactive[0] == 0 && c->h_nactive[3] == 0) break;      // every pair has left this level
+            }
         }
     }
     r360_launch_finalize(c->st, g, c->d_res + first, c->rows, c->cols, first);
@@ -689,8 +703,9 @@ int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const 
     if (trace) CK(c, cudaMemsetAsync(c->d_trace, 0, sizeof(r360_iter_record) * n_rec, c->st));
     int n_ev = 0;
     if (c->P.occlusion == 0) {
+        const bool latency_mode = c->early_exit && n_pairs <= kLatencyPairs;
         int rc = enqueue_register(c, 0, n_pairs, n_pairs, init_pose != nullptr, trace ? c->d_trace : nullptr,
-                                  c->P.projection == R360_SPHERE, &n_ev);
+                                  c->P.projection == R360_SPHERE && !latency_mode, &n_ev, latency_mode);
         if (rc) return rc;
     } else {
         // the occlusion variants keep per-texel candidate lists for every pair of a batch: bounded batches
