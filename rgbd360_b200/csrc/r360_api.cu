@@ -40,7 +40,9 @@ struct Ctx {
     r360_params P{};
     R360Level lv[R360_MAX_LEVELS]{};
     long long px_total = 0;
-    cudaStream_t st = nullptr, cs = nullptr;
+    cudaStream_t st = nullptr, cs = nullptr, st2 = nullptr;      // compute, copy, and the side stream of the error-only passes
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_err = true;                     // R360_OVERLAP_ERR=0: error-only launches on the compute stream (A/B)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_copy[kStages]{}, ev_done[kStages]{};
     int chunk = kChunkFrames;                    // frames per chunk = min(kChunkFrames, max_frames)
@@ -457,6 +459,9 @@ void r360_destroy(r360_ctx* c) {
     for (int b = 0; b < kStages; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->st2) cudaStreamDestroy(c->st2);
     if (c->st) cudaStreamDestroy(c->st);
     if (c->cs) cudaStreamDestroy(c->cs);
     delete c;
@@ -482,6 +487,10 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     if (params->occlusion != 0) CK(c, r360_occ_init());
     CK(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
+    CK(c, cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if (const char* e = getenv("R360_OVERLAP_ERR")) c->overlap_err = atoi(e) != 0;
     CK(c, cudaEventCreate(&c->ev_t0));
     CK(c, cudaEventCreate(&c->ev_t1));
     c->chunk = std::min(kChunkFrames, max_frames);
@@ -651,8 +660,20 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
         const int n_eval = pin ? 2 * c->P.max_iters + 1 : c->P.max_iters + 1 + (two_lists ? R360_SPEC_EXTRA : 0);
         for (int k = 0; k < n_eval; ++k) {
             if (time_passes) CK(c, cudaEventRecord(c->ev_pass[(*n_ev)++], c->st));
+            // The fused and the error-only launch of a pass work on disjoint pair lists: the error-only one goes to a side
+            // stream, so whichever is small (a few stragglers) runs in the shadow of the other instead of after it.
+            const bool side = two_lists && k > 0 && c->overlap_err && !latency_mode;      // the first pass of a level is always fused
+            if (side) {
+                CK(c, cudaEventRecord(c->ev_fork, c->st));
+                CK(c, cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
+                r360_launch_pass(c->st2, a_err, c->pass_grid_err, false);
+                CK(c, cudaEventRecord(c->ev_join, c->st2));
+                ++c->launches;
+            }
             launch_evaluation(c, a, n, level);
-            if (two_lists && k > 0) {                                       // the first pass of a level is always fused
+            if (side) {
+                CK(c, cudaStreamWaitEvent(c->st, c->ev_join, 0));
+            } else if (two_lists && k > 0) {
                 r360_launch_pass(c->st, a_err, c->pass_grid_err, false);
                 ++c->launches;
             }

@@ -205,6 +205,69 @@ __device__ __forceinline__ void r360_texel_pair(float4 v, float4 u, float4 d, fl
     out[1] = make_float4(G.dx.x, G.dy.x, v.w, v.z);
     out[2] = make_float4(G.ix.y, G.iy.y, G.dx.y, G.dy.y);
 }
+// ---- the same gradients for a thread that walks DOWN a column of pixel pairs (k_pyr_head): of the 12 reciprocals per
+// pixel of calcGradientXY, three are shared.  Lanes are packed {depth, gray} of ONE pixel -- the order the plane is stored
+// in, so differences are formed on the loaded register pairs as they are.
+//   x: the three horizontal differences of a pair (v0 - w, v1 - v0, e - v1) serve both pixels: pixel 0's forward
+//      difference IS pixel 1's backward difference (same operands, same bits) -> 3 reciprocal pairs instead of 4;
+//   y: the backward difference of row r is the forward difference of row r - 1 -> its reciprocal (and its scaled copy for
+//      the monotonicity test) is carried in registers from row to row -> 2 reciprocal pairs per row instead of 4.
+// Every value is produced by the same IEEE operation on the same operands as r360_hgrad2, so the planes keep their bits.
+struct R360ColState { float2 ra0, ra1, ka0, ka1; };     // 1 / (v[r] - v[r-1]) and (v[r] - v[r-1]) 2^100 of pixel 0 / 1, {depth, gray}
+__device__ __forceinline__ float2 r360_lo(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 r360_hi(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ void r360_col_state_init(R360ColState& st, float4 u, float4 v) {
+    const float K = 1.2676506002282294e30f;                                  // 2^100
+    const float2 a0 = f2add(r360_lo(v), f2neg(r360_lo(u))), a1 = f2add(r360_hi(v), f2neg(r360_hi(u)));
+    st.ra0 = f2rcp_rn(a0); st.ra1 = f2rcp_rn(a1);
+    st.ka0 = f2mul(a0, R360_F2(K)); st.ka1 = f2mul(a1, R360_F2(K));
+}
+__device__ __forceinline__ float2 r360_hsel(float2 rsum, float2 ka, float2 kb) {
+    const float2 r = f2rcp_rn(rsum);
+    const float2 g = f2add(r, r);
+    const float2 p = f2mul(ka, kb);
+    return make_float2(p.x > 0.f ? g.x : 0.f, p.y > 0.f ? g.y : 0.f);
+}
+// Texels of the pixel pair (r, c), (r, c + 1): v the pair, d the pair below, wv / e the pixels west / east; st: the column
+// state (updated to row r for the next row).  Same outputs as r360_texel_pair.
+__device__ __forceinline__ void r360_texel_pair_col(R360ColState& st, float4 v, float4 u, float4 d, float2 wv, float2 e, int r, int c,
+                                                    int rows, int cols, const R360MaskGeom& mg, float4 out[3]) {
+    const float K = 1.2676506002282294e30f;
+    // y: forward differences of this row; the backward ones are the state
+    const float2 ay0 = f2add(r360_lo(d), f2neg(r360_lo(v))), ay1 = f2add(r360_hi(d), f2neg(r360_hi(v)));
+    const float2 ray0 = f2rcp_rn(ay0), ray1 = f2rcp_rn(ay1);
+    const float2 kay0 = f2mul(ay0, R360_F2(K)), kay1 = f2mul(ay1, R360_F2(K));
+    float2 gy0 = r360_hsel(f2add(ray0, st.ra0), kay0, st.ka0);               // {Dy, Iy} of pixel 0
+    float2 gy1 = r360_hsel(f2add(ray1, st.ra1), kay1, st.ka1);
+    st.ra0 = ray0; st.ra1 = ray1; st.ka0 = kay0; st.ka1 = kay1;
+    // x: three differences for the two pixels
+    const float2 d0 = f2add(r360_lo(v), f2neg(wv)), d1 = f2add(r360_hi(v), f2neg(r360_lo(v))), d2 = f2add(e, f2neg(r360_hi(v)));
+    const float2 r0 = f2rcp_rn(d0), r1 = f2rcp_rn(d1), r2 = f2rcp_rn(d2);
+    const float2 k0 = f2mul(d0, R360_F2(K)), k1 = f2mul(d1, R360_F2(K)), k2 = f2mul(d2, R360_F2(K));
+    float2 gx0 = r360_hsel(f2add(r1, r0), k1, k0);                           // {Dx, Ix} of pixel 0
+    float2 gx1 = r360_hsel(f2add(r2, r1), k2, k1);
+    const float2 chk = f2add(f2add(gx0, gx1), f2add(gy0, gy1));              // Inf / NaN if any term is
+    if (!(fabsf(chk.x) < INFINITY) | !(fabsf(chk.y) < INFINITY)) {           // rare: the scalar IEEE operators, out of line
+        const float2 ix = r360_hgrad2_scalar(v.y, v.w, wv.y, v.w, e.y, v.y), dx = r360_hgrad2_scalar(v.x, v.z, wv.x, v.z, e.x, v.x);
+        const float2 iy = r360_hgrad2_scalar(v.y, d.y, u.y, v.w, d.w, u.w), dy = r360_hgrad2_scalar(v.x, d.x, u.x, v.z, d.z, u.z);
+        gx0 = make_float2(dx.x, ix.x); gx1 = make_float2(dx.y, ix.y);
+        gy0 = make_float2(dy.x, iy.x); gy1 = make_float2(dy.y, iy.y);
+    }
+    bool z0 = !(r > 0 && r < rows - 1) || c == 0, z1 = !(r > 0 && r < rows - 1) || c + 2 == cols;     // image border
+    if (mg.ws > 0) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int cc = c + p, k0i = mg.magic ? (int)__umulhi((unsigned)cc, mg.magic) : cc, rem = cc - k0i * mg.ws;
+            const bool masked = (rem == 0 && k0i >= 1 && k0i <= mg.n_sensors - 1) || (rem == mg.ws - 1 && k0i + 1 <= mg.n_sensors - 1);
+            if (p == 0) z0 |= masked; else z1 |= masked;
+        }
+    }
+    if (z0) { gx0 = make_float2(0.f, 0.f); gy0 = gx0; }
+    if (z1) { gx1 = make_float2(0.f, 0.f); gy1 = gx1; }
+    out[0] = make_float4(v.y, v.x, gx0.y, gy0.y);
+    out[1] = make_float4(gx0.x, gy0.x, v.w, v.z);
+    out[2] = make_float4(gx1.y, gy1.y, gx1.x, gy1.x);
+}
 static inline R360MaskGeom r360_mask_geom(int cols, int n_sensors) {
     R360MaskGeom mg;
     mg.n_sensors = n_sensors;
@@ -342,25 +405,37 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
     }
     __syncthreads();
 
-    // ---- phase 2: level-0 outputs, one pixel pair per step (pair p of row ly: columns tx0 + 2p, + 1)
+    // ---- phase 2: level-0 outputs.  A thread walks down a strip of rows of ONE pixel-pair column (lane = column pair, so a
+    //      warp still writes one contiguous row segment per step) and carries the vertical differences' reciprocals from
+    //      row to row (r360_texel_pair_col).
     float2* __restrict__ l0 = l0_dst[f];
     float4* __restrict__ tex = reinterpret_cast<float4*>(texel_dst[f]);
-    for (int q = threadIdx.x; q < (R360_F0_TW / 2) * R360_F0_TH; q += 256) {
-        const int ly = q / (R360_F0_TW / 2), lp = q - ly * (R360_F0_TW / 2);
-        const int r = ty0 + ly, c = tx0 + 2 * lp;
-        if (r >= rows || c >= cols) continue;                                   // cols is even: the pair is inside or outside
-        const int sy = ly + 2, sx = 2 * lp + 4;
-        const float4 v = *reinterpret_cast<const float4*>(&s_dg[sy][sx]);       // {d0, g0, d1, g1}
-        const size_t pi = ((size_t)r * cols + c) >> 1;                          // pixel-pair index
-        if (l0) reinterpret_cast<float4*>(l0)[pi] = v;
-        if (tex) {
-            const float4 u = *reinterpret_cast<const float4*>(&s_dg[sy - 1][sx]);
-            const float4 d = *reinterpret_cast<const float4*>(&s_dg[sy + 1][sx]);
-            float4 t[3];
-            r360_texel_pair(v, u, d, s_dg[sy][sx - 1], s_dg[sy][sx + 2], r, c, rows, cols, mg, t);
-            tex[3 * pi + 0] = t[0];
-            tex[3 * pi + 1] = t[1];
-            tex[3 * pi + 2] = t[2];
+    {
+        constexpr int STRIP = R360_F0_TH / (256 / (R360_F0_TW / 2));             // rows per thread
+        const int lp = threadIdx.x % (R360_F0_TW / 2), ly0 = (threadIdx.x / (R360_F0_TW / 2)) * STRIP;
+        const int c = tx0 + 2 * lp, sx = 2 * lp + 4;
+        if (c < cols && ty0 + ly0 < rows) {                                      // cols is even: the pair is inside or outside
+            float4 u = *reinterpret_cast<const float4*>(&s_dg[ly0 + 1][sx]);     // row above the strip
+            float4 v = *reinterpret_cast<const float4*>(&s_dg[ly0 + 2][sx]);
+            R360ColState st;
+            if (tex) r360_col_state_init(st, u, v);
+            size_t pi = ((size_t)(ty0 + ly0) * cols + c) >> 1;                   // pixel-pair index
+            const size_t pi_step = (size_t)cols >> 1;
+#pragma unroll 2
+            for (int ly = ly0; ly < ly0 + STRIP; ++ly, pi += pi_step) {
+                const int r = ty0 + ly;
+                if (r >= rows) break;
+                const float4 d = *reinterpret_cast<const float4*>(&s_dg[ly + 3][sx]);
+                if (l0) reinterpret_cast<float4*>(l0)[pi] = v;
+                if (tex) {
+                    float4 t[3];
+                    r360_texel_pair_col(st, v, u, d, s_dg[ly + 2][sx - 1], s_dg[ly + 2][sx + 2], r, c, rows, cols, mg, t);
+                    tex[3 * pi + 0] = t[0];
+                    tex[3 * pi + 1] = t[1];
+                    tex[3 * pi + 2] = t[2];
+                }
+                u = v; v = d;
+            }
         }
     }
 

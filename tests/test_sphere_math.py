@@ -78,3 +78,23 @@ def test_pseudo_exp_is_mrpt_form(orc):
         assert np.array_equal(T[:3, 3], v[:3])
         assert np.allclose(T[:3, :3], Rotation.from_rotvec(v[3:]).as_matrix(), atol=1e-12)
         assert np.array_equal(T[3], [0, 0, 0, 1])
+
+
+def test_inverse4_of_rigid_and_general_matrices(orc):
+    """r360_inverse4 (the restatement of Eigen's Matrix4f::inverse() used for the sensor extrinsics, RPI.h:4923, 5125,
+    Calib360.h:129 -- third-party arithmetic, shared by the reference stand-in, the oracle and the product) against numpy:
+    float accuracy on the rig's own extrinsics, on random rigid poses and on general well-conditioned matrices."""
+    import os
+    rng = np.random.default_rng(4)
+    Rt = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame360_raw_1.npz"))["Rt"].astype(np.float32)
+    mats = [Rt[s] for s in range(8)]
+    for _ in range(20):
+        Q, _r = np.linalg.qr(rng.standard_normal((3, 3)))
+        T = np.eye(4); T[:3, :3] = Q; T[:3, 3] = rng.standard_normal(3)
+        mats.append(T.astype(np.float32))
+        mats.append((np.eye(4) * 3 + rng.standard_normal((4, 4))).astype(np.float32))
+    for M in mats:
+        inv = orc.inverse4(M)
+        want = np.linalg.inv(M.astype(np.float64))
+        assert np.allclose(inv, want, rtol=2e-5, atol=2e-6 * np.abs(want).max()), np.abs(inv - want).max()
+        assert np.allclose(inv.astype(np.float64) @ M.astype(np.float64), np.eye(4), atol=2e-5)
