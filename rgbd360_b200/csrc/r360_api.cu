@@ -42,7 +42,8 @@ struct Ctx {
     long long px_total = 0;
     cudaStream_t st = nullptr, cs = nullptr, st2 = nullptr;      // compute, copy, and the side stream of the error-only passes
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool overlap_err = true;                     // R360_OVERLAP_ERR=0: error-only launches on the compute stream (A/B)
+    bool overlap_err = false;                    // R360_OVERLAP_ERR=1: error-only launches on a side stream (measured: no gain -- the
+                                                 // persistent grids fill the chip either way; profiles/r02_overlap_err_ab.txt)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_copy[kStages]{}, ev_done[kStages]{};
     int chunk = kChunkFrames;                    // frames per chunk = min(kChunkFrames, max_frames)
