@@ -61,7 +61,7 @@ class RegisterRGBD360 {
     bool RegisterDensePhotoICP(const RigFrame& frame1, const RigFrame& frame2, const float* pose_estim = nullptr,
                                int method = R360_PHOTO_CONSISTENCY, registrationType = DEFAULT_6DoF) {
         if (method != R360_PHOTO_CONSISTENCY)
-            throw std::invalid_argument("RegisterDensePhotoICP: only PHOTO_CONSISTENCY is defined (RPI.h:5366-5367 reads an unassigned matrix)");
+            throw std::invalid_argument("RegisterDensePhotoICP: only PHOTO_CONSISTENCY is defined (RPI.h:5372-5374 reads an unassigned matrix)");
         std::vector<uint8_t> roles(8, R360_ROLE_TARGET);
         check(r360_set_frames(ctx_, 0, 8, frame1.rgb, frame1.depth_mm, roles.data()));       // setTargetFrame x 8   (:380)
         roles.assign(8, R360_ROLE_SOURCE);

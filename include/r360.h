@@ -181,7 +181,7 @@ int r360_eval_error_pinhole(r360_ctx* ctx, int src, int trg, int level, const fl
  * gradients summed over the rig, one 6-DoF Levenberg-Marquardt loop on the ROBOT pose (lambda 0.001, step 10,
  * tol_residual 0.1, tol_update 1e-6, 10 iterations: RegisterRGBD360.h:391-398, fixed here whatever the ctx params say).
  * Contexts created with projection = R360_PINHOLE, method = R360_PHOTO_CONSISTENCY (the driver's default; upstream the
- * Hessian's depth row reads a matrix that is never assigned, RPI.h:5366-5367, so the other methods are undefined there
+ * Hessian's depth row reads a matrix that is never assigned, RPI.h:5372-5374, so the other methods are undefined there
  * and refused here) and r360_set_camera(f, f, w/2 - 0.5, h/2 - 0.5), f = 525 w / 640 (RegisterRGBD360.h:361-369).
  * A rig frame occupies 8 consecutive frame slots (sensor s at first + s): src_first / trg_first name sensor 0 of
  * frame2 (source) / frame1 (target).  Rt: the 8 sensor poses calib->Rt_ (column-major 4x4 each), shared by all pairs.

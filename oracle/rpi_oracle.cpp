@@ -987,7 +987,7 @@ int align_pinhole(const Frame* src, const Frame* trg, const float* guess, const 
 //     back-projection is formed in double and narrowed), applies the photo saliency `continue`, and accumulates H and g
 //     in float pixel by pixel in row-major order (no OpenMP: the pragma is commented out upstream);
 //   * the Hessian's depth row subtracts `jacobianRt_z`, a matrix that is DECLARED BUT NEVER ASSIGNED upstream
-//     (RPI.h:5217-5218, 5366-5367: the statement `jacobianT36.block(2,0,1,6);` has no effect): the depth methods are
+//     (RPI.h:5226-5228, 5372-5374: the statement `jacobianT36.block(2,0,1,6);` has no effect): the depth methods are
 //     undefined behaviour there, so only PHOTO_CONSISTENCY (the driver's default and what its callers pass) is defined;
 //   * the driver evaluates `new_error` at pose_estim instead of pose_estim_temp (RegisterRGBD360.h:462, 488): with a
 //     deterministic summation diff_error is exactly 0, no step is ever accepted, every level runs ONE loop body and the

@@ -852,7 +852,7 @@ static int rig_check(r360_ctx* c, const float* Rt) {
     if (!c->have_cam) return fail(c, R360_E_STATE, "rig: call r360_set_camera first (RegisterRGBD360.h:361-369)");
     if (c->P.method != R360_PHOTO_CONSISTENCY)
         return fail(c, R360_E_STATE, "rig: only PHOTO_CONSISTENCY is defined (calcHessianGradient_robot's depth row reads a matrix that "
-                                     "is never assigned upstream, RPI.h:5366-5367)");
+                                     "is never assigned upstream, RPI.h:5372-5374)");
     if (c->P.occlusion != 0) return fail(c, R360_E_STATE, "rig: occlusion must be 0");
     if (!Rt) return fail(c, R360_E_ARG, "rig: null extrinsics");
     if (!c->d_rig_src) {

@@ -264,7 +264,7 @@ __global__ void k_gn_step_pin(R360GnArgs g, int level) {
 // =========================================================================== the 8-sensor rig
 // calcPhotoICPError_robot (RPI.h:4905-5092) + calcHessianGradient_robot (RPI.h:5100-5407) of ONE sensor of ONE pair at
 // the pair's pose_eval, PHOTO_CONSISTENCY (the only method whose Hessian is defined upstream: the depth row uses a matrix
-// that is never assigned, RPI.h:5366-5367).  blockIdx.y = 8 * active pair + sensor; all 8 sensors add into the pair's
+// that is never assigned, RPI.h:5372-5374).  blockIdx.y = 8 * active pair + sensor; all 8 sensors add into the pair's
 // accumulators, which IS the driver's sum over the rig (RegisterRGBD360.h:403-440).  The two functions warp differently
 // (one float matrix vs three matrix-vector products with double intrinsics) and so may hit different texels: both chains
 // are evaluated, each with the reference's own operation sequence.

@@ -12,7 +12,7 @@ What the reference does, and what is therefore asserted:
     over the sensors whose order is the threads' arrival order, so `error - new_error` is 0 or +-1 ulp from run to run and some
     runs take an (unevaluated) step: the recording keeps how many of 12 runs returned the guess; the comparison is made on those;
   * `faithful = False` (the candidate is evaluated: the evident intent) is checked against the analytic ground truth;
-  * only PHOTO_CONSISTENCY is defined upstream (the Hessian's depth row reads a matrix that is never assigned, RPI.h:5366-5367).
+  * only PHOTO_CONSISTENCY is defined upstream (the Hessian's depth row reads a matrix that is never assigned, RPI.h:5372-5374).
 GPU: counters exact, sums 1e-4 (5e-4 on H against the reference's serial float accumulation over 8 x 76 800 pixels), the
 faithful run returns the guess bit for bit, the fixed run's pose within 1e-4 of the oracle's.
 """
