@@ -17,10 +17,16 @@
 #include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
+#include <nvtx3/nvToolsExt.h>          // header-only: ranges show up in nsys / ncu timelines, cost nothing without a tool attached
 #include "r360_kernels.h"
 #include "synth.h"
 
 namespace {
+
+struct NvtxRange {                      // one named range per C-ABI call that enqueues device work
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_create_error;     // r360_create failures (no ctx yet); ranks may be host threads
 
@@ -289,6 +295,7 @@ int stage_and_build(Ctx* c, int first_slot, int m, const uint8_t* rgb, const uin
 int set_frames_impl(Ctx* c, int first, int n, const uint8_t* rgb, const void* depth, bool depth_is_f32,
                     bool on_device, const uint8_t* roles) {
     if (!c) return R360_E_ARG;
+    NvtxRange nvtx("r360_set_frames");
     if (first < 0 || n < 0 || first + n > c->max_frames || !rgb || !depth)
         return fail(c, R360_E_ARG, "set_frames: bad range [%d,%d) of %d slots or null input", first, first + n, c->max_frames);
     if (roles)
@@ -698,6 +705,7 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
 int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const int32_t* trg_idx, const float* init_pose,
                         r360_result* out, r360_iter_record* trace) {
     if (!c) return R360_E_ARG;
+    NvtxRange nvtx("r360_register_pairs");
     if (n_pairs < 0 || n_pairs > c->max_pairs || !src_idx || !trg_idx || !out)
         return fail(c, R360_E_ARG, "register_pairs: n_pairs %d not in [0,%d] or null argument", n_pairs, c->max_pairs);
     if (n_pairs == 0) return R360_OK;
@@ -763,6 +771,7 @@ int r360_register_pairs(r360_ctx* c, int n_pairs, const int32_t* src_idx, const 
 int r360_register_host_pairs(r360_ctx* c, int n_pairs, const uint8_t* rgb, const uint16_t* depth_mm,
                              const float* init_pose, r360_result* out) {
     if (!c) return R360_E_ARG;
+    NvtxRange nvtx("r360_register_host_pairs");
     if (n_pairs < 0 || n_pairs > c->max_pairs || 2 * n_pairs > c->max_frames || !rgb || !depth_mm || !out)
         return fail(c, R360_E_ARG, "register_host_pairs: n_pairs %d needs max_pairs >= n_pairs and max_frames >= 2 n_pairs, non-null buffers", n_pairs);
     if (n_pairs == 0) return R360_OK;
@@ -924,6 +933,7 @@ int r360_eval_rig(r360_ctx* c, int src_first, int trg_first, int level, const fl
 int r360_register_rig_pairs(r360_ctx* c, int n_pairs, const int32_t* src_first, const int32_t* trg_first, const float* Rt,
                             const float* init_pose, int faithful_new_error, r360_result* out) {
     if (!c) return R360_E_ARG;
+    NvtxRange nvtx("r360_register_rig_pairs");
     if (n_pairs < 0 || n_pairs > c->max_pairs || !src_first || !trg_first || !out)
         return fail(c, R360_E_ARG, "register_rig_pairs: n_pairs %d not in [0,%d] or null argument", n_pairs, c->max_pairs);
     if (n_pairs == 0) return R360_OK;
@@ -1229,6 +1239,7 @@ void r360_synth_gt_pose(int kind, int src_id, int trg_id, double T[16]) { r360_s
 
 int r360_allgather_results(r360_ctx* c, void* nccl_comm, const r360_result* local, int n_local, int n_ranks, r360_result* all) {
     if (!c) return R360_E_ARG;
+    NvtxRange nvtx("r360_allgather_results");
     if (!nccl_comm || n_local < 0 || n_ranks < 1 || (n_local > 0 && (!local || !all)))
         return fail(c, R360_E_ARG, "allgather_results: null communicator / buffer or bad counts (n_local %d, n_ranks %d)", n_local, n_ranks);
     if (n_local == 0) return R360_OK;

@@ -80,3 +80,29 @@ int main() {
                            "-L", os.path.join(ROOT, "rgbd360_b200"), "-lrgbd360_b200",
                            "-Wl,-rpath," + os.path.join(ROOT, "rgbd360_b200")])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_cpp_rig_and_driver_headers_compile(native, tmp_path):
+    """include/RegisterRGBD360_b200.hpp and include/Drivers360_b200.hpp compile and link against the C ABI; without a GPU
+    the rig class fails loudly at construction (r360_create: no CUDA device), it never falls back."""
+    src = tmp_path / "t.cpp"
+    src.write_text('''
+#include <cstdio>
+#include <stdexcept>
+#include "RegisterRGBD360_b200.hpp"
+#include "Drivers360_b200.hpp"
+int main() {
+    const r360::Pose I = r360::identityPose();
+    if (r360::toRobotFrame(r360::toSphereFrame(I))[0] < 0.999f) return 2;
+    try {
+        r360::RegisterRGBD360 reg(240, 320);
+        reg.setFaithfulNewError(false);
+    } catch (const std::runtime_error& e) { std::printf("no device: %s\\n", e.what()); return 0; }
+    return 0;
+}
+''')
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", os.path.join(ROOT, "rgbd360_b200"), "-lrgbd360_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "rgbd360_b200")])
+    assert subprocess.call([str(exe)]) == 0
