@@ -642,6 +642,10 @@ k_pass(R360PassArgs a) {
 #pragma unroll kUnroll
 #endif
         for (int k = 0; k < n_it; ++k) {
+#ifdef R360_PASS_SYNC_EVERY
+            // keeps the CTA's warps in step (they share texel rows in L1 and stream one region): n_it is uniform over the CTA
+            if ((k & (R360_PASS_SYNC_EVERY - 1)) == R360_PASS_SYNC_EVERY - 1) __syncthreads();
+#endif
             if (k + S - 1 < n_it) {
                 s_cur = s_nxt;
                 s_nxt = i + STRIDE < p_end ? __ldg(&src4[(i + STRIDE) >> 1]) : zero4;
