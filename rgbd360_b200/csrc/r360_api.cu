@@ -967,10 +967,16 @@ int r360_register_rig_pairs(r360_ctx* c, int n_pairs, const int32_t* src_first, 
         R360PassArgs a = pass_args(c, level, n_pairs, 0);
         const R360RigArgs rig = rig_args(c, Rt, level);
         const int n_eval = 2 * g.params.max_iters + 1;         // one initial evaluation; every loop body may add one damped retry
+        const bool latency_mode = c->early_exit && n_pairs <= kLatencyPairs;     // as r360_register_pairs: stop a level once every pair has left it
         for (int k = 0; k < n_eval; ++k) {
             r360_launch_rig_eval(c->st, a, rig, n_pairs, c->sm_count);
             r360_launch_gn_step_rig(c->st, g, level);
             c->launches += 2;
+            if (latency_mode) {
+                CK(c, cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->st));
+                CK(c, cudaStreamSynchronize(c->st));
+                if (c->h_nactive[0] == 0 && c->h_nactive[3] == 0) break;
+            }
         }
     }
     r360_launch_finalize(c->st, g, c->d_res, c->rows, c->cols, 0);
