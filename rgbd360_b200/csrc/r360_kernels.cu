@@ -529,6 +529,7 @@ k_pass(R360PassArgs a) {
     // this thread's slots: stage s at + s * STAGE_BYTES; texels at +0, geometry at + GEO_OFF
     constexpr unsigned STAGE_BYTES = 2 * R360_PASS_THREADS * R360_SLOT_BYTES, GEO_OFF = R360_PASS_THREADS * R360_SLOT_BYTES;
     const unsigned slot0 = r360_smem_addr(reinterpret_cast<char*>(s_pipe) + R360_SLOT_BYTES * threadIdx.x);
+    const unsigned ts = r360_smem_addr(s_T);                         // held in a register: no generic pointer, no window arithmetic in the loop
 
     int ap = item / ipp;
     int sub = item - ap * ipp;
@@ -585,16 +586,15 @@ k_pass(R360PassArgs a) {
             R360Geo2 g;
             int rr[2], cc[2];
 #ifdef R360_T_IN_REGS
-            r360_index_pair(T, s_T, lv, sp, a.one, g, rr, cc, n_fb);
+            r360_index_pair(T, ts, lv, sp, a.one, g, rr, cc, n_fb);
 #else
             float T[16];                                             // pose: 3 x LDS.128 per iteration, no long-lived registers
             {
-                const float4 c0 = reinterpret_cast<const float4*>(s_T)[0], c1 = reinterpret_cast<const float4*>(s_T)[1],
-                             c2 = reinterpret_cast<const float4*>(s_T)[2], c3 = reinterpret_cast<const float4*>(s_T)[3];
+                const float4 c0 = r360_lds128(ts), c1 = r360_lds128(ts + 16), c2 = r360_lds128(ts + 32), c3 = r360_lds128(ts + 48);
                 T[0] = c0.x; T[1] = c0.y; T[2] = c0.z; T[4] = c1.x; T[5] = c1.y; T[6] = c1.z;
                 T[8] = c2.x; T[9] = c2.y; T[10] = c2.z; T[12] = c3.x; T[13] = c3.y; T[14] = c3.z;
             }
-            r360_index_pair(T, s_T, lv, sp, a.one, g, rr, cc, n_fb);
+            r360_index_pair(T, ts, lv, sp, a.one, g, rr, cc, n_fb);
 #endif
             // RPI.h:2683 / 2989 (no c' >= 0 test upstream; c' is never negative, the unsigned compare
             // only guards memory)
@@ -610,7 +610,7 @@ k_pass(R360PassArgs a) {
             r360_sts128(dst + GEO_OFF + 16, make_float4(g.pz.x, g.pz.y, g.dinv.x, g.dinv.y));
             // |p| > 0: its sign carries the in-bounds flag of the pixel
             r360_sts128(dst + GEO_OFF + 32, make_float4(sp.Is.x, sp.Is.y, ok0 ? g.dist.x : -g.dist.x, ok1 ? g.dist.y : -g.dist.y));
-            n_vis += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
+            r360_count(n_vis, ok0); r360_count(n_vis, ok1);
             // next pixel pair of this thread
             i += STRIDE;
             r += lv.stride_r;
@@ -876,9 +876,12 @@ __global__ void k_level_begin(R360GnArgs g, int level) {
 //   phase 1: the pass evaluated the candidate pose_tmp = exp(update) * pose_estim.
 // The reference runs errorPhotoICP_sphere(pose_tmp) and, if accepted, calcHessGrad_sphere at the
 // same pose in the next loop body; the fused pass already produced both.
+// One pair per WARP (lane 0 works): the pivoting solves and the accept / reject branches of different pairs diverge,
+// and 32 of them in one warp run one after the other -- the step is pure latency between two pixel passes.
 __global__ void k_gn_step(R360GnArgs g, int level) {
     const r360_params P = g.params;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
+    if (*g.n_active == 0 && *g.n_active_err == 0) return;       // every pair has left the level: the remaining launches of its schedule are empty
+    for (int p = threadIdx.x == 0 ? (int)blockIdx.x : g.n_pairs; p < g.n_pairs; p += gridDim.x) {
         R360Pair* ps = g.pairs + p;
         if (!ps->active) continue;
         double acc[R360_ACC_DOUBLES + 1];
@@ -1203,7 +1206,7 @@ void r360_launch_level_begin(cudaStream_t st, const R360GnArgs& g, int level) {
     k_level_begin<<<r360_blocks(g.n_pairs, 64, 1024), 64, 0, st>>>(g, level);
 }
 void r360_launch_gn_step(cudaStream_t st, const R360GnArgs& g, int level) {
-    k_gn_step<<<r360_blocks(g.n_pairs, 32, 1024), 32, 0, st>>>(g, level);
+    k_gn_step<<<r360_blocks(g.n_pairs, 1, 1024), 32, 0, st>>>(g, level);
 }
 void r360_launch_finalize(cudaStream_t st, const R360GnArgs& g, r360_result* out, int rows, int cols, int pair_id0) {
     k_finalize<<<r360_blocks(g.n_pairs, 128, 1024), 128, 0, st>>>(g, out, rows, cols, pair_id0);
