@@ -324,6 +324,7 @@ k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long lo
 #endif
 #define R360_F0_SW (R360_F0_TW + 8)            // smem columns: global x = tx0 - 4 + sx
 #define R360_F0_SH (R360_F0_TH + 4)            // smem rows:    global y = ty0 - 2 + sy
+#define R360_F0_ROWB (R360_F0_SW * 8)          // bytes per smem row
 __device__ __forceinline__ int r360_reflect101_clamped(int i, int n) {
     i = r360_reflect101(i, n);
     return min(max(i, 0), n - 1);               // partial tiles reach far outside; those values are never used
@@ -332,143 +333,246 @@ __device__ __forceinline__ float r360_gray_u8(unsigned r, unsigned g, unsigned b
     const int v = (int)(r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15;
     return (float)v * (float)(1. / 255);
 }
+__device__ __forceinline__ float2 r360_lds64(unsigned smem) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem) : "memory");
+    return v;
+}
+// g if p > 0 and the pixel is not masked, else 0: ONE compare that takes the mask as its predicate input and one select
+// (nvcc makes two selects of `(p > 0) & !z ? g : 0`).  NaN compares false, as `p > 0.f` does.
+__device__ __forceinline__ float r360_sel_pos(float p, float g, bool z) {
+    float o;
+    asm("{\n\t.reg .pred q, t;\n\tsetp.ne.s32 q, %3, 0;\n\tsetp.gt.and.f32 t, %1, 0f00000000, !q;\n\tselp.f32 %0, %2, 0f00000000, t;\n\t}"
+        : "=f"(o) : "f"(p), "f"(g), "r"((int)z));
+    return o;
+}
+// r360_hsel with the border / sensor-joint mask folded into the select.
+__device__ __forceinline__ float2 r360_hsel_z(float2 rsum, float2 ka, float2 kb, bool z) {
+    const float2 r = f2rcp_rn(rsum);
+    const float2 g = f2add(r, r);
+    const float2 p = f2mul(ka, kb);
+    return make_float2(r360_sel_pos(p.x, g.x, z), r360_sel_pos(p.y, g.y, z));
+}
+// r360_texel_pair_col with the masks of the pair's two pixels (image border, sensor joints) decided by the caller --
+// the column part is the same for every row of a strip.  SCALED = false: the differences themselves stand in for their
+// 2^100 multiples in the monotonicity test -- exact when no product of two non-zero differences can underflow, which
+// holds for 8-bit gray (steps of 1/255) and 16-bit millimetre depth (steps of 0.001), not for CV_32F depth.
+template <bool SCALED>
+__device__ __forceinline__ void r360_col_state_init_t(R360ColState& st, float4 u, float4 v) {
+    const float K = 1.2676506002282294e30f;                                  // 2^100
+    const float2 a0 = f2add(r360_lo(v), f2neg(r360_lo(u))), a1 = f2add(r360_hi(v), f2neg(r360_hi(u)));
+    st.ra0 = f2rcp_rn(a0); st.ra1 = f2rcp_rn(a1);
+    st.ka0 = SCALED ? f2mul(a0, R360_F2(K)) : a0; st.ka1 = SCALED ? f2mul(a1, R360_F2(K)) : a1;
+}
+template <bool SCALED>
+__device__ __forceinline__ void r360_texel_pair_colz(R360ColState& st, float4 v, float4 u, float4 d, float2 wv, float2 e, bool z0,
+                                                     bool z1, float4 out[3]) {
+    const float K = 1.2676506002282294e30f;
+    const float2 ay0 = f2add(r360_lo(d), f2neg(r360_lo(v))), ay1 = f2add(r360_hi(d), f2neg(r360_hi(v)));
+    const float2 ray0 = f2rcp_rn(ay0), ray1 = f2rcp_rn(ay1);
+    const float2 kay0 = SCALED ? f2mul(ay0, R360_F2(K)) : ay0, kay1 = SCALED ? f2mul(ay1, R360_F2(K)) : ay1;
+    const float2 gy0 = r360_hsel_z(f2add(ray0, st.ra0), kay0, st.ka0, z0);   // {Dy, Iy} of pixel 0
+    const float2 gy1 = r360_hsel_z(f2add(ray1, st.ra1), kay1, st.ka1, z1);
+    st.ra0 = ray0; st.ra1 = ray1; st.ka0 = kay0; st.ka1 = kay1;
+    const float2 d0 = f2add(r360_lo(v), f2neg(wv)), d1 = f2add(r360_hi(v), f2neg(r360_lo(v))), d2 = f2add(e, f2neg(r360_hi(v)));
+    const float2 r0 = f2rcp_rn(d0), r1 = f2rcp_rn(d1), r2 = f2rcp_rn(d2);
+    const float2 k0 = SCALED ? f2mul(d0, R360_F2(K)) : d0, k1 = SCALED ? f2mul(d1, R360_F2(K)) : d1, k2 = SCALED ? f2mul(d2, R360_F2(K)) : d2;
+    const float2 gx0 = r360_hsel_z(f2add(r1, r0), k1, k0, z0);               // {Dx, Ix} of pixel 0
+    const float2 gx1 = r360_hsel_z(f2add(r2, r1), k2, k1, z1);
+    // the selects write the texel registers directly; the finite check adds them up in the pairing they are stored in
+    // (any order will do: it only has to come out Inf / NaN when an unmasked term is)
+    float2 i0 = make_float2(gx0.y, gy0.y), q0 = make_float2(gx0.x, gy0.x);   // {Ix, Iy}, {Dx, Dy} of pixel 0
+    float2 i1 = make_float2(gx1.y, gy1.y), q1 = make_float2(gx1.x, gy1.x);
+    const float2 chk = f2add(f2add(i0, q0), f2add(i1, q1));
+    if (!(fabsf(chk.x) < INFINITY) | !(fabsf(chk.y) < INFINITY)) {           // rare: the scalar IEEE operators, out of line
+        const float2 ix = r360_hgrad2_scalar(v.y, v.w, wv.y, v.w, e.y, v.y), dx = r360_hgrad2_scalar(v.x, v.z, wv.x, v.z, e.x, v.x);
+        const float2 iy = r360_hgrad2_scalar(v.y, d.y, u.y, v.w, d.w, u.w), dy = r360_hgrad2_scalar(v.x, d.x, u.x, v.z, d.z, u.z);
+        i0 = z0 ? make_float2(0.f, 0.f) : make_float2(ix.x, iy.x); q0 = z0 ? make_float2(0.f, 0.f) : make_float2(dx.x, dy.x);
+        i1 = z1 ? make_float2(0.f, 0.f) : make_float2(ix.y, iy.y); q1 = z1 ? make_float2(0.f, 0.f) : make_float2(dx.y, dy.y);
+    }
+    out[0] = make_float4(v.y, v.x, i0.x, i0.y);
+    out[1] = make_float4(q0.x, q0.y, v.w, v.z);
+    out[2] = make_float4(i1.x, i1.y, q1.x, q1.y);
+}
+// Sensor-joint columns k*ws-1 and k*ws, k = 1..n_sensors-1 (RPI.h:4537-4549); c / ws by multiplication (exact for c * ws < 2^32).
+__device__ __forceinline__ bool r360_joint_column(int cc, const R360MaskGeom& mg) {
+    if (mg.ws <= 0) return false;
+    const int k0 = mg.magic ? (int)__umulhi((unsigned)cc, mg.magic) : cc, rem = cc - k0 * mg.ws;
+    return (rem == 0 && k0 >= 1 && k0 <= mg.n_sensors - 1) || (rem == mg.ws - 1 && k0 + 1 <= mg.n_sensors - 1);
+}
+// Horizontal 5-tap of one staged row at level-1 column ox (global columns 2x-2 .. 2x+2 = smem columns 2ox+2 .. 2ox+6) and
+// the two depth parents of that column: k_down's r360_down_hrow, from shared memory.
+__device__ __forceinline__ R360HRow r360_head_hrow(unsigned row_addr) {     // address of smem column 2ox+2 of the row
+    const float4 A = r360_lds128(row_addr), B = r360_lds128(row_addr + 16);
+    const float2 C = r360_lds64(row_addr + 32);
+    R360HRow o;
+    o.h = B.y * 6 + (A.w + B.w) * 4 + A.y + C.y;
+    o.dl = B.x; o.dr = B.z;
+    return o;
+}
 template <bool F32DEPTH>
 __global__ void __launch_bounds__(256, R360_F0_MINB)
 k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_mm, const float* __restrict__ depth_m,
            float2* const* __restrict__ l0_dst, float2* const* __restrict__ l1_dst, float* const* __restrict__ texel_dst,
            int rows, int cols, int tiles_x, float min_d, float max_d, R360MaskGeom mg) {
     __shared__ __align__(16) float2 s_dg[R360_F0_SH][R360_F0_SW];
-    __shared__ float s_h[R360_F0_SH][R360_F0_TW / 2];
     const int f = blockIdx.y;
     const int ty0 = (blockIdx.x / tiles_x) * R360_F0_TH, tx0 = (blockIdx.x % tiles_x) * R360_F0_TW;
     const size_t n_px = (size_t)rows * cols;
     const uint8_t* __restrict__ c8 = rgb + (size_t)f * n_px * 3;
     const float ds = (float)0.001;
+    const unsigned sbase = r360_smem_addr(&s_dg[0][0]);
 
-    // ---- phase 1: raw input -> {depth, gray} of the tile + halo, 4 pixels per step.  All raw loads of the
-    //      thread are issued first (registers), then converted: the HBM latency is paid once per tile,
-    //      not once per group.
-    constexpr int GROUPS = R360_F0_SW / 4, N_GROUPS = GROUPS * R360_F0_SH, NIT = (N_GROUPS + 255) / 256;
-    uint32_t w0[NIT], w1[NIT], w2[NIT];
-    uint32_t dw[NIT][F32DEPTH ? 4 : 2];
-#pragma unroll
-    for (int k = 0; k < NIT; ++k) {
-        const int q = threadIdx.x + 256 * k;
-        const int sy = q / GROUPS, gq = q - sy * GROUPS;
-        const int gy = r360_reflect101_clamped(ty0 - 2 + sy, rows);
+    // ---- phase 1: raw input -> {depth, gray} of the tile + halo.  A thread owns ONE group of 4 columns and walks down the
+    //      rows (row stride 14: 18 groups x 14 rows = 252 threads), so the column part of its addresses and the border
+    //      decision are made once; pixel offsets are 32-bit.  All raw loads of the thread are issued first (registers),
+    //      then converted: the HBM latency is paid once per tile, not once per group.
+    constexpr int GROUPS = R360_F0_SW / 4, RPP = 256 / GROUPS, NIT = (R360_F0_SH + RPP - 1) / RPP;
+    {
+        const int tr = threadIdx.x / GROUPS, gq = threadIdx.x - tr * GROUPS;
         const int gx0 = tx0 - 4 + 4 * gq;
-        if (q < N_GROUPS && gx0 >= 0 && gx0 + 3 < cols) {
-            const size_t i0 = (size_t)gy * cols + gx0;                         // multiple of 4
-            const uint32_t* c4 = reinterpret_cast<const uint32_t*>(c8 + 3 * i0);
-            w0[k] = __ldg(c4); w1[k] = __ldg(c4 + 1); w2[k] = __ldg(c4 + 2);
-            if (F32DEPTH) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(depth_m + (size_t)f * n_px + i0));
-                dw[k][0] = t.x; dw[k][1] = t.y; dw[k][F32DEPTH ? 2 : 0] = t.z; dw[k][F32DEPTH ? 3 : 1] = t.w;
-            } else {
-                const uint2 t = __ldg(reinterpret_cast<const uint2*>(depth_mm + (size_t)f * n_px + i0));
-                dw[k][0] = t.x; dw[k][1] = t.y;
+        if (tr < RPP) {
+            const unsigned sdst = sbase + (unsigned)(tr * R360_F0_SW + 4 * gq) * 8u;
+            if (gx0 >= 0 && gx0 + 3 < cols) {
+                uint32_t w0[NIT], w1[NIT], w2[NIT];
+                uint32_t dw[NIT][F32DEPTH ? 4 : 2];
+                const uint32_t* __restrict__ c32 = reinterpret_cast<const uint32_t*>(c8);
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    const int sy = tr + RPP * k;
+                    if (sy < R360_F0_SH) {
+                        const unsigned off = (unsigned)r360_reflect101_clamped(ty0 - 2 + sy, rows) * (unsigned)cols + (unsigned)gx0;   // multiple of 4
+                        const uint32_t* c4 = c32 + 3u * (off >> 2);
+                        w0[k] = __ldg(c4); w1[k] = __ldg(c4 + 1); w2[k] = __ldg(c4 + 2);
+                        if (F32DEPTH) {
+                            const uint4 t = __ldg(reinterpret_cast<const uint4*>(depth_m + (size_t)f * n_px) + (off >> 2));
+                            dw[k][0] = t.x; dw[k][1] = t.y; dw[k][F32DEPTH ? 2 : 0] = t.z; dw[k][F32DEPTH ? 3 : 1] = t.w;
+                        } else {
+                            const uint2 t = __ldg(reinterpret_cast<const uint2*>(depth_mm + (size_t)f * n_px) + (off >> 2));
+                            dw[k][0] = t.x; dw[k][1] = t.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    if (tr + RPP * k < R360_F0_SH) {
+                        float d[4], g[4];
+                        g[0] = r360_gray_u8(w0[k] & 0xffu, (w0[k] >> 8) & 0xffu, (w0[k] >> 16) & 0xffu);
+                        g[1] = r360_gray_u8(w0[k] >> 24, w1[k] & 0xffu, (w1[k] >> 8) & 0xffu);
+                        g[2] = r360_gray_u8((w1[k] >> 16) & 0xffu, w1[k] >> 24, w2[k] & 0xffu);
+                        g[3] = r360_gray_u8((w2[k] >> 8) & 0xffu, (w2[k] >> 16) & 0xffu, w2[k] >> 24);
+                        if (F32DEPTH) {
+                            d[0] = __uint_as_float(dw[k][0]); d[1] = __uint_as_float(dw[k][1]);
+                            d[2] = __uint_as_float(dw[k][F32DEPTH ? 2 : 0]); d[3] = __uint_as_float(dw[k][F32DEPTH ? 3 : 1]);
+                        } else {
+                            d[0] = (float)(dw[k][0] & 0xffffu) * ds; d[1] = (float)(dw[k][0] >> 16) * ds;
+                            d[2] = (float)(dw[k][1] & 0xffffu) * ds; d[3] = (float)(dw[k][1] >> 16) * ds;
+                        }
+                        r360_sts128(sdst + (unsigned)(RPP * k) * R360_F0_ROWB, make_float4(d[0], g[0], d[1], g[1]));
+                        r360_sts128(sdst + (unsigned)(RPP * k) * R360_F0_ROWB + 16, make_float4(d[2], g[2], d[3], g[3]));
+                    }
+                }
+            } else {                                                           // image border columns: REFLECT_101, pixel by pixel
+                for (int sy = tr; sy < R360_F0_SH; sy += RPP) {
+                    const int gy = r360_reflect101_clamped(ty0 - 2 + sy, rows);
+                    float d[4], g[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int gx = r360_reflect101_clamped(gx0 + j, cols);
+                        const size_t i = (size_t)gy * cols + gx;
+                        g[j] = r360_gray_u8(c8[3 * i], c8[3 * i + 1], c8[3 * i + 2]);
+                        d[j] = F32DEPTH ? depth_m[(size_t)f * n_px + i] : (float)depth_mm[(size_t)f * n_px + i] * ds;
+                    }
+                    const unsigned a = sbase + (unsigned)(sy * R360_F0_SW + 4 * gq) * 8u;
+                    r360_sts128(a, make_float4(d[0], g[0], d[1], g[1]));
+                    r360_sts128(a + 16, make_float4(d[2], g[2], d[3], g[3]));
+                }
             }
         }
-    }
-#pragma unroll
-    for (int k = 0; k < NIT; ++k) {
-        const int q = threadIdx.x + 256 * k;
-        if (q >= N_GROUPS) continue;
-        const int sy = q / GROUPS, gq = q - sy * GROUPS;
-        const int gx0 = tx0 - 4 + 4 * gq;
-        float d[4], g[4];
-        if (gx0 >= 0 && gx0 + 3 < cols) {
-            g[0] = r360_gray_u8(w0[k] & 0xffu, (w0[k] >> 8) & 0xffu, (w0[k] >> 16) & 0xffu);
-            g[1] = r360_gray_u8(w0[k] >> 24, w1[k] & 0xffu, (w1[k] >> 8) & 0xffu);
-            g[2] = r360_gray_u8((w1[k] >> 16) & 0xffu, w1[k] >> 24, w2[k] & 0xffu);
-            g[3] = r360_gray_u8((w2[k] >> 8) & 0xffu, (w2[k] >> 16) & 0xffu, w2[k] >> 24);
-            if (F32DEPTH) {
-                d[0] = __uint_as_float(dw[k][0]); d[1] = __uint_as_float(dw[k][1]);
-                d[2] = __uint_as_float(dw[k][F32DEPTH ? 2 : 0]); d[3] = __uint_as_float(dw[k][F32DEPTH ? 3 : 1]);
-            } else {
-                d[0] = (float)(dw[k][0] & 0xffffu) * ds; d[1] = (float)(dw[k][0] >> 16) * ds;
-                d[2] = (float)(dw[k][1] & 0xffffu) * ds; d[3] = (float)(dw[k][1] >> 16) * ds;
-            }
-        } else {                                                               // image border columns: REFLECT_101
-            const int gy = r360_reflect101_clamped(ty0 - 2 + sy, rows);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int gx = r360_reflect101_clamped(gx0 + j, cols);
-                const size_t i = (size_t)gy * cols + gx;
-                g[j] = r360_gray_u8(c8[3 * i], c8[3 * i + 1], c8[3 * i + 2]);
-                d[j] = F32DEPTH ? depth_m[(size_t)f * n_px + i] : (float)depth_mm[(size_t)f * n_px + i] * ds;
-            }
-        }
-        float4* o = reinterpret_cast<float4*>(&s_dg[sy][4 * gq]);
-        o[0] = make_float4(d[0], g[0], d[1], g[1]);
-        o[1] = make_float4(d[2], g[2], d[3], g[3]);
     }
     __syncthreads();
 
     // ---- phase 2: level-0 outputs.  A thread walks down a strip of rows of ONE pixel-pair column (lane = column pair, so a
     //      warp still writes one contiguous row segment per step) and carries the vertical differences' reciprocals from
-    //      row to row (r360_texel_pair_col).
-    float2* __restrict__ l0 = l0_dst[f];
-    float4* __restrict__ tex = reinterpret_cast<float4*>(texel_dst[f]);
+    //      row to row (r360_texel_pair_colz).  Everything that depends only on the column -- the joint / border masks, the
+    //      shared-memory address -- is set up once; the strip is unrolled, so the row offsets are immediates.
     {
+        float4* __restrict__ l0 = reinterpret_cast<float4*>(l0_dst[f]);
+        float4* __restrict__ tex = reinterpret_cast<float4*>(texel_dst[f]);
         constexpr int STRIP = R360_F0_TH / (256 / (R360_F0_TW / 2));             // rows per thread
         const int lp = threadIdx.x % (R360_F0_TW / 2), ly0 = (threadIdx.x / (R360_F0_TW / 2)) * STRIP;
-        const int c = tx0 + 2 * lp, sx = 2 * lp + 4;
-        if (c < cols && ty0 + ly0 < rows) {                                      // cols is even: the pair is inside or outside
-            float4 u = *reinterpret_cast<const float4*>(&s_dg[ly0 + 1][sx]);     // row above the strip
-            float4 v = *reinterpret_cast<const float4*>(&s_dg[ly0 + 2][sx]);
-            R360ColState st;
-            if (tex) r360_col_state_init(st, u, v);
-            size_t pi = ((size_t)(ty0 + ly0) * cols + c) >> 1;                   // pixel-pair index
-            const size_t pi_step = (size_t)cols >> 1;
-#pragma unroll 2
-            for (int ly = ly0; ly < ly0 + STRIP; ++ly, pi += pi_step) {
-                const int r = ty0 + ly;
-                if (r >= rows) break;
-                const float4 d = *reinterpret_cast<const float4*>(&s_dg[ly + 3][sx]);
-                if (l0) reinterpret_cast<float4*>(l0)[pi] = v;
-                if (tex) {
-                    float4 t[3];
-                    r360_texel_pair_col(st, v, u, d, s_dg[ly + 2][sx - 1], s_dg[ly + 2][sx + 2], r, c, rows, cols, mg, t);
-                    tex[3 * pi + 0] = t[0];
-                    tex[3 * pi + 1] = t[1];
-                    tex[3 * pi + 2] = t[2];
+        const int c = tx0 + 2 * lp, r0 = ty0 + ly0;
+        if (c < cols && r0 < rows) {                                             // cols is even: the pair is inside or outside
+            const unsigned sa = sbase + (unsigned)((ly0 + 1) * R360_F0_SW + 2 * lp + 4) * 8u;   // the row above the strip
+            const int n_row = min(STRIP, rows - r0);
+            const unsigned half = (unsigned)cols >> 1;
+            unsigned po = ((unsigned)r0 * (unsigned)cols + (unsigned)c) >> 1;    // pixel-pair index
+            float4 v = r360_lds128(sa + R360_F0_ROWB);
+            if (tex) {
+                float4 u = r360_lds128(sa);
+                R360ColState st;
+                r360_col_state_init_t<F32DEPTH>(st, u, v);
+                const bool zc0 = (c == 0) | r360_joint_column(c, mg), zc1 = (c + 2 == cols) | r360_joint_column(c + 1, mg);
+                auto strip = [&](auto with_l0) {                                 // a frame with both roles also gets its plane
+#pragma unroll
+                    for (int k = 0; k < STRIP; ++k) {
+                        if (k >= n_row) break;
+                        const float4 d = r360_lds128(sa + (k + 2) * R360_F0_ROWB);
+                        const float2 wv = r360_lds64(sa + (k + 1) * R360_F0_ROWB - 8), e = r360_lds64(sa + (k + 1) * R360_F0_ROWB + 16);
+                        if (decltype(with_l0)::value) l0[po] = v;
+                        const bool rb = (unsigned)(r0 + k - 1) >= (unsigned)(rows - 2);      // first / last image row
+                        float4 t[3];
+                        r360_texel_pair_colz<F32DEPTH>(st, v, u, d, wv, e, zc0 | rb, zc1 | rb, t);
+                        float4* o = tex + 3 * (size_t)po;
+                        o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+                        u = v; v = d; po += half;
+                    }
+                };
+                if (l0) strip(std::true_type{}); else strip(std::false_type{});
+            } else if (l0) {
+#pragma unroll
+                for (int k = 0; k < STRIP; ++k) {
+                    if (k >= n_row) break;
+                    l0[po] = v;
+                    v = r360_lds128(sa + (k + 2) * R360_F0_ROWB);
+                    po += half;
                 }
-                u = v; v = d;
             }
         }
     }
 
-    // ---- phase 3: level 1.  Horizontal 5-tap of every staged row (k_down's r360_down_hrow), then the
-    //      vertical combination and the depth valid-mean.
-    for (int q = threadIdx.x; q < (R360_F0_TW / 2) * R360_F0_SH; q += 256) {
-        const int sy = q / (R360_F0_TW / 2), ox = q - sy * (R360_F0_TW / 2);
-        const float2* row = &s_dg[sy][2 * ox + 2];                              // global columns 2x-2 .. 2x+2
-        const float c0 = row[0].y, c1 = row[1].y, c2 = row[2].y, c3 = row[3].y, c4 = row[4].y;
-        s_h[sy][ox] = c2 * 6 + (c1 + c3) * 4 + c0 + c4;
-    }
-    __syncthreads();
-    float2* __restrict__ l1 = l1_dst[f] ;
-    const int h1 = rows >> 1, wd1 = cols >> 1;
-    for (int q = threadIdx.x; q < (R360_F0_TW / 2) * (R360_F0_TH / 2); q += 256) {
-        const int oy = q / (R360_F0_TW / 2), ox = q - oy * (R360_F0_TW / 2);
-        const int y = (ty0 >> 1) + oy, x = (tx0 >> 1) + ox;
-        if (y >= h1 || x >= wd1) continue;
-        const float hm2 = s_h[2 * oy][ox], hm1 = s_h[2 * oy + 1][ox], r0 = s_h[2 * oy + 2][ox],
-                    r1 = s_h[2 * oy + 3][ox], r2 = s_h[2 * oy + 4][ox];
-        const float a = (hm2 + r2) + (r0 + r0);
-        const float b = ((hm1 + r1) + r0) * 4.0f;
-        const float gray = (a + b) * (1.f / 256);
-        const float4 p0 = *reinterpret_cast<const float4*>(&s_dg[2 * oy + 2][2 * ox + 4]);   // row 2y:   {dl, g, dr, g}
-        const float4 p1 = *reinterpret_cast<const float4*>(&s_dg[2 * oy + 3][2 * ox + 4]);   // row 2y+1
-        float av = 0.f;
-        unsigned cnt = 0;
-        if (p0.x > min_d && p0.x < max_d) { av += p0.x; ++cnt; }
-        if (p0.z > min_d && p0.z < max_d) { av += p0.z; ++cnt; }
-        if (p1.x > min_d && p1.x < max_d) { av += p1.x; ++cnt; }
-        if (p1.z > min_d && p1.z < max_d) { av += p1.z; ++cnt; }
-        const float depth = cnt > 0 ? av / cnt : 0.f;
-        l1[(size_t)y * wd1 + x] = make_float2(depth, gray);
+    // ---- phase 3: level 1.  A thread owns one output column of a strip of 4 output rows and rolls the horizontally
+    //      filtered rows through registers (k_down's scheme, from shared memory): 2 new rows per output row.
+    {
+        constexpr int OSTRIP = (R360_F0_TH / 2) / (256 / (R360_F0_TW / 2));      // output rows per thread
+        const int ox = threadIdx.x % (R360_F0_TW / 2), oy0 = (threadIdx.x / (R360_F0_TW / 2)) * OSTRIP;
+        const int h1 = rows >> 1, wd1 = cols >> 1;
+        const int x = (tx0 >> 1) + ox, y0 = (ty0 >> 1) + oy0;
+        if (x < wd1 && y0 < h1) {
+            float2* __restrict__ l1 = l1_dst[f] + (size_t)y0 * wd1 + x;
+            const int n_out = min(OSTRIP, h1 - y0);
+            const unsigned ra = sbase + (unsigned)(2 * oy0 * R360_F0_SW + 2 * ox + 2) * 8u;    // smem row 2 oy0, column 2 ox + 2
+            float hm2 = r360_head_hrow(ra).h, hm1 = r360_head_hrow(ra + R360_F0_ROWB).h;
+            R360HRow q0 = r360_head_hrow(ra + 2 * R360_F0_ROWB);
+#pragma unroll
+            for (int j = 0; j < OSTRIP; ++j) {
+                if (j >= n_out) break;
+                const R360HRow q1 = r360_head_hrow(ra + (2 * j + 3) * R360_F0_ROWB);
+                const R360HRow q2 = r360_head_hrow(ra + (2 * j + 4) * R360_F0_ROWB);
+                const float a = (hm2 + q2.h) + (q0.h + q0.h);
+                const float b = ((hm1 + q1.h) + q0.h) * 4.0f;
+                const float gray = (a + b) * (1.f / 256);
+                float av = 0.f;
+                unsigned cnt = 0;
+                if (q0.dl > min_d && q0.dl < max_d) { av += q0.dl; ++cnt; }
+                if (q0.dr > min_d && q0.dr < max_d) { av += q0.dr; ++cnt; }
+                if (q1.dl > min_d && q1.dl < max_d) { av += q1.dl; ++cnt; }
+                if (q1.dr > min_d && q1.dr < max_d) { av += q1.dr; ++cnt; }
+                const float depth = cnt > 0 ? av / cnt : 0.f;
+                l1[(size_t)j * wd1] = make_float2(depth, gray);
+                hm2 = q0.h; hm1 = q1.h; q0 = q2;
+            }
+        }
     }
 }
 
