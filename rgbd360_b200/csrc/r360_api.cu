@@ -53,6 +53,7 @@ struct Ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_copy[kStages]{}, ev_done[kStages]{};
     int chunk = kChunkFrames;                    // frames per chunk = min(kChunkFrames, max_frames)
+    bool use_pyr_mid = true;                     // R360_PYR_MID=0: k_down + k_texel for the levels >= 1 (A/B measurements)
     bool use_pyr_head = true;                    // R360_PYR_HEAD=0 in the environment: the separate level-0 kernels (A/B measurements)
     long long n_chunks_done = 0;                 // staging-buffer rotation across calls
     std::vector<cudaEvent_t> ev_pass;            // pairs of events around each pixel pass
@@ -256,6 +257,19 @@ int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t
     } else {
         r360_launch_level0(c->st, rgb_dev, depth_mm_dev, depth_m_dev, c->d_pyr + table_off, n, c->rows * c->cols, c->sm_count);
         ++c->launches;
+    }
+    if (fused_head && c->use_pyr_mid) {
+        // levels >= 1: the level's target texels and the next level from ONE read of its plane (k_texel + k_down in one kernel)
+        for (int l = 1; l < c->L; ++l) {
+            const bool next = l + 1 < c->L;
+            if (!next && !n_t) break;
+            r360_launch_pyr_mid(c->st, c->d_pyr + table_off, n_t ? c->d_tex + table_off : nullptr, c->lv[l].px_off,
+                                next ? c->lv[l + 1].px_off : -1, c->lv[l].rows, c->lv[l].cols, c->P.min_depth, c->P.max_depth,
+                                c->P.n_sensors_mask, n);
+            ++c->launches;
+        }
+        CK(c, cudaGetLastError());
+        return R360_OK;
     }
     for (int l = fused_head ? 2 : 1; l < c->L; ++l) {
         r360_launch_down(c->st, c->d_pyr + table_off, c->lv[l - 1].px_off, c->lv[l].px_off, c->lv[l - 1].rows,
@@ -566,6 +580,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaMallocHost(&c->h_l1, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_l1, sizeof(void*) * max_frames));
     CK(c, cudaMallocHost(&c->h_tex, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_tex, sizeof(void*) * max_frames));
     if (const char* e = getenv("R360_PYR_HEAD")) c->use_pyr_head = atoi(e) != 0;
+    if (const char* e = getenv("R360_PYR_MID")) c->use_pyr_mid = atoi(e) != 0;
 
     const int np = max_pairs + 1;     // + 1 spare slot for the eval hooks
     CK(c, cudaMalloc(&c->d_pairs, sizeof(R360Pair) * np));

@@ -325,12 +325,24 @@ k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long lo
 #define R360_F0_SW (R360_F0_TW + 8)            // smem columns: global x = tx0 - 4 + sx
 #define R360_F0_SH (R360_F0_TH + 4)            // smem rows:    global y = ty0 - 2 + sy
 #define R360_F0_ROWB (R360_F0_SW * 8)          // bytes per smem row
+#ifdef R360_F0_STAGE
+#define R360_F0_DYN_SMEM (8 * 96 * 16)         // staging rows of the 8 warps (variant build)
+#else
+#define R360_F0_DYN_SMEM 0
+#endif
 __device__ __forceinline__ int r360_reflect101_clamped(int i, int n) {
     i = r360_reflect101(i, n);
     return min(max(i, 0), n - 1);               // partial tiles reach far outside; those values are never used
 }
 __device__ __forceinline__ float r360_gray_u8(unsigned r, unsigned g, unsigned b) {
     const int v = (int)(r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15;
+    return (float)v * (float)(1. / 255);
+}
+// r * 9798 + g * 19235 + b * 3735 of the three bytes of `px` starting at bit `sh` (0 or 8), as hi * 256 + lo byte dot products.
+__device__ __forceinline__ float r360_gray_dp4a(unsigned px, int sh) {
+    const unsigned WL = 0x00972346u << sh, WH = 0x000e4b26u << sh;            // low / high bytes of {9798, 19235, 3735}
+    const unsigned lo = __dp4a(px, WL, 16384u), hi = __dp4a(px, WH, 0u);
+    const int v = (int)(hi * 256u + lo) >> 15;
     return (float)v * (float)(1. / 255);
 }
 __device__ __forceinline__ float2 r360_lds64(unsigned smem) {
@@ -410,16 +422,28 @@ __device__ __forceinline__ R360HRow r360_head_hrow(unsigned row_addr) {     // a
     o.dl = B.x; o.dr = B.z;
     return o;
 }
-template <bool F32DEPTH>
+// IN: 0 = RGB8 + 16-bit depth, 1 = RGB8 + CV_32F depth, 2 = the {depth, gray} plane of a level >= 1 (plane_in[f] + off_in):
+// the same tile pass then writes that level's target texels and the next level (k_texel + k_down in one read of the plane).
+// off_l1 / off_tex: element offsets added to l1_dst[f] / texel_dst[f]; a null table or entry = that output is not wanted.
+#define R360_IN_PLANE 2
+template <int IN>
 __global__ void __launch_bounds__(256, R360_F0_MINB)
 k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_mm, const float* __restrict__ depth_m,
-           float2* const* __restrict__ l0_dst, float2* const* __restrict__ l1_dst, float* const* __restrict__ texel_dst,
+           const float2* const* __restrict__ plane_in, long long off_in,
+           float2* const* __restrict__ l0_dst, float2* const* __restrict__ l1_dst, long long off_l1,
+           float* const* __restrict__ texel_dst, long long off_tex,
            int rows, int cols, int tiles_x, float min_d, float max_d, R360MaskGeom mg) {
+    constexpr bool F32DEPTH = IN == 1;
+    constexpr bool SCALED = IN != 0;                                             // see r360_texel_pair_colz
     __shared__ __align__(16) float2 s_dg[R360_F0_SH][R360_F0_SW];
+#ifdef R360_F0_STAGE
+    extern __shared__ __align__(16) float4 s_stage[];                            // [8][96] per warp: the texels of one pair row (32 x 48 B)
+#endif
     const int f = blockIdx.y;
     const int ty0 = (blockIdx.x / tiles_x) * R360_F0_TH, tx0 = (blockIdx.x % tiles_x) * R360_F0_TW;
     const size_t n_px = (size_t)rows * cols;
-    const uint8_t* __restrict__ c8 = rgb + (size_t)f * n_px * 3;
+    const uint8_t* __restrict__ c8 = IN == R360_IN_PLANE ? nullptr : rgb + (size_t)f * n_px * 3;
+    const float2* __restrict__ pin = IN == R360_IN_PLANE ? plane_in[f] + off_in : nullptr;
     const float ds = (float)0.001;
     const unsigned sbase = r360_smem_addr(&s_dg[0][0]);
 
@@ -433,7 +457,25 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
         const int gx0 = tx0 - 4 + 4 * gq;
         if (tr < RPP) {
             const unsigned sdst = sbase + (unsigned)(tr * R360_F0_SW + 4 * gq) * 8u;
-            if (gx0 >= 0 && gx0 + 3 < cols) {
+            if (IN == R360_IN_PLANE && gx0 >= 0 && gx0 + 3 < cols) {               // four staged pixels = two 16-byte loads
+                float4 a[NIT], b[NIT];
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    const int sy = tr + RPP * k;
+                    if (sy < R360_F0_SH) {
+                        const unsigned off = (unsigned)r360_reflect101_clamped(ty0 - 2 + sy, rows) * (unsigned)cols + (unsigned)gx0;   // even
+                        const float4* q = reinterpret_cast<const float4*>(pin + off);
+                        a[k] = __ldg(q); b[k] = __ldg(q + 1);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    if (tr + RPP * k < R360_F0_SH) {
+                        r360_sts128(sdst + (unsigned)(RPP * k) * R360_F0_ROWB, a[k]);
+                        r360_sts128(sdst + (unsigned)(RPP * k) * R360_F0_ROWB + 16, b[k]);
+                    }
+                }
+            } else if (IN != R360_IN_PLANE && gx0 >= 0 && gx0 + 3 < cols) {
                 uint32_t w0[NIT], w1[NIT], w2[NIT];
                 uint32_t dw[NIT][F32DEPTH ? 4 : 2];
                 const uint32_t* __restrict__ c32 = reinterpret_cast<const uint32_t*>(c8);
@@ -457,10 +499,19 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
                 for (int k = 0; k < NIT; ++k) {
                     if (tr + RPP * k < R360_F0_SH) {
                         float d[4], g[4];
+#ifdef R360_GRAY_DP4A
+                        // the same integer sum as r360_gray_u8 as two byte dot products (weights split into high and low
+                        // bytes): no byte extraction for pixels 0 and 3, one permute for pixels 1 and 2
+                        g[0] = r360_gray_dp4a(w0[k], 0);
+                        g[1] = r360_gray_dp4a(__byte_perm(w0[k], w1[k], 0x0543), 0);
+                        g[2] = r360_gray_dp4a(__byte_perm(w1[k], w2[k], 0x0432), 0);
+                        g[3] = r360_gray_dp4a(w2[k], 8);
+#else
                         g[0] = r360_gray_u8(w0[k] & 0xffu, (w0[k] >> 8) & 0xffu, (w0[k] >> 16) & 0xffu);
                         g[1] = r360_gray_u8(w0[k] >> 24, w1[k] & 0xffu, (w1[k] >> 8) & 0xffu);
                         g[2] = r360_gray_u8((w1[k] >> 16) & 0xffu, w1[k] >> 24, w2[k] & 0xffu);
                         g[3] = r360_gray_u8((w2[k] >> 8) & 0xffu, (w2[k] >> 16) & 0xffu, w2[k] >> 24);
+#endif
                         if (F32DEPTH) {
                             d[0] = __uint_as_float(dw[k][0]); d[1] = __uint_as_float(dw[k][1]);
                             d[2] = __uint_as_float(dw[k][F32DEPTH ? 2 : 0]); d[3] = __uint_as_float(dw[k][F32DEPTH ? 3 : 1]);
@@ -480,8 +531,13 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
                     for (int j = 0; j < 4; ++j) {
                         const int gx = r360_reflect101_clamped(gx0 + j, cols);
                         const size_t i = (size_t)gy * cols + gx;
-                        g[j] = r360_gray_u8(c8[3 * i], c8[3 * i + 1], c8[3 * i + 2]);
-                        d[j] = F32DEPTH ? depth_m[(size_t)f * n_px + i] : (float)depth_mm[(size_t)f * n_px + i] * ds;
+                        if (IN == R360_IN_PLANE) {
+                            const float2 t = __ldg(pin + i);
+                            d[j] = t.x; g[j] = t.y;
+                        } else {
+                            g[j] = r360_gray_u8(c8[3 * i], c8[3 * i + 1], c8[3 * i + 2]);
+                            d[j] = F32DEPTH ? depth_m[(size_t)f * n_px + i] : (float)depth_mm[(size_t)f * n_px + i] * ds;
+                        }
                     }
                     const unsigned a = sbase + (unsigned)(sy * R360_F0_SW + 4 * gq) * 8u;
                     r360_sts128(a, make_float4(d[0], g[0], d[1], g[1]));
@@ -497,8 +553,9 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
     //      row to row (r360_texel_pair_colz).  Everything that depends only on the column -- the joint / border masks, the
     //      shared-memory address -- is set up once; the strip is unrolled, so the row offsets are immediates.
     {
-        float4* __restrict__ l0 = reinterpret_cast<float4*>(l0_dst[f]);
-        float4* __restrict__ tex = reinterpret_cast<float4*>(texel_dst[f]);
+        float4* __restrict__ l0 = IN == R360_IN_PLANE ? nullptr : reinterpret_cast<float4*>(l0_dst[f]);
+        float* const tex_f = texel_dst ? texel_dst[f] : nullptr;
+        float4* __restrict__ tex = tex_f ? reinterpret_cast<float4*>(tex_f + off_tex) : nullptr;
         constexpr int STRIP = R360_F0_TH / (256 / (R360_F0_TW / 2));             // rows per thread
         const int lp = threadIdx.x % (R360_F0_TW / 2), ly0 = (threadIdx.x / (R360_F0_TW / 2)) * STRIP;
         const int c = tx0 + 2 * lp, r0 = ty0 + ly0;
@@ -511,8 +568,12 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
             if (tex) {
                 float4 u = r360_lds128(sa);
                 R360ColState st;
-                r360_col_state_init_t<F32DEPTH>(st, u, v);
+                r360_col_state_init_t<SCALED>(st, u, v);
                 const bool zc0 = (c == 0) | r360_joint_column(c, mg), zc1 = (c + 2 == cols) | r360_joint_column(c + 1, mg);
+#ifdef R360_F0_STAGE
+                const bool full_warp = tx0 + R360_F0_TW <= cols;                  // every lane of the warp has a pair (uniform over the CTA)
+                const unsigned stg = r360_smem_addr(&s_stage[(threadIdx.x / 32) * 96]);
+#endif
                 auto strip = [&](auto with_l0) {                                 // a frame with both roles also gets its plane
 #pragma unroll
                     for (int k = 0; k < STRIP; ++k) {
@@ -522,9 +583,23 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
                         if (decltype(with_l0)::value) l0[po] = v;
                         const bool rb = (unsigned)(r0 + k - 1) >= (unsigned)(rows - 2);      // first / last image row
                         float4 t[3];
-                        r360_texel_pair_colz<F32DEPTH>(st, v, u, d, wv, e, zc0 | rb, zc1 | rb, t);
-                        float4* o = tex + 3 * (size_t)po;
-                        o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+                        r360_texel_pair_colz<SCALED>(st, v, u, d, wv, e, zc0 | rb, zc1 | rb, t);
+#ifdef R360_F0_STAGE
+                        // the pair's 48 bytes leave the warp as three 512-byte rows instead of 32 strided pieces per store:
+                        // 12 cache lines per pair row instead of 36
+                        if (full_warp) {
+                            r360_sts128(stg + lp * 48, t[0]); r360_sts128(stg + lp * 48 + 16, t[1]); r360_sts128(stg + lp * 48 + 32, t[2]);
+                            __syncwarp();
+                            const float4 a0 = r360_lds128(stg + lp * 16), a1 = r360_lds128(stg + 512 + lp * 16), a2 = r360_lds128(stg + 1024 + lp * 16);
+                            __syncwarp();
+                            float4* o = tex + 3 * (size_t)(po - lp) + lp;
+                            o[0] = a0; o[32] = a1; o[64] = a2;
+                        } else
+#endif
+                        {
+                            float4* o = tex + 3 * (size_t)po;
+                            o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+                        }
                         u = v; v = d; po += half;
                     }
                 };
@@ -548,8 +623,8 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
         const int ox = threadIdx.x % (R360_F0_TW / 2), oy0 = (threadIdx.x / (R360_F0_TW / 2)) * OSTRIP;
         const int h1 = rows >> 1, wd1 = cols >> 1;
         const int x = (tx0 >> 1) + ox, y0 = (ty0 >> 1) + oy0;
-        if (x < wd1 && y0 < h1) {
-            float2* __restrict__ l1 = l1_dst[f] + (size_t)y0 * wd1 + x;
+        if (l1_dst && x < wd1 && y0 < h1) {
+            float2* __restrict__ l1 = l1_dst[f] + off_l1 + (size_t)y0 * wd1 + x;
             const int n_out = min(OSTRIP, h1 - y0);
             const unsigned ra = sbase + (unsigned)(2 * oy0 * R360_F0_SW + 2 * ox + 2) * 8u;    // smem row 2 oy0, column 2 ox + 2
             float hm2 = r360_head_hrow(ra).h, hm1 = r360_head_hrow(ra + R360_F0_ROWB).h;
@@ -1263,11 +1338,21 @@ void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* d
     const int tiles_x = (cols + R360_F0_TW - 1) / R360_F0_TW, tiles_y = (rows + R360_F0_TH - 1) / R360_F0_TH;
     dim3 grid(tiles_x * tiles_y, n_frames);
     if (depth_mm)
-        k_pyr_head<false><<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, l0_dst, l1_dst, texel_dst, rows, cols, tiles_x, min_d,
-                                                max_d, r360_mask_geom(cols, n_sensors));
+        k_pyr_head<0><<<grid, 256, R360_F0_DYN_SMEM, st>>>(rgb, depth_mm, depth_m, nullptr, 0, l0_dst, l1_dst, 0, texel_dst, 0, rows, cols,
+                                                           tiles_x, min_d, max_d, r360_mask_geom(cols, n_sensors));
     else
-        k_pyr_head<true><<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, l0_dst, l1_dst, texel_dst, rows, cols, tiles_x, min_d,
-                                               max_d, r360_mask_geom(cols, n_sensors));
+        k_pyr_head<1><<<grid, 256, R360_F0_DYN_SMEM, st>>>(rgb, depth_mm, depth_m, nullptr, 0, l0_dst, l1_dst, 0, texel_dst, 0, rows, cols,
+                                                           tiles_x, min_d, max_d, r360_mask_geom(cols, n_sensors));
+}
+// Level l >= 1 of every frame of a chunk in one read of its plane: the level's target texels (frames whose entry of
+// `tex` is not null; tex == nullptr: none) and level l + 1 (off_next >= 0).
+void r360_launch_pyr_mid(cudaStream_t st, float2* const* pyr, float* const* tex, long long off, long long off_next, int rows, int cols,
+                         float min_d, float max_d, int n_sensors, int n_frames) {
+    const int tiles_x = (cols + R360_F0_TW - 1) / R360_F0_TW, tiles_y = (rows + R360_F0_TH - 1) / R360_F0_TH;
+    dim3 grid(tiles_x * tiles_y, n_frames);
+    k_pyr_head<R360_IN_PLANE><<<grid, 256, R360_F0_DYN_SMEM, st>>>(nullptr, nullptr, nullptr, pyr, off, nullptr, off_next >= 0 ? pyr : nullptr,
+                                                                   off_next >= 0 ? off_next : 0, tex, off * R360_TEXEL_FLOATS, rows, cols, tiles_x,
+                                                                   min_d, max_d, r360_mask_geom(cols, n_sensors));
 }
 // The pass kernel's pipeline slots need more than the 48 KB default of dynamic shared memory.
 template <int METHOD, bool WITH_H>
@@ -1276,6 +1361,11 @@ static cudaError_t r360_pass_attr() {
 }
 cudaError_t r360_pass_init() {
     cudaError_t e = r360_pass_attr<R360_PHOTO_CONSISTENCY, true>();
+#ifdef R360_F0_STAGE
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pyr_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_F0_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pyr_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_F0_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pyr_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_F0_DYN_SMEM);
+#endif
     if (e == cudaSuccess) e = r360_pass_attr<R360_DEPTH_CONSISTENCY, true>();
     if (e == cudaSuccess) e = r360_pass_attr<R360_PHOTO_DEPTH, true>();
     if (e == cudaSuccess) e = r360_pass_attr<R360_PHOTO_CONSISTENCY, false>();

@@ -86,6 +86,8 @@ void r360_launch_texel(cudaStream_t st, float2* const* pyr, float* const* trg, l
 void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* depth_mm, const float* depth_m,
                           float2* const* l0_dst, float2* const* l1_dst, float* const* texel_dst, int rows, int cols,
                           float min_d, float max_d, int n_sensors, int n_frames);
+void r360_launch_pyr_mid(cudaStream_t st, float2* const* pyr, float* const* tex, long long off, long long off_next, int rows, int cols,
+                         float min_d, float max_d, int n_sensors, int n_frames);
 cudaError_t r360_pass_init();
 void r360_launch_pass(cudaStream_t st, const R360PassArgs& a, int grid, bool with_h = true);
 // occlusion variants (r360_occ.cu): head / next / dinv hold n_pairs * lv.n entries each
