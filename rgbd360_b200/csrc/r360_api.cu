@@ -209,9 +209,9 @@ R360GnArgs gn_args(Ctx* c, int n_pairs, r360_iter_record* trace, int first = 0) 
     return g;
 }
 
-// Pyramid build of frames [first, first+n) from inputs resident on the device (or staged there).
-int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t* depth_mm_dev,
-                const float* depth_m_dev, const uint8_t* roles, int table_off) {
+// Host side of the per-frame pointer tables of ONE chunk (frames [first, first+n), table entries [table_off, table_off+n)):
+// where each frame's pyramid / texels go, by role.  Returns the number of target frames through n_t.
+int fill_tables(Ctx* c, int first, int n, const uint8_t* roles, int table_off, int* n_t_out) {
     int n_t = 0;
     for (int k = 0; k < n; ++k) {
         const int slot = first + k;
@@ -232,25 +232,40 @@ int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t
             c->h_trg_t[table_off + n_t] = c->trg[slot];
             ++n_t;
         }
+        c->h_l0[table_off + k] = (role & R360_ROLE_SOURCE) ? c->h_pyr[table_off + k] : nullptr;
+        c->h_l1[table_off + k] = c->L >= 2 ? c->h_pyr[table_off + k] + c->lv[1].px_off : nullptr;
+        c->h_tex[table_off + k] = (role & R360_ROLE_TARGET) ? c->trg[slot] : nullptr;
     }
+    *n_t_out = n_t;
+    return R360_OK;
+}
+// Device copies of table entries [table_off, table_off+n): once per call for all its chunks (set_frames), not per chunk --
+// six small copies in front of every chunk's kernels cost the build 0.2 ms per 1024 frames.
+int upload_tables(Ctx* c, int table_off, int n) {
     CK(c, cudaMemcpyAsync(c->d_pyr + table_off, c->h_pyr + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
-    if (n_t) {
-        CK(c, cudaMemcpyAsync(c->d_pyr_t + table_off, c->h_pyr_t + table_off, sizeof(float2*) * n_t, cudaMemcpyHostToDevice, c->st));
-        CK(c, cudaMemcpyAsync(c->d_trg_t + table_off, c->h_trg_t + table_off, sizeof(float*) * n_t, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_pyr_t + table_off, c->h_pyr_t + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_trg_t + table_off, c->h_trg_t + table_off, sizeof(float*) * n, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_l0 + table_off, c->h_l0 + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_l1 + table_off, c->h_l1 + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(c->d_tex + table_off, c->h_tex + table_off, sizeof(float*) * n, cudaMemcpyHostToDevice, c->st));
+    return R360_OK;
+}
+
+// Pyramid build of frames [first, first+n) from inputs resident on the device (or staged there).  n_t_ready >= 0: the
+// tables of this chunk are already on the device (the caller filled and uploaded them for the whole call).
+int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t* depth_mm_dev,
+                const float* depth_m_dev, const uint8_t* roles, int table_off, int n_t_ready = -1) {
+    int n_t = n_t_ready;
+    if (n_t_ready < 0) {
+        int rc = fill_tables(c, first, n, roles, table_off, &n_t);
+        if (rc) return rc;
+        rc = upload_tables(c, table_off, n);
+        if (rc) return rc;
     }
     // Levels 0 and 1 and the level-0 texels come from ONE pass over the raw input (k_pyr_head) when the
     // pyramid has a level 1; the remaining levels from k_down / k_texel.
     const bool fused_head = c->L >= 2 && c->use_pyr_head;
     if (fused_head) {
-        for (int k = 0; k < n; ++k) {
-            const int role = roles ? roles[k] : R360_ROLE_BOTH;
-            c->h_l0[table_off + k] = (role & R360_ROLE_SOURCE) ? c->h_pyr[table_off + k] : nullptr;
-            c->h_l1[table_off + k] = c->h_pyr[table_off + k] + c->lv[1].px_off;
-            c->h_tex[table_off + k] = (role & R360_ROLE_TARGET) ? c->trg[first + k] : nullptr;
-        }
-        CK(c, cudaMemcpyAsync(c->d_l0 + table_off, c->h_l0 + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
-        CK(c, cudaMemcpyAsync(c->d_l1 + table_off, c->h_l1 + table_off, sizeof(float2*) * n, cudaMemcpyHostToDevice, c->st));
-        CK(c, cudaMemcpyAsync(c->d_tex + table_off, c->h_tex + table_off, sizeof(float*) * n, cudaMemcpyHostToDevice, c->st));
         r360_launch_pyr_head(c->st, rgb_dev, depth_mm_dev, depth_m_dev, c->d_l0 + table_off, c->d_l1 + table_off,
                              c->d_tex + table_off, c->rows, c->cols, c->P.min_depth, c->P.max_depth, c->P.n_sensors_mask, n);
         ++c->launches;
@@ -289,7 +304,7 @@ int build_chunk(Ctx* c, int first, int n, const uint8_t* rgb_dev, const uint16_t
 // One chunk of host frames: H2D on the copy stream into the next staging buffer (the copy stream
 // runs up to kStages - 1 chunks ahead of the compute stream), pyramid build on the compute stream.
 int stage_and_build(Ctx* c, int first_slot, int m, const uint8_t* rgb, const uint8_t* depth, bool depth_is_f32,
-                    const uint8_t* roles, int table_off) {
+                    const uint8_t* roles, int table_off, int n_t_ready = -1) {
     const size_t npx = (size_t)c->rows * c->cols;
     const size_t dsz = depth_is_f32 ? sizeof(float) : sizeof(uint16_t);
     const int b = (int)(c->n_chunks_done % kStages);
@@ -299,7 +314,7 @@ int stage_and_build(Ctx* c, int first_slot, int m, const uint8_t* rgb, const uin
     CK(c, cudaEventRecord(c->ev_copy[b], c->cs));
     CK(c, cudaStreamWaitEvent(c->st, c->ev_copy[b], 0));
     int rc = build_chunk(c, first_slot, m, c->stage_rgb[b], depth_is_f32 ? nullptr : (const uint16_t*)c->stage_depth[b],
-                         depth_is_f32 ? (const float*)c->stage_depth[b] : nullptr, roles, table_off);
+                         depth_is_f32 ? (const float*)c->stage_depth[b] : nullptr, roles, table_off, n_t_ready);
     if (rc) return rc;
     CK(c, cudaEventRecord(c->ev_done[b], c->st));
     ++c->n_chunks_done;
@@ -319,15 +334,24 @@ int set_frames_impl(Ctx* c, int first, int n, const uint8_t* rgb, const void* de
     const size_t npx = (size_t)c->rows * c->cols;
     const size_t dsz = depth_is_f32 ? sizeof(float) : sizeof(uint16_t);
     CK(c, cudaEventRecord(c->ev_t0, c->st));
+    std::vector<int> n_t((size_t)(n + c->chunk - 1) / c->chunk + 1, 0);
+    for (int off = 0; off < n; off += c->chunk) {                    // the pointer tables of every chunk, uploaded once
+        int rc = fill_tables(c, first + off, std::min(c->chunk, n - off), roles ? roles + off : nullptr, off, &n_t[off / c->chunk]);
+        if (rc) return rc;
+    }
+    if (n > 0) {
+        int rc = upload_tables(c, 0, n);
+        if (rc) return rc;
+    }
     for (int off = 0; off < n; off += c->chunk) {
         const int m = std::min(c->chunk, n - off);
         int rc = on_device
                      ? build_chunk(c, first + off, m, rgb + (size_t)off * npx * 3,
                                    depth_is_f32 ? nullptr : (const uint16_t*)((const uint8_t*)depth + (size_t)off * npx * dsz),
                                    depth_is_f32 ? (const float*)((const uint8_t*)depth + (size_t)off * npx * dsz) : nullptr,
-                                   roles ? roles + off : nullptr, off)
+                                   roles ? roles + off : nullptr, off, n_t[off / c->chunk])
                      : stage_and_build(c, first + off, m, rgb + (size_t)off * npx * 3, (const uint8_t*)depth + (size_t)off * npx * dsz,
-                                       depth_is_f32, roles ? roles + off : nullptr, off);
+                                       depth_is_f32, roles ? roles + off : nullptr, off, n_t[off / c->chunk]);
         if (rc) return rc;
     }
     CK(c, cudaEventRecord(c->ev_t1, c->st));
