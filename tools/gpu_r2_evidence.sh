@@ -4,6 +4,7 @@
 mkdir -p gpurun_out
 t0=$(date +%s); stamp() { echo "[+$(( $(date +%s) - t0 )) s] $*"; }
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
+stamp "fill / copy bandwidth"; python tools/gpu_fill_bw.py
 stamp bench
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -3 gpurun_out/bench_full.err; cut -c1-600 gpurun_out/bench_full.json
 stamp "launch list of one step (512 pairs)"
@@ -14,8 +15,11 @@ stamp "full captures"
 # one 512-pair step: level 0 starts after 3 levels x (14 fused + 13 error-only) = 81 k_pass launches
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_pass -s 81 -c 5 -f -o gpurun_out/prof_pass \
     python bench.py --one-step > gpurun_out/b_ncu2.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pyr_head -s 1 -c 1 -f -o gpurun_out/prof_pyr_head \
+# per chunk of 128 frames: k_pyr_head<0> (raw input), then k_pyr_head<2> for levels 1, 2, 3 -- launch 4 is the head of the second chunk, launch 1 the level-1 pass
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pyr_head -s 4 -c 1 -f -o gpurun_out/prof_pyr_head \
     python bench.py --one-step --pairs 128 > gpurun_out/b_ncu3.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pyr_head -s 1 -c 1 -f -o gpurun_out/prof_pyr_mid \
+    python bench.py --one-step --pairs 128 > gpurun_out/b_ncu4.log 2>&1
 stamp sanitizer
 for tool in memcheck racecheck initcheck synccheck; do
   echo "== $tool: smoke()"
