@@ -249,6 +249,45 @@ def test_non_power_of_two_width(orc, r360):
     ctx.close()
 
 
+@pytest.mark.parametrize("shape", [(80, 480, 3), (72, 200, 3), (256, 512, 4), (16, 32, 2)])
+def test_pyramid_routes_agree_bit_for_bit(orc, r360, shape, monkeypatch):
+    """The fused pyramid passes (k_pyr_head over the raw input, the same pass over the plane of every level >= 1) against the
+    separate kernels (k_level0 / k_down / k_texel) and against the oracle: every plane of every level, both roles, partial
+    tiles, widths that are not a multiple of the tile, 16-bit and CV_32F depth."""
+    rows, cols, L = shape
+    P = orc.default_params(n_levels=L)
+    rng = np.random.default_rng(rows * 1000 + cols)
+    rgb = rng.integers(0, 256, size=(2, rows, cols, 3), dtype=np.uint8)
+    d = rng.integers(0, 12000, size=(2, rows, cols)).astype(np.uint16)
+    d[rng.random(d.shape) < 0.1] = 0                                      # invalid depth
+    ref = [orc.Frame(rgb[k], d[k], P, True) for k in range(2)]
+    dumps = {}
+    for mid, head in (("1", "1"), ("0", "1"), ("0", "0")):
+        monkeypatch.setenv("R360_PYR_MID", mid)
+        monkeypatch.setenv("R360_PYR_HEAD", head)
+        for f32 in (False, True):
+            ctx = r360.Context(rows, cols, 2, 1, r360.default_params(n_levels=L))
+            ctx.set_frames(0, rgb, (d.astype(np.float32) * np.float32(0.001)) if f32 else d)
+            out = []
+            for k in range(2):
+                for level in range(L):
+                    g = ctx.dump_level(k, level)
+                    gs = ctx.dump_source_level(k, level)
+                    out.append(np.concatenate([g[n].view(np.int32).ravel() for n in ("gray", "depth", "ggx", "ggy", "dgx", "dgy")] +
+                                              [gs[n].view(np.int32).ravel() for n in ("gray", "depth")]))
+                    if not f32:
+                        o = ref[k].level(level)
+                        for n in ("gray", "depth", "ggx", "ggy", "dgx", "dgy"):
+                            assert np.array_equal(g[n].view(np.int32), o[n].view(np.int32)), (mid, head, k, level, n)
+            dumps[(mid, head, f32)] = np.concatenate(out)
+            ctx.close()
+    for f32 in (False, True):
+        assert np.array_equal(dumps[("1", "1", f32)], dumps[("0", "1", f32)])
+        assert np.array_equal(dumps[("1", "1", f32)], dumps[("0", "0", f32)])
+    # the same depth values as CV_32F: the monotonicity test on 2^100-scaled differences == the one on the differences themselves
+    assert np.array_equal(dumps[("1", "1", False)], dumps[("1", "1", True)])
+
+
 def test_register_host_pairs_streaming(r360):
     """The pipelined host entry point (upload + pyramids + batched registration overlapped) returns
     the same records as set_frames + register_pairs; more pairs than one internal batch."""
