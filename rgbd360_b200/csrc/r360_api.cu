@@ -832,8 +832,11 @@ int r360_register_host_pairs(r360_ctx* c, int n_pairs, const uint8_t* rgb, const
     for (size_t k = 0; k < roles.size(); ++k) roles[k] = (k & 1) ? R360_ROLE_SOURCE : R360_ROLE_TARGET;
     CK(c, cudaEventRecord(c->ev_t0, c->st));
     int n_ev = 0;
-    for (int first = 0; first < n_pairs; first += kStreamPairs) {
-        const int nb = std::min(kStreamPairs, n_pairs - first);
+    // Batches of kStreamPairs; the last kStreamPairs pairs go in halves (32, 16, 8, 8): the upload is the bottleneck of the
+    // call, and what the device still has to do after the last byte arrived -- the pipeline's drain -- is the last batch.
+    for (int first = 0, nb = 0; first < n_pairs; first += nb) {
+        const int left = n_pairs - first;
+        nb = left > kStreamPairs ? kStreamPairs : (left > 8 ? (left + 1) / 2 : left);
         for (int off = 0; off < 2 * nb; off += c->chunk) {
             const int m = std::min(c->chunk, 2 * nb - off);
             const size_t f0 = 2 * (size_t)first + off;
