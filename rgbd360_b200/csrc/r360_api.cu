@@ -729,9 +729,17 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
             else r360_launch_gn_step(c->st, g, level);
             ++c->launches;
             if (latency_mode) {
-                CK(c, cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->st));
-                CK(c, cudaStreamSynchronize(c->st));
-                if (c->h_nactive[0] == 0 && c->h_nactive[3] == 0) break;      // every pair has left this level
+                // The host stays ONE step ahead: step k is enqueued before the list lengths of step k - 1 are looked at, so the
+                // device never waits for the round trip; when step k - 1 emptied the lists, step k runs as three empty launches.
+                int* h = c->h_nactive + 4 * (k & 1);
+                cudaEvent_t ev = (k & 1) ? c->ev_join : c->ev_fork;
+                CK(c, cudaMemcpyAsync(h, c->d_nactive, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->st));
+                CK(c, cudaEventRecord(ev, c->st));
+                if (k >= 1) {
+                    const int* hp = c->h_nactive + 4 * ((k - 1) & 1);
+                    CK(c, cudaEventSynchronize((k & 1) ? c->ev_fork : c->ev_join));
+                    if (hp[0] == 0 && hp[3] == 0) break;                      // every pair has left this level
+                }
             }
         }
     }
@@ -832,11 +840,14 @@ int r360_register_host_pairs(r360_ctx* c, int n_pairs, const uint8_t* rgb, const
     for (size_t k = 0; k < roles.size(); ++k) roles[k] = (k & 1) ? R360_ROLE_SOURCE : R360_ROLE_TARGET;
     CK(c, cudaEventRecord(c->ev_t0, c->st));
     int n_ev = 0;
-    // Batches of kStreamPairs; the last kStreamPairs pairs go in halves (32, 16, 8, 8): the upload is the bottleneck of the
-    // call, and what the device still has to do after the last byte arrived -- the pipeline's drain -- is the last batch.
+    // Batches of kStreamPairs; in a call of several batches the last kStreamPairs pairs go in halves (32, 16, 8, 8): the
+    // upload is the bottleneck of the call, and what the device still has to do after the last byte arrived -- the
+    // pipeline's drain -- is the last batch.  A call of at most one batch stays one batch (the decomposition, and with it
+    // every bit of the records, is that of r360_register_pairs).
+    const bool halve_tail = n_pairs > kStreamPairs;
     for (int first = 0, nb = 0; first < n_pairs; first += nb) {
         const int left = n_pairs - first;
-        nb = left > kStreamPairs ? kStreamPairs : (left > 8 ? (left + 1) / 2 : left);
+        nb = left > kStreamPairs ? kStreamPairs : (halve_tail && left > 8 ? (left + 1) / 2 : left);
         for (int off = 0; off < 2 * nb; off += c->chunk) {
             const int m = std::min(c->chunk, 2 * nb - off);
             const size_t f0 = 2 * (size_t)first + off;
