@@ -729,17 +729,9 @@ static int enqueue_register(r360_ctx* c, int first, int n, int n_total, bool has
             else r360_launch_gn_step(c->st, g, level);
             ++c->launches;
             if (latency_mode) {
-                // The host stays ONE step ahead: step k is enqueued before the list lengths of step k - 1 are looked at, so the
-                // device never waits for the round trip; when step k - 1 emptied the lists, step k runs as three empty launches.
-                int* h = c->h_nactive + 4 * (k & 1);
-                cudaEvent_t ev = (k & 1) ? c->ev_join : c->ev_fork;
-                CK(c, cudaMemcpyAsync(h, c->d_nactive, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->st));
-                CK(c, cudaEventRecord(ev, c->st));
-                if (k >= 1) {
-                    const int* hp = c->h_nactive + 4 * ((k - 1) & 1);
-                    CK(c, cudaEventSynchronize((k & 1) ? c->ev_fork : c->ev_join));
-                    if (hp[0] == 0 && hp[3] == 0) break;                      // every pair has left this level
-                }
+                CK(c, cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->st));
+                CK(c, cudaStreamSynchronize(c->st));
+                if (c->h_nactive[0] == 0 && c->h_nactive[3] == 0) break;      // every pair has left this level
             }
         }
     }
