@@ -4,7 +4,6 @@
 mkdir -p gpurun_out
 t0=$(date +%s); stamp() { echo "[+$(( $(date +%s) - t0 )) s] $*"; }
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
-stamp "fill / copy bandwidth"; python tools/gpu_fill_bw.py
 stamp bench
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -3 gpurun_out/bench_full.err; cut -c1-600 gpurun_out/bench_full.json
 stamp "launch list of one step (512 pairs)"
