@@ -205,7 +205,7 @@ __device__ __forceinline__ void r360_texel_pair(float4 v, float4 u, float4 d, fl
     out[1] = make_float4(G.dx.x, G.dy.x, v.w, v.z);
     out[2] = make_float4(G.ix.y, G.iy.y, G.dx.y, G.dy.y);
 }
-// ---- the same gradients for a thread that walks DOWN a column of pixel pairs (k_pyr_head): of the 12 reciprocals per
+// ---- the same gradients for a thread that walks DOWN a column of pixel pairs (k_pyr_head, r360_texel_pair_colz below): of the 12 reciprocals per
 // pixel of calcGradientXY, three are shared.  Lanes are packed {depth, gray} of ONE pixel -- the order the plane is stored
 // in, so differences are formed on the loaded register pairs as they are.
 //   x: the three horizontal differences of a pair (v0 - w, v1 - v0, e - v1) serve both pixels: pixel 0's forward
@@ -216,58 +216,6 @@ __device__ __forceinline__ void r360_texel_pair(float4 v, float4 u, float4 d, fl
 struct R360ColState { float2 ra0, ra1, ka0, ka1; };     // 1 / (v[r] - v[r-1]) and (v[r] - v[r-1]) 2^100 of pixel 0 / 1, {depth, gray}
 __device__ __forceinline__ float2 r360_lo(float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 r360_hi(float4 v) { return make_float2(v.z, v.w); }
-__device__ __forceinline__ void r360_col_state_init(R360ColState& st, float4 u, float4 v) {
-    const float K = 1.2676506002282294e30f;                                  // 2^100
-    const float2 a0 = f2add(r360_lo(v), f2neg(r360_lo(u))), a1 = f2add(r360_hi(v), f2neg(r360_hi(u)));
-    st.ra0 = f2rcp_rn(a0); st.ra1 = f2rcp_rn(a1);
-    st.ka0 = f2mul(a0, R360_F2(K)); st.ka1 = f2mul(a1, R360_F2(K));
-}
-__device__ __forceinline__ float2 r360_hsel(float2 rsum, float2 ka, float2 kb) {
-    const float2 r = f2rcp_rn(rsum);
-    const float2 g = f2add(r, r);
-    const float2 p = f2mul(ka, kb);
-    return make_float2(p.x > 0.f ? g.x : 0.f, p.y > 0.f ? g.y : 0.f);
-}
-// Texels of the pixel pair (r, c), (r, c + 1): v the pair, d the pair below, wv / e the pixels west / east; st: the column
-// state (updated to row r for the next row).  Same outputs as r360_texel_pair.
-__device__ __forceinline__ void r360_texel_pair_col(R360ColState& st, float4 v, float4 u, float4 d, float2 wv, float2 e, int r, int c,
-                                                    int rows, int cols, const R360MaskGeom& mg, float4 out[3]) {
-    const float K = 1.2676506002282294e30f;
-    // y: forward differences of this row; the backward ones are the state
-    const float2 ay0 = f2add(r360_lo(d), f2neg(r360_lo(v))), ay1 = f2add(r360_hi(d), f2neg(r360_hi(v)));
-    const float2 ray0 = f2rcp_rn(ay0), ray1 = f2rcp_rn(ay1);
-    const float2 kay0 = f2mul(ay0, R360_F2(K)), kay1 = f2mul(ay1, R360_F2(K));
-    float2 gy0 = r360_hsel(f2add(ray0, st.ra0), kay0, st.ka0);               // {Dy, Iy} of pixel 0
-    float2 gy1 = r360_hsel(f2add(ray1, st.ra1), kay1, st.ka1);
-    st.ra0 = ray0; st.ra1 = ray1; st.ka0 = kay0; st.ka1 = kay1;
-    // x: three differences for the two pixels
-    const float2 d0 = f2add(r360_lo(v), f2neg(wv)), d1 = f2add(r360_hi(v), f2neg(r360_lo(v))), d2 = f2add(e, f2neg(r360_hi(v)));
-    const float2 r0 = f2rcp_rn(d0), r1 = f2rcp_rn(d1), r2 = f2rcp_rn(d2);
-    const float2 k0 = f2mul(d0, R360_F2(K)), k1 = f2mul(d1, R360_F2(K)), k2 = f2mul(d2, R360_F2(K));
-    float2 gx0 = r360_hsel(f2add(r1, r0), k1, k0);                           // {Dx, Ix} of pixel 0
-    float2 gx1 = r360_hsel(f2add(r2, r1), k2, k1);
-    const float2 chk = f2add(f2add(gx0, gx1), f2add(gy0, gy1));              // Inf / NaN if any term is
-    if (!(fabsf(chk.x) < INFINITY) | !(fabsf(chk.y) < INFINITY)) {           // rare: the scalar IEEE operators, out of line
-        const float2 ix = r360_hgrad2_scalar(v.y, v.w, wv.y, v.w, e.y, v.y), dx = r360_hgrad2_scalar(v.x, v.z, wv.x, v.z, e.x, v.x);
-        const float2 iy = r360_hgrad2_scalar(v.y, d.y, u.y, v.w, d.w, u.w), dy = r360_hgrad2_scalar(v.x, d.x, u.x, v.z, d.z, u.z);
-        gx0 = make_float2(dx.x, ix.x); gx1 = make_float2(dx.y, ix.y);
-        gy0 = make_float2(dy.x, iy.x); gy1 = make_float2(dy.y, iy.y);
-    }
-    bool z0 = !(r > 0 && r < rows - 1) || c == 0, z1 = !(r > 0 && r < rows - 1) || c + 2 == cols;     // image border
-    if (mg.ws > 0) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int cc = c + p, k0i = mg.magic ? (int)__umulhi((unsigned)cc, mg.magic) : cc, rem = cc - k0i * mg.ws;
-            const bool masked = (rem == 0 && k0i >= 1 && k0i <= mg.n_sensors - 1) || (rem == mg.ws - 1 && k0i + 1 <= mg.n_sensors - 1);
-            if (p == 0) z0 |= masked; else z1 |= masked;
-        }
-    }
-    if (z0) { gx0 = make_float2(0.f, 0.f); gy0 = gx0; }
-    if (z1) { gx1 = make_float2(0.f, 0.f); gy1 = gx1; }
-    out[0] = make_float4(v.y, v.x, gx0.y, gy0.y);
-    out[1] = make_float4(gx0.x, gy0.x, v.w, v.z);
-    out[2] = make_float4(gx1.y, gy1.y, gx1.x, gy1.x);
-}
 static inline R360MaskGeom r360_mask_geom(int cols, int n_sensors) {
     R360MaskGeom mg;
     mg.n_sensors = n_sensors;
@@ -325,24 +273,12 @@ k_texel(float2* const* __restrict__ pyr, float* const* __restrict__ trg, long lo
 #define R360_F0_SW (R360_F0_TW + 8)            // smem columns: global x = tx0 - 4 + sx
 #define R360_F0_SH (R360_F0_TH + 4)            // smem rows:    global y = ty0 - 2 + sy
 #define R360_F0_ROWB (R360_F0_SW * 8)          // bytes per smem row
-#ifdef R360_F0_STAGE
-#define R360_F0_DYN_SMEM (8 * 96 * 16)         // staging rows of the 8 warps (variant build)
-#else
-#define R360_F0_DYN_SMEM 0
-#endif
 __device__ __forceinline__ int r360_reflect101_clamped(int i, int n) {
     i = r360_reflect101(i, n);
     return min(max(i, 0), n - 1);               // partial tiles reach far outside; those values are never used
 }
 __device__ __forceinline__ float r360_gray_u8(unsigned r, unsigned g, unsigned b) {
     const int v = (int)(r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15;
-    return (float)v * (float)(1. / 255);
-}
-// r * 9798 + g * 19235 + b * 3735 of the three bytes of `px` starting at bit `sh` (0 or 8), as hi * 256 + lo byte dot products.
-__device__ __forceinline__ float r360_gray_dp4a(unsigned px, int sh) {
-    const unsigned WL = 0x00972346u << sh, WH = 0x000e4b26u << sh;            // low / high bytes of {9798, 19235, 3735}
-    const unsigned lo = __dp4a(px, WL, 16384u), hi = __dp4a(px, WH, 0u);
-    const int v = (int)(hi * 256u + lo) >> 15;
     return (float)v * (float)(1. / 255);
 }
 __device__ __forceinline__ float2 r360_lds64(unsigned smem) {
@@ -436,9 +372,6 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
     constexpr bool F32DEPTH = IN == 1;
     constexpr bool SCALED = IN != 0;                                             // see r360_texel_pair_colz
     __shared__ __align__(16) float2 s_dg[R360_F0_SH][R360_F0_SW];
-#ifdef R360_F0_STAGE
-    extern __shared__ __align__(16) float4 s_stage[];                            // [8][96] per warp: the texels of one pair row (32 x 48 B)
-#endif
     const int f = blockIdx.y;
     const int ty0 = (blockIdx.x / tiles_x) * R360_F0_TH, tx0 = (blockIdx.x % tiles_x) * R360_F0_TW;
     const size_t n_px = (size_t)rows * cols;
@@ -499,19 +432,10 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
                 for (int k = 0; k < NIT; ++k) {
                     if (tr + RPP * k < R360_F0_SH) {
                         float d[4], g[4];
-#ifdef R360_GRAY_DP4A
-                        // the same integer sum as r360_gray_u8 as two byte dot products (weights split into high and low
-                        // bytes): no byte extraction for pixels 0 and 3, one permute for pixels 1 and 2
-                        g[0] = r360_gray_dp4a(w0[k], 0);
-                        g[1] = r360_gray_dp4a(__byte_perm(w0[k], w1[k], 0x0543), 0);
-                        g[2] = r360_gray_dp4a(__byte_perm(w1[k], w2[k], 0x0432), 0);
-                        g[3] = r360_gray_dp4a(w2[k], 8);
-#else
                         g[0] = r360_gray_u8(w0[k] & 0xffu, (w0[k] >> 8) & 0xffu, (w0[k] >> 16) & 0xffu);
                         g[1] = r360_gray_u8(w0[k] >> 24, w1[k] & 0xffu, (w1[k] >> 8) & 0xffu);
                         g[2] = r360_gray_u8((w1[k] >> 16) & 0xffu, w1[k] >> 24, w2[k] & 0xffu);
                         g[3] = r360_gray_u8((w2[k] >> 8) & 0xffu, (w2[k] >> 16) & 0xffu, w2[k] >> 24);
-#endif
                         if (F32DEPTH) {
                             d[0] = __uint_as_float(dw[k][0]); d[1] = __uint_as_float(dw[k][1]);
                             d[2] = __uint_as_float(dw[k][F32DEPTH ? 2 : 0]); d[3] = __uint_as_float(dw[k][F32DEPTH ? 3 : 1]);
@@ -570,10 +494,6 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
                 R360ColState st;
                 r360_col_state_init_t<SCALED>(st, u, v);
                 const bool zc0 = (c == 0) | r360_joint_column(c, mg), zc1 = (c + 2 == cols) | r360_joint_column(c + 1, mg);
-#ifdef R360_F0_STAGE
-                const bool full_warp = tx0 + R360_F0_TW <= cols;                  // every lane of the warp has a pair (uniform over the CTA)
-                const unsigned stg = r360_smem_addr(&s_stage[(threadIdx.x / 32) * 96]);
-#endif
                 auto strip = [&](auto with_l0) {                                 // a frame with both roles also gets its plane
 #pragma unroll
                     for (int k = 0; k < STRIP; ++k) {
@@ -584,22 +504,8 @@ k_pyr_head(const uint8_t* __restrict__ rgb, const uint16_t* __restrict__ depth_m
                         const bool rb = (unsigned)(r0 + k - 1) >= (unsigned)(rows - 2);      // first / last image row
                         float4 t[3];
                         r360_texel_pair_colz<SCALED>(st, v, u, d, wv, e, zc0 | rb, zc1 | rb, t);
-#ifdef R360_F0_STAGE
-                        // the pair's 48 bytes leave the warp as three 512-byte rows instead of 32 strided pieces per store:
-                        // 12 cache lines per pair row instead of 36
-                        if (full_warp) {
-                            r360_sts128(stg + lp * 48, t[0]); r360_sts128(stg + lp * 48 + 16, t[1]); r360_sts128(stg + lp * 48 + 32, t[2]);
-                            __syncwarp();
-                            const float4 a0 = r360_lds128(stg + lp * 16), a1 = r360_lds128(stg + 512 + lp * 16), a2 = r360_lds128(stg + 1024 + lp * 16);
-                            __syncwarp();
-                            float4* o = tex + 3 * (size_t)(po - lp) + lp;
-                            o[0] = a0; o[32] = a1; o[64] = a2;
-                        } else
-#endif
-                        {
-                            float4* o = tex + 3 * (size_t)po;
-                            o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
-                        }
+                        float4* o = tex + 3 * (size_t)po;
+                        o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
                         u = v; v = d; po += half;
                     }
                 };
@@ -1338,10 +1244,10 @@ void r360_launch_pyr_head(cudaStream_t st, const uint8_t* rgb, const uint16_t* d
     const int tiles_x = (cols + R360_F0_TW - 1) / R360_F0_TW, tiles_y = (rows + R360_F0_TH - 1) / R360_F0_TH;
     dim3 grid(tiles_x * tiles_y, n_frames);
     if (depth_mm)
-        k_pyr_head<0><<<grid, 256, R360_F0_DYN_SMEM, st>>>(rgb, depth_mm, depth_m, nullptr, 0, l0_dst, l1_dst, 0, texel_dst, 0, rows, cols,
+        k_pyr_head<0><<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, nullptr, 0, l0_dst, l1_dst, 0, texel_dst, 0, rows, cols,
                                                            tiles_x, min_d, max_d, r360_mask_geom(cols, n_sensors));
     else
-        k_pyr_head<1><<<grid, 256, R360_F0_DYN_SMEM, st>>>(rgb, depth_mm, depth_m, nullptr, 0, l0_dst, l1_dst, 0, texel_dst, 0, rows, cols,
+        k_pyr_head<1><<<grid, 256, 0, st>>>(rgb, depth_mm, depth_m, nullptr, 0, l0_dst, l1_dst, 0, texel_dst, 0, rows, cols,
                                                            tiles_x, min_d, max_d, r360_mask_geom(cols, n_sensors));
 }
 // Level l >= 1 of every frame of a chunk in one read of its plane: the level's target texels (frames whose entry of
@@ -1350,7 +1256,7 @@ void r360_launch_pyr_mid(cudaStream_t st, float2* const* pyr, float* const* tex,
                          float min_d, float max_d, int n_sensors, int n_frames) {
     const int tiles_x = (cols + R360_F0_TW - 1) / R360_F0_TW, tiles_y = (rows + R360_F0_TH - 1) / R360_F0_TH;
     dim3 grid(tiles_x * tiles_y, n_frames);
-    k_pyr_head<R360_IN_PLANE><<<grid, 256, R360_F0_DYN_SMEM, st>>>(nullptr, nullptr, nullptr, pyr, off, nullptr, off_next >= 0 ? pyr : nullptr,
+    k_pyr_head<R360_IN_PLANE><<<grid, 256, 0, st>>>(nullptr, nullptr, nullptr, pyr, off, nullptr, off_next >= 0 ? pyr : nullptr,
                                                                    off_next >= 0 ? off_next : 0, tex, off * R360_TEXEL_FLOATS, rows, cols, tiles_x,
                                                                    min_d, max_d, r360_mask_geom(cols, n_sensors));
 }
@@ -1361,11 +1267,6 @@ static cudaError_t r360_pass_attr() {
 }
 cudaError_t r360_pass_init() {
     cudaError_t e = r360_pass_attr<R360_PHOTO_CONSISTENCY, true>();
-#ifdef R360_F0_STAGE
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pyr_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_F0_DYN_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pyr_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_F0_DYN_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pyr_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, R360_F0_DYN_SMEM);
-#endif
     if (e == cudaSuccess) e = r360_pass_attr<R360_DEPTH_CONSISTENCY, true>();
     if (e == cudaSuccess) e = r360_pass_attr<R360_PHOTO_DEPTH, true>();
     if (e == cudaSuccess) e = r360_pass_attr<R360_PHOTO_CONSISTENCY, false>();
