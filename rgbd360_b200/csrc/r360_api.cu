@@ -53,6 +53,7 @@ struct Ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_copy[kStages]{}, ev_done[kStages]{};
     int chunk = kChunkFrames;                    // frames per chunk = min(kChunkFrames, max_frames)
+    bool pin_packed = true;                      // R360_PIN_PACKED=0: the scalar one-pixel-per-thread pinhole evaluation (A/B measurements)
     bool use_pyr_mid = true;                     // R360_PYR_MID=0: k_down + k_texel for the levels >= 1 (A/B measurements)
     bool use_pyr_head = true;                    // R360_PYR_HEAD=0 in the environment: the separate level-0 kernels (A/B measurements)
     long long n_chunks_done = 0;                 // staging-buffer rotation across calls
@@ -411,7 +412,7 @@ R360PinLevel pin_level(const Ctx* c, int level) {
 
 void launch_evaluation(Ctx* c, const R360PassArgs& a, int n_pairs, int level) {
     if (c->P.projection == R360_PINHOLE) {
-        r360_launch_pin_eval(c->st, a, pin_level(c, level), n_pairs, c->sm_count);
+        r360_launch_pin_eval(c->st, a, pin_level(c, level), n_pairs, c->sm_count, c->pin_packed);
         ++c->launches;
     } else if (c->P.occlusion == 0) {
         r360_launch_pass(c->st, a, c->pass_grid);
@@ -605,6 +606,7 @@ static int create_impl(r360_ctx* c, int device, int rows, int cols, int max_fram
     CK(c, cudaMallocHost(&c->h_tex, sizeof(void*) * max_frames)); CK(c, cudaMalloc(&c->d_tex, sizeof(void*) * max_frames));
     if (const char* e = getenv("R360_PYR_HEAD")) c->use_pyr_head = atoi(e) != 0;
     if (const char* e = getenv("R360_PYR_MID")) c->use_pyr_mid = atoi(e) != 0;
+    if (const char* e = getenv("R360_PIN_PACKED")) c->pin_packed = atoi(e) != 0;
 
     const int np = max_pairs + 1;     // + 1 spare slot for the eval hooks
     CK(c, cudaMalloc(&c->d_pairs, sizeof(R360Pair) * np));

@@ -95,7 +95,7 @@ cudaError_t r360_occ_init();
 void r360_launch_occ_pass(cudaStream_t st, const R360PassArgs& a, int n_pairs, int* head, int* next, float* dinv,
                           int sm_count);
 // pinhole registration (r360_pinhole.cuh)
-void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count);
+void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count, bool packed = true);
 void r360_launch_gn_step_pin(cudaStream_t st, const R360GnArgs& g, int level);
 // the 8-sensor rig (r360_pinhole.cuh)
 void r360_launch_rig_eval(cudaStream_t st, const R360PassArgs& a, const R360RigArgs& rig, int n_pairs, int sm_count);

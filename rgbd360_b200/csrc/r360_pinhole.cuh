@@ -8,7 +8,8 @@
 // Same pyramids and texel layout as the spherical path (built without the sensor-joint mask).  The
 // index maps are bit-exact by construction: the projection is evaluated with the reference's own
 // operation sequence -- including its double-precision 1 / z narrowed to float (RPI.h:659) -- and the
-// file is compiled with --fmad=false.  Not a throughput path: one pixel per thread, direct gathers.
+// file is compiled with --fmad=false.  k_pin_eval: one pixel per thread (the plain statement, R360_PIN_PACKED=0);
+// k_pin_eval2: two pixels per thread in packed fp32x2 (the default).  Both gather directly.
 #pragma once
 
 #define R360_PIN_THREADS 256
@@ -145,6 +146,168 @@ k_pin_eval(R360PassArgs a, R360PinLevel pl) {
     }
 }
 
+// The same evaluation, two horizontally adjacent pixels per thread in packed fp32x2 (the formulation of k_pass): the
+// projection is the reference's operation sequence on both pixels at once -- every product and sum of R X + t and of the
+// projection rounded separately (f2add_sep), the reciprocal of z still formed in DOUBLE and narrowed (RPI.h:659), the
+// rounding to the nearest texel by the 1.5 * 2^23 trick with the scalar function on exact ties and out-of-range values -- so
+// the index maps and the counters are those of k_pin_eval bit for bit; residuals, weights and Jacobian rows use fused
+// multiply-adds like the spherical kernel (sums within float rounding of the scalar kernel's).  Both pixels' six texel
+// gathers are issued together; 28 FFMA2 per residual row pair.
+template <int METHOD>
+__global__ void __launch_bounds__(R360_PIN_THREADS, 2)
+k_pin_eval2(R360PassArgs a, R360PinLevel pl) {
+    __shared__ float s_red[R360_PIN_THREADS / 32][R360_ACC_DOUBLES + 1];
+    __shared__ int s_cnt[R360_PIN_THREADS / 32][R360_ACC_INTS];
+    const int ap = blockIdx.y;
+    if (ap >= *a.n_active) return;
+    const R360Level lv = a.lv;
+    const r360_params P = a.params;
+    const int pair = a.active_list[ap];
+    const R360Pair* ps = a.pairs + pair;
+    float T[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) T[k] = ps->pose_eval[k];
+    const float4* __restrict__ src4 = reinterpret_cast<const float4*>(a.src_base[pair] + lv.px_off);
+    const float2* __restrict__ trg = reinterpret_cast<const float2*>(a.trg_base[pair] + lv.px_off * R360_TEXEL_FLOATS);
+    const float one = a.one;
+
+    R360Acc2 A;
+    r360_acc_zero(A);
+    float2 sumP = make_float2(0.f, 0.f), sumD = sumP;
+    int n_vis = 0, n_photo = 0, n_depth = 0;
+    const int n2 = lv.n >> 1;                                               // cols is even at every level: pixel pairs never straddle rows
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += gridDim.x * blockDim.x) {
+        const int i = 2 * q;
+        const int r = (int)(((unsigned long long)i * lv.div_magic) >> 40), c = i - r * lv.cols;
+        const float4 s = __ldg(&src4[q]);                                   // {d0, g0, d1, g1}
+        const bool v0 = (P.min_depth < s.x) & (s.x < P.max_depth), v1 = (P.min_depth < s.z) & (s.z < P.max_depth);   // RPI.h:4293-4299
+        if (!(v0 | v1)) continue;
+        const float2 z = make_float2(v0 ? s.x : 1.f, v1 ? s.z : 1.f);       // invalid lanes stay finite
+        const float2 cf = make_float2((float)c - pl.ox, (float)(c + 1) - pl.ox);
+        const float rf = (float)r - pl.oy;
+        const float2 X = f2mul(f2mul(cf, z), R360_F2(pl.inv_fx));           // RPI.h:4295
+        const float2 Y = f2mul(f2mul(R360_F2(rf), z), R360_F2(pl.inv_fy));
+        const float2 px = f2add(f2add_sep(f2add_sep(f2mul(X, R360_F2(T[0])), one, f2mul(Y, R360_F2(T[4]))), one, f2mul(z, R360_F2(T[8]))), R360_F2(T[12]));
+        const float2 py = f2add(f2add_sep(f2add_sep(f2mul(X, R360_F2(T[1])), one, f2mul(Y, R360_F2(T[5]))), one, f2mul(z, R360_F2(T[9]))), R360_F2(T[13]));
+        const float2 pz = f2add(f2add_sep(f2add_sep(f2mul(X, R360_F2(T[2])), one, f2mul(Y, R360_F2(T[6]))), one, f2mul(z, R360_F2(T[10]))), R360_F2(T[14]));
+        const float2 iz = make_float2((float)(1.0 / (double)pz.x), (float)(1.0 / (double)pz.y));     // RPI.h:659
+        const float2 tc = f2add_sep(f2mul(f2mul(px, R360_F2(pl.fx)), iz), one, R360_F2(pl.ox));      // RPI.h:662
+        const float2 tr = f2add_sep(f2mul(f2mul(py, R360_F2(pl.fy)), iz), one, R360_F2(pl.oy));
+        // round half away from zero == round to nearest except on exact ties; nearest via 1.5 * 2^23, exact for |v| < 2^22
+        const float M = 12582912.0f;
+        const float2 mr = f2add_sep(tr, one, R360_F2(M)), mc = f2add_sep(tc, one, R360_F2(M));
+        const float2 dr = f2add(tr, f2add(R360_F2(M), f2neg(mr))), dc = f2add(tc, f2add(R360_F2(M), f2neg(mc)));
+        int ri0 = __float_as_int(mr.x) - 0x4B400000, ri1 = __float_as_int(mr.y) - 0x4B400000;
+        int ci0 = __float_as_int(mc.x) - 0x4B400000, ci1 = __float_as_int(mc.y) - 0x4B400000;
+        const bool e0 = !((fmaxf(fabsf(dr.x), fabsf(dc.x)) < 0.5f) & (fmaxf(fabsf(tr.x), fabsf(tc.x)) < 4194304.f));
+        const bool e1 = !((fmaxf(fabsf(dr.y), fabsf(dc.y)) < 0.5f) & (fmaxf(fabsf(tr.y), fabsf(tc.y)) < 4194304.f));
+        if (e0) { ri0 = r360_round_to_int_dev(tr.x); ci0 = r360_round_to_int_dev(tc.x); }            // ties, huge values, NaN: the scalar rule
+        if (e1) { ri1 = r360_round_to_int_dev(tr.y); ci1 = r360_round_to_int_dev(tc.y); }
+        const bool ok0 = v0 & ((unsigned)ri0 < (unsigned)lv.rows) & ((unsigned)ci0 < (unsigned)lv.cols);   // RPI.h:667-668
+        const bool ok1 = v1 & ((unsigned)ri1 < (unsigned)lv.rows) & ((unsigned)ci1 < (unsigned)lv.cols);
+        if (!(ok0 | ok1)) continue;
+        const float2* ta = trg + 3u * (ok0 ? (unsigned)(ri0 * lv.cols + ci0) : 0u);
+        const float2* tb = trg + 3u * (ok1 ? (unsigned)(ri1 * lv.cols + ci1) : 0u);
+        const float2 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2);     // {gray, depth}, {Ix, Iy}, {Dx, Dy}
+        const float2 b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2);
+        const bool fin0 = ok0 & (fabsf(a0.y) < INFINITY), fin1 = ok1 & (fabsf(b0.y) < INFINITY);
+        // weighted residuals (shared by the error and the Hessian rows)
+        float2 rp = make_float2(0.f, 0.f), wp = rp, rd = rp, wd = rp;
+        if (METHOD != R360_DEPTH_CONSISTENCY) {
+            const float2 e = make_float2(a0.x - s.y, b0.x - s.w);
+            float w0 = a.inv_std_photo, w1 = a.inv_std_photo;
+            if (!(fabsf(e.x) < P.std_photo)) { const float u = r360_rcp_fast(fabsf(e.x)); w0 = r360_sqrt_fast(u * (2.f * a.inv_std_photo - u)); }
+            if (!(fabsf(e.y) < P.std_photo)) { const float u = r360_rcp_fast(fabsf(e.y)); w1 = r360_sqrt_fast(u * (2.f * a.inv_std_photo - u)); }
+            wp = make_float2(ok0 ? w0 : 0.f, ok1 ? w1 : 0.f);
+            rp = f2mul(wp, e);
+            sumP = f2fma(rp, rp, sumP);                                     // errorPhotoICP: no saliency test (RPI.h:669-703)
+            r360_count(n_photo, ok0); r360_count(n_photo, ok1);
+        }
+        if (METHOD != R360_PHOTO_CONSISTENCY) {
+            const float2 D = make_float2(fin0 ? a0.y : 1.f, fin1 ? b0.y : 1.f);
+            const float2 f = f2add(D, f2neg(pz));
+            const float2 sd = f2mul(R360_F2(P.std_depth), pz);              // RPI.h:694: transformed SOURCE depth
+            float w0 = r360_rcp_fast(sd.x), w1 = r360_rcp_fast(sd.y);
+            if (!(fabsf(f.x) < sd.x)) { const float u = r360_rcp_fast(fabsf(f.x)); w0 = r360_sqrt_fast(u * (2.f * w0 - u)); }
+            if (!(fabsf(f.y) < sd.y)) { const float u = r360_rcp_fast(fabsf(f.y)); w1 = r360_sqrt_fast(u * (2.f * w1 - u)); }
+            wd = make_float2(fin0 ? w0 : 0.f, fin1 ? w1 : 0.f);
+            rd = f2mul(wd, f);
+            sumD = f2fma(rd, rd, sumD);
+            r360_count(n_depth, fin0); r360_count(n_depth, fin1);
+        }
+        r360_count(n_vis, ok0); r360_count(n_vis, ok1);
+        // ---- calcHessGrad (RPI.h:967-1085): both saliency `continue`s drop the whole pixel
+        bool h0 = ok0, h1 = ok1;
+        if (METHOD != R360_DEPTH_CONSISTENCY) {
+            h0 = h0 & !((fabsf(a1.x) < P.thres_sal_int) & (fabsf(a1.y) < P.thres_sal_int));
+            h1 = h1 & !((fabsf(b1.x) < P.thres_sal_int) & (fabsf(b1.y) < P.thres_sal_int));
+        }
+        if (METHOD != R360_PHOTO_CONSISTENCY) {
+            h0 = h0 & !((fabsf(a2.x) < P.thres_sal_depth) & (fabsf(a2.y) < P.thres_sal_depth));
+            h1 = h1 & !((fabsf(b2.x) < P.thres_sal_depth) & (fabsf(b2.y) < P.thres_sal_depth));
+        }
+        if (!(h0 | h1)) continue;
+        const float2 iz2 = f2mul(iz, iz);
+        const float2 fxz = f2mul(R360_F2(pl.fx), iz), fyz = f2mul(R360_F2(pl.fy), iz);
+        const float2 fxz2 = f2mul(R360_F2(pl.fx), iz2), fyz2 = f2mul(R360_F2(pl.fy), iz2);
+        // jacobianWarpRt, RPI.h:970-984 (rows J0 = d col, J1 = d row)
+        const float2 J02 = f2neg(f2mul(fxz2, px)), J12 = f2neg(f2mul(fyz2, py));
+        const float2 J03 = f2mul(J02, py), J13 = f2neg(f2fma(f2mul(fyz2, py), py, R360_F2(pl.fy)));
+        const float2 J04 = f2fma(f2mul(fxz2, px), px, R360_F2(pl.fx)), J14 = f2mul(f2mul(fyz2, px), py);
+        const float2 J05 = f2neg(f2mul(fxz, py)), J15 = f2mul(fyz, px);
+        float2 J[6];
+        if (METHOD != R360_DEPTH_CONSISTENCY) {
+            const float2 w = make_float2(h0 ? wp.x : 0.f, h1 ? wp.y : 0.f);     // selects, not products: a dropped pixel adds exact zeros whatever its weight
+            const float2 ga = f2mul(w, make_float2(a1.x, b1.x)), gb = f2mul(w, make_float2(a1.y, b1.y));
+            J[0] = f2mul(ga, fxz); J[1] = f2mul(gb, fyz);
+            J[2] = f2fma(ga, J02, f2mul(gb, J12)); J[3] = f2fma(ga, J03, f2mul(gb, J13));
+            J[4] = f2fma(ga, J04, f2mul(gb, J14)); J[5] = f2fma(ga, J05, f2mul(gb, J15));
+            r360_accumulate(A, J, make_float2(h0 ? rp.x : 0.f, h1 ? rp.y : 0.f));
+        }
+        if (METHOD != R360_PHOTO_CONSISTENCY) {
+            const float2 w = make_float2(h0 ? wd.x : 0.f, h1 ? wd.y : 0.f);     // 0 where the depth is not finite
+            const float2 ga = f2mul(w, make_float2(a2.x, b2.x)), gb = f2mul(w, make_float2(a2.y, b2.y));
+            // w ((Dx J0 + Dy J1) - jacobianRt_z),  jacobianRt_z = [0, 0, 1, py, -px, 0]   (RPI.h:1053)
+            J[0] = f2mul(ga, fxz); J[1] = f2mul(gb, fyz);
+            J[2] = f2add(f2fma(ga, J02, f2mul(gb, J12)), f2neg(w));
+            J[3] = f2fma(f2neg(w), py, f2fma(ga, J03, f2mul(gb, J13)));
+            J[4] = f2fma(w, px, f2fma(ga, J04, f2mul(gb, J14)));
+            J[5] = f2fma(ga, J05, f2mul(gb, J15));
+            r360_accumulate(A, J, make_float2(h0 ? rd.x : 0.f, h1 ? rd.y : 0.f));
+        }
+    }
+
+    // ---- block reduction (as k_pin_eval): 27 normal-equation sums + PhotoResidual + DepthResidual, 3 counters
+    float acc[R360_ACC_DOUBLES + 1];
+    r360_acc_unpack(A, acc);                                                // fills 0..27 (27 = A.e2, unused here)
+    acc[27] = sumP.x + sumP.y;
+    acc[28] = sumD.x + sumD.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < R360_ACC_DOUBLES + 1; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) s_red[wid][k] = v;
+    }
+    n_vis = __reduce_add_sync(0xffffffffu, n_vis);
+    n_photo = __reduce_add_sync(0xffffffffu, n_photo);
+    n_depth = __reduce_add_sync(0xffffffffu, n_depth);
+    if (lane == 0) { s_cnt[wid][0] = n_vis; s_cnt[wid][1] = n_photo; s_cnt[wid][2] = n_depth; s_cnt[wid][3] = 0; }
+    __syncthreads();
+    if (threadIdx.x < R360_ACC_DOUBLES + 1) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < R360_PIN_THREADS / 32; ++k) sum += (double)s_red[k][threadIdx.x];
+        r360_fx_add(a.acc + (size_t)pair * R360_ACC_STRIDE, threadIdx.x, sum);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + R360_ACC_INTS) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < R360_PIN_THREADS / 32; ++k) sum += s_cnt[k][threadIdx.x - 32];
+        atomicAdd(&a.cnt[(size_t)pair * R360_ACC_INTS + threadIdx.x - 32], sum);
+    }
+}
+
 // exp(update) * pose_estim with the FULL exponential (CPose3D::exp(v), RPI.h:4375)
 __device__ void r360_pin_candidate(R360Pair* ps, const float upd[6]) {
     double ud[6], Td[16];
@@ -162,7 +325,8 @@ __device__ void r360_pin_candidate(R360Pair* ps, const float upd[6]) {
 __global__ void k_gn_step_pin(R360GnArgs g, int level) {
     const r360_params P = g.params;
     const int per_level = 2 * P.max_iters + 2;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
+    if (*g.n_active == 0) return;                                // every pair has left the level: the rest of its schedule is empty
+    for (int p = threadIdx.x == 0 ? (int)blockIdx.x : g.n_pairs; p < g.n_pairs; p += gridDim.x) {   // one pair per warp, as k_gn_step
         R360Pair* ps = g.pairs + p;
         if (!ps->active) continue;
         double acc[R360_ACC_DOUBLES + 1];
@@ -455,7 +619,8 @@ __device__ void r360_rig_candidate(R360Pair* ps, float* cand) {
 // are bit-reproducible, so diff_error is exactly 0, the candidate is never taken and every level runs one loop body.
 __global__ void k_gn_step_rig(R360GnArgs g, int level) {
     const r360_params P = g.params;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.n_pairs; p += gridDim.x * blockDim.x) {
+    if (*g.n_active == 0) return;                                // every pair has left the level: the rest of its schedule is empty
+    for (int p = threadIdx.x == 0 ? (int)blockIdx.x : g.n_pairs; p < g.n_pairs; p += gridDim.x) {   // one pair per warp, as k_gn_step
         R360Pair* ps = g.pairs + p;
         if (!ps->active) continue;
         double acc[R360_ACC_DOUBLES + 1];
@@ -537,16 +702,24 @@ void r360_launch_rig_eval(cudaStream_t st, const R360PassArgs& a, const R360RigA
     k_rig_eval<<<grid, R360_PIN_THREADS, 0, st>>>(a, rig);
 }
 void r360_launch_gn_step_rig(cudaStream_t st, const R360GnArgs& g, int level) {
-    k_gn_step_rig<<<r360_blocks(g.n_pairs, 32, 1024), 32, 0, st>>>(g, level);
+    k_gn_step_rig<<<r360_blocks(g.n_pairs, 1, 1024), 32, 0, st>>>(g, level);
 }
 
-void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count) {
+void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count, bool packed) {
     long long blocks = ((long long)a.lv.n + R360_PIN_THREADS - 1) / R360_PIN_THREADS;
     long long cap = 8LL * sm_count / (n_pairs > 0 ? n_pairs : 1);
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const dim3 grid((unsigned)blocks, (unsigned)n_pairs);
+    if (packed && (a.lv.cols & 1) == 0) {
+        switch (a.params.method) {
+            case R360_PHOTO_CONSISTENCY: k_pin_eval2<R360_PHOTO_CONSISTENCY><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
+            case R360_DEPTH_CONSISTENCY: k_pin_eval2<R360_DEPTH_CONSISTENCY><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
+            default: k_pin_eval2<R360_PHOTO_DEPTH><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
+        }
+        return;
+    }
     switch (a.params.method) {
         case R360_PHOTO_CONSISTENCY: k_pin_eval<R360_PHOTO_CONSISTENCY><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
         case R360_DEPTH_CONSISTENCY: k_pin_eval<R360_DEPTH_CONSISTENCY><<<grid, R360_PIN_THREADS, 0, st>>>(a, pl); break;
@@ -554,5 +727,5 @@ void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinL
     }
 }
 void r360_launch_gn_step_pin(cudaStream_t st, const R360GnArgs& g, int level) {
-    k_gn_step_pin<<<r360_blocks(g.n_pairs, 32, 1024), 32, 0, st>>>(g, level);
+    k_gn_step_pin<<<r360_blocks(g.n_pairs, 1, 1024), 32, 0, st>>>(g, level);
 }
