@@ -13,6 +13,9 @@
 #pragma once
 
 #define R360_PIN_THREADS 256
+#ifndef R360_PIN_CAP
+#define R360_PIN_CAP 16                       // blocks per pair so that the grid is <= 16 CTAs per SM (8: 7.33 ms, 16: 6.37 ms, 32: 6.78 ms per 256-pair batch)
+#endif
 
 template <int METHOD>
 __global__ void __launch_bounds__(R360_PIN_THREADS)
@@ -694,7 +697,7 @@ __global__ void k_gn_step_rig(R360GnArgs g, int level) {
 
 void r360_launch_rig_eval(cudaStream_t st, const R360PassArgs& a, const R360RigArgs& rig, int n_pairs, int sm_count) {
     long long blocks = ((long long)a.lv.n + R360_PIN_THREADS - 1) / R360_PIN_THREADS;
-    long long cap = 8LL * sm_count / (8LL * (n_pairs > 0 ? n_pairs : 1));
+    long long cap = (long long)R360_PIN_CAP * sm_count / (8LL * (n_pairs > 0 ? n_pairs : 1));
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -707,9 +710,6 @@ void r360_launch_gn_step_rig(cudaStream_t st, const R360GnArgs& g, int level) {
 
 void r360_launch_pin_eval(cudaStream_t st, const R360PassArgs& a, const R360PinLevel& pl, int n_pairs, int sm_count, bool packed) {
     long long blocks = ((long long)a.lv.n + R360_PIN_THREADS - 1) / R360_PIN_THREADS;
-#ifndef R360_PIN_CAP
-#define R360_PIN_CAP 16                       // blocks per pair so that the grid is <= 16 CTAs per SM (8: 7.33 ms, 16: 6.37 ms, 32: 6.78 ms per 256-pair batch)
-#endif
     long long cap = (long long)R360_PIN_CAP * sm_count / (n_pairs > 0 ? n_pairs : 1);
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
