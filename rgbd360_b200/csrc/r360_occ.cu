@@ -115,14 +115,15 @@ k_occ_scatter(R360PassArgs a, int* __restrict__ head, int* __restrict__ next, fl
         s_nxt = r360_occ_src(src4, i + stride, lv.n);           // in flight across this iteration's atomics
         OccPixelPair o;
         r360_occ_pixel_pair<OCC, OCC == 2 ? 1 : 0>(a, lv, P, T, ps->pose_eval, s_cur, trg, i, o);
-        if (r360_occ_candidate<OCC>(o.inb[0], o.ta[0].y, o.g.dist.x)) {
-            dv[i] = o.g.dinv.x;
-            nx[i] = atomicExch(&hd[o.ii[0]], i);
-        }
-        if (r360_occ_candidate<OCC>(o.inb[1], o.tb[0].y, o.g.dist.y)) {
-            dv[i + 1] = o.g.dinv.y;
-            nx[i + 1] = atomicExch(&hd[o.ii[1]], i + 1);
-        }
+        // both exchanges are issued before either result is stored: two round trips to L2 in flight instead of one after
+        // the other (same thread, so two candidates of one texel still enter its list in pixel order)
+        const bool c0 = r360_occ_candidate<OCC>(o.inb[0], o.ta[0].y, o.g.dist.x);
+        const bool c1 = r360_occ_candidate<OCC>(o.inb[1], o.tb[0].y, o.g.dist.y);
+        int p0 = -1, p1 = -1;
+        if (c0) p0 = atomicExch(&hd[o.ii[0]], i);
+        if (c1) p1 = atomicExch(&hd[o.ii[1]], i + 1);
+        if (c0) { dv[i] = o.g.dinv.x; nx[i] = p0; }
+        if (c1) { dv[i + 1] = o.g.dinv.y; nx[i + 1] = p1; }
     }
 }
 
